@@ -1,0 +1,178 @@
+/* b200reg — B200-native scan-to-map registration engine, C ABI.
+ *
+ * Drop-in boundary for the hot path of matiable/pointcloud-slam.
+ * The reference has no C ABI of its own; each entry point below names the C++
+ * interface it replaces (paths relative to the reference's src/).  Thin C++
+ * adaptors that re-create those interfaces on top of this ABI live in
+ * pointcloud-slam_b200/host/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns int32 status: B200_OK, a positive "soft" status
+ *     (no effective points / not converged) or a negative error; nothing throws;
+ *   - handles are opaque; the caller owns every host buffer; device memory and
+ *     one CUDA stream belong to the handle; a handle is not re-entrant, distinct
+ *     handles may be used from different threads;
+ *   - point clouds are passed as (const float* xyz, n, stride_bytes): x,y,z are the
+ *     first three floats of each record (stride 48 = pcl::PointXYZINormal,
+ *     32/16 = PointXYZI, 12 = packed);
+ *   - there is no CPU fallback: without a CUDA device create() fails with
+ *     B200_ERR_CUDA.
+ */
+#ifndef B200REG_H_
+#define B200REG_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_NO_EFFECTIVE_POINTS 1 /* dyn_share.valid == false on every pass (laser_mapping.cc:657-661) */
+#define B200_NOT_CONVERGED 2       /* NDT: converged_ == false (NaN step, ndt_omp_impl.hpp:119-123) */
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_NOMEM (-3)
+#define B200_ERR_RANGE (-4)    /* coordinate outside the +-2^20-cell key range, or NDT grid too large */
+#define B200_ERR_CAPACITY (-5) /* voxel capacity reached (LRU eviction not implemented yet) */
+#define B200_ERR_NCCL (-6)
+
+const char* b200_version(void);
+const char* b200_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * B1 — local map.  Replaces jueying_lio::IVox<3, DEFAULT, PointType>
+ * (jueying_lio/include/ivox3d/ivox3d.h:53-88).
+ * ------------------------------------------------------------------------- */
+typedef struct b200_map b200_map;
+typedef struct {
+    float resolution;         /* IVox::Options::resolution_  (ivox3d.h:54) */
+    int32_t nearby;           /* NearbyType: 0 CENTER, 6, 18, 26 (ivox3d.h:46-51); other -> 18 (laser_mapping.cc:138-149) */
+    uint64_t capacity_voxels; /* IVox::Options::capacity_ (ivox3d.h:57) */
+    float max_range;          /* GetClosestPoint max_range, 5.0 (ivox3d.h:79) */
+    uint64_t max_points;      /* device point-pool size hint; 0 = 8M */
+} b200_map_params;
+
+/* IVox(Options) (ivox3d.h:64-67) */
+int32_t b200_map_create(const b200_map_params* params, int32_t device, b200_map** out);
+int32_t b200_map_destroy(b200_map* map);
+/* IVox::AddPoints(const PointVector&) (ivox3d.h:73, 256-281).  Insertion ordinals continue across calls. */
+int32_t b200_map_insert(b200_map* map, const float* xyz, int64_t n, int64_t stride_bytes);
+/* IVox::GetClosestPoint(pt, closest_pt, 5, max_range) (ivox3d.h:79, 132-204) for n query points.
+ * idx[n*5]: insertion ordinals ascending by (distance, stencil/in-voxel enumeration rank), -1 padded;
+ * sqdist[n*5] float squared distances; count[n]. */
+int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist,
+                      int32_t* count);
+/* IVox::NumValidGrids() (ivox3d.h:88) / NumPoints() (ivox3d.h:85) */
+int64_t b200_map_num_voxels(b200_map* map);
+int64_t b200_map_num_points(b200_map* map);
+
+/* ------------------------------------------------------------------------- *
+ * B2 — IEKF measurement update.  Replaces
+ *   esekfom::esekf::update_iterated_dyn_share_modified (IKFoM_toolkit/esekfom/esekfom.hpp:1526-1834)
+ *   driven with LaserMapping::ObsModel (jueying_lio/src/laser_mapping.cc:592-701),
+ *   and LaserMapping::MapIncremental (laser_mapping.cc:525-583).
+ * State vector x[26]: pos(3) rot(x,y,z,w) offset_R_L_I(x,y,z,w) offset_T_L_I(3) vel(3) bg(3) ba(3) grav(3)
+ * (use-ikfom.hpp:14-15, Eigen quaternion coefficient order).  P[23*23] row-major.
+ * ------------------------------------------------------------------------- */
+typedef struct b200_iekf b200_iekf;
+typedef struct {
+    int32_t max_iter;         /* NUM_MAX_ITERATIONS (laser_mapping.cc:89) */
+    float plane_thr;          /* ESTI_PLANE_THRESHOLD (laser_mapping.cc:90) */
+    int32_t extrinsic_est_en; /* laser_mapping.cc:687 */
+    double R;                 /* LASER_POINT_COV (options.h:12) */
+    double limit[23];         /* epsi (laser_mapping.cc:19) */
+    double filter_size_map;   /* filter_size_map_min_ (laser_mapping.cc:547) */
+} b200_iekf_params;
+
+#define B200_MAX_PASSES 8
+typedef struct {
+    int32_t status;
+    int32_t passes;     /* ObsModel evaluations */
+    int32_t knn_passes; /* of which searched the map (dyn_share.converge == true) */
+    int32_t converged;  /* t > 1 at exit */
+    int32_t n_eff[B200_MAX_PASSES];
+    int32_t knn[B200_MAX_PASSES];
+    float gpu_ms; /* device time of the whole update (CUDA events on the handle's stream) */
+} b200_iekf_stats;
+
+int32_t b200_iekf_create(const b200_iekf_params* params, b200_map* map, b200_iekf** out);
+int32_t b200_iekf_destroy(b200_iekf* ekf);
+/* kf_.update_iterated_dyn_share_modified(R, t) for one downsampled scan (laser_mapping.cc:335-351). */
+int32_t b200_iekf_update(b200_iekf* ekf, const float* scan_body_xyz, int64_t n, int64_t stride_bytes, double* x26,
+                         double* P23x23, b200_iekf_stats* stats);
+/* Same update with the scan already resident on the device (float4 per point: x,y,z,unused). */
+int32_t b200_iekf_update_device(b200_iekf* ekf, const void* d_scan_float4, int64_t n, double* x26, double* P23x23,
+                                b200_iekf_stats* stats);
+/* h_x^T h_x (12x12 row-major) and h_x^T h of pass `pass` of the last update (H/b parity, 1e-6 relative) */
+int32_t b200_iekf_last_HtH(b200_iekf* ekf, int32_t pass, double* HtH144, double* Hth12, double* x_in26);
+/* One ObsModel evaluation at state x with dyn_share.converge = converge (parity primitive). */
+int32_t b200_iekf_obs_model(b200_iekf* ekf, const float* scan_body_xyz, int64_t n, int64_t stride_bytes, const double* x26,
+                            int32_t converge, double* HtH144, double* Hth12, int32_t* n_eff);
+/* Per-point arrays after the last ObsModel evaluation: plane_coef_, residuals_, point_selected_surf_,
+ * nearest_points_ (as insertion ordinals) — any pointer may be NULL. */
+int32_t b200_iekf_point_state(b200_iekf* ekf, int64_t n, float* plane4, float* residual, uint8_t* selected, int32_t* nn_idx5,
+                              int32_t* nn_count);
+/* LaserMapping::MapIncremental() at state x using the neighbours cached by the last update. */
+int32_t b200_iekf_map_incremental(b200_iekf* ekf, const double* x26, int32_t ekf_inited, int32_t* n_added,
+                                  int32_t* n_no_downsample);
+
+/* ------------------------------------------------------------------------- *
+ * B3 — NDT registration.  Replaces pclomp::NormalDistributionsTransform
+ * (pointcloud_match/ndt_omp/include/pclomp/ndt_omp.h:117-261, ndt_omp_impl.hpp) and
+ * pclomp::VoxelGridCovariance (voxel_grid_covariance_omp_impl.hpp:49-442).
+ * 4x4 matrices are float[16] column-major (Eigen::Matrix4f layout).
+ * ------------------------------------------------------------------------- */
+typedef struct b200_ndt b200_ndt;
+typedef struct {
+    float resolution;     /* setResolution (ndt_omp.h:142) */
+    double step_size;     /* setStepSize */
+    double outlier_ratio; /* setOutlierRatio */
+    double trans_eps;     /* setTransformationEpsilon */
+    int32_t max_iter;     /* setMaximumIterations */
+    int32_t search;       /* 1 DIRECT1, 7 DIRECT7, 27 DIRECT26 (ndt_omp.h NeighborSearchMethod) */
+    int32_t min_pts;      /* min_points_per_voxel_ = 6 (voxel_grid_covariance_omp.h:210) */
+    double eig_ratio;     /* min_covar_eigvalue_mult_ = 0.01 (voxel_grid_covariance_omp.h:211) */
+} b200_ndt_params;
+typedef struct {
+    int32_t converged;
+    int32_t iters;      /* getFinalNumIteration */
+    int32_t evals;      /* computeDerivatives calls */
+    int32_t hess_evals; /* computeHessian calls */
+    double trans_probability; /* getTransformationProbability */
+    double hessian[36];
+    double score;
+    double p_final[6];
+    float gpu_ms;
+} b200_ndt_result;
+
+int32_t b200_ndt_create(const b200_ndt_params* params, int32_t device, b200_ndt** out);
+int32_t b200_ndt_destroy(b200_ndt* ndt);
+/* setInputTarget -> init() -> VoxelGridCovariance::filter(true) (ndt_omp.h:125-130,299-306) */
+int32_t b200_ndt_set_target(b200_ndt* ndt, const float* xyz, int64_t n, int64_t stride_bytes);
+/* setInputSource */
+int32_t b200_ndt_set_source(b200_ndt* ndt, const float* xyz, int64_t n, int64_t stride_bytes);
+int64_t b200_ndt_num_voxels(b200_ndt* ndt); /* leaves with nr_points >= min_pts and a valid covariance */
+/* valid leaves sorted by the reference's leaf id; any pointer may be NULL */
+int64_t b200_ndt_leaves(b200_ndt* ndt, int64_t max, int64_t* ids, int32_t* npts, double* mean3, double* cov9, double* icov9);
+/* align(output, guess) -> computeTransformation (ndt_omp_impl.hpp:70-156) */
+int32_t b200_ndt_align(b200_ndt* ndt, const float* guess16, float* final16, b200_ndt_result* result);
+/* computeDerivatives at pose vector p (x,y,z,roll,pitch,yaw) (ndt_omp_impl.hpp:169-267) */
+int32_t b200_ndt_derivatives(b200_ndt* ndt, const double* p6, double* score, double* g6, double* H36);
+/* computeHessian (double path, ndt_omp_impl.hpp:499-560) */
+int32_t b200_ndt_hessian(b200_ndt* ndt, const double* p6, double* H36);
+/* calculateScore for h candidate poses (ndt_omp_impl.hpp:836-880) — global relocalization primitive */
+int32_t b200_ndt_score_batch(b200_ndt* ndt, const float* poses16, int64_t h, double* scores);
+/* argmin over scores of this process's hypothesis slice; with a communicator the reduction spans all ranks */
+typedef struct b200_comm b200_comm;
+#define B200_NCCL_ID_BYTES 128
+int32_t b200_comm_unique_id(uint8_t* id128);
+int32_t b200_comm_init_rank(int32_t nranks, int32_t rank, const uint8_t* id128, int32_t device, b200_comm** out);
+int32_t b200_comm_destroy(b200_comm* comm);
+/* Hypotheses h_begin..h_begin+h-1 of a global grid are scored on this rank; every rank receives the global
+ * argmin (lowest score, ties to the lower index) through one 8-byte ncclAllReduce(min). comm may be NULL. */
+int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t* best,
+                          double* best_score, float* gpu_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

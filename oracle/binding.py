@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+PARITY UNPINNED: see oracle/oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ORC_MAX_PASSES = 8
+
+
+class LioParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("nearby", C.c_int32), ("capacity_voxels", C.c_uint64),
+                ("max_iter", C.c_int32), ("plane_thr", C.c_float), ("extrinsic_est_en", C.c_int32),
+                ("R", C.c_double), ("limit", C.c_double * 23), ("filter_size_map", C.c_double),
+                ("num_threads", C.c_int32)]
+
+
+class IekfStats(C.Structure):
+    _fields_ = [("status", C.c_int32), ("passes", C.c_int32), ("knn_passes", C.c_int32), ("converged", C.c_int32),
+                ("n_eff", C.c_int32 * ORC_MAX_PASSES), ("knn", C.c_int32 * ORC_MAX_PASSES),
+                ("x_in", (C.c_double * 26) * ORC_MAX_PASSES), ("HtH", (C.c_double * 144) * ORC_MAX_PASSES),
+                ("Hth", (C.c_double * 12) * ORC_MAX_PASSES),
+                ("ms_match", C.c_double), ("ms_jacobian", C.c_double), ("ms_solve", C.c_double)]
+
+
+class NdtParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+                ("trans_eps", C.c_double), ("max_iter", C.c_int32), ("search", C.c_int32), ("min_pts", C.c_int32),
+                ("eig_ratio", C.c_double), ("num_threads", C.c_int32)]
+
+
+class NdtResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iters", C.c_int32), ("evals", C.c_int32), ("hess_evals", C.c_int32),
+                ("trans_probability", C.c_double), ("hessian", C.c_double * 36), ("score", C.c_double),
+                ("p_final", C.c_double * 6)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "smallmat.h", "oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        L.orc_lio_create.restype = vp
+        L.orc_lio_create.argtypes = [C.POINTER(LioParams)]
+        L.orc_lio_destroy.argtypes = [vp]
+        L.orc_map_insert.restype = i64
+        L.orc_map_insert.argtypes = [vp, vp, i64, i64]
+        L.orc_map_num_voxels.restype = i64
+        L.orc_map_num_voxels.argtypes = [vp]
+        L.orc_map_num_points.restype = i64
+        L.orc_map_num_points.argtypes = [vp]
+        L.orc_map_knn5.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+        L.orc_map_knn_candidates.restype = i64
+        L.orc_map_knn_candidates.argtypes = [vp, vp, i64, i64]
+        L.orc_iekf_update.restype = i32
+        L.orc_iekf_update.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(IekfStats)]
+        L.orc_obs_model.restype = i32
+        L.orc_obs_model.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, vp]
+        L.orc_point_state.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.orc_last_rows.restype = i32
+        L.orc_last_rows.argtypes = [vp, vp, vp, i32]
+        L.orc_map_incremental.restype = i64
+        L.orc_map_incremental.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
+        L.orc_esti_plane.restype = i32
+        L.orc_esti_plane.argtypes = [vp, i32, C.c_float, vp]
+        L.orc_state_boxplus.argtypes = [vp, vp]
+        L.orc_state_boxminus.argtypes = [vp, vp, vp]
+        L.orc_inverse.argtypes = [vp, i32, vp]
+        L.orc_ndt_create.restype = vp
+        L.orc_ndt_create.argtypes = [C.POINTER(NdtParams)]
+        L.orc_ndt_destroy.argtypes = [vp]
+        L.orc_ndt_set_target.restype = i64
+        L.orc_ndt_set_target.argtypes = [vp, vp, i64, i64]
+        L.orc_ndt_set_source.argtypes = [vp, vp, i64, i64]
+        L.orc_ndt_num_leaves.restype = i64
+        L.orc_ndt_num_leaves.argtypes = [vp]
+        L.orc_ndt_leaves.restype = i64
+        L.orc_ndt_leaves.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.orc_ndt_grid.argtypes = [vp, vp, vp]
+        L.orc_ndt_derivatives.restype = C.c_double
+        L.orc_ndt_derivatives.argtypes = [vp, vp, vp, vp, i32]
+        L.orc_ndt_hessian.argtypes = [vp, vp, vp]
+        L.orc_ndt_align.restype = i32
+        L.orc_ndt_align.argtypes = [vp, vp, vp, C.POINTER(NdtResult)]
+        L.orc_ndt_score_batch.argtypes = [vp, vp, i64, vp]
+        L.orc_ndt_nbhd_total.restype = i64
+        L.orc_ndt_nbhd_total.argtypes = [vp, vp]
+        L.orc_euler_from_matrix.argtypes = [vp, vp]
+        L.orc_matrix_from_pose.argtypes = [vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def lio_params(resolution=0.5, nearby=18, capacity=1_000_000, max_iter=3, plane_thr=0.1, extrinsic_est_en=False,
+               R=0.001, limit=0.001, filter_size_map=0.5, num_threads=0) -> LioParams:
+    p = LioParams()
+    p.resolution, p.nearby, p.capacity_voxels = resolution, nearby, capacity
+    p.max_iter, p.plane_thr, p.extrinsic_est_en = max_iter, plane_thr, int(extrinsic_est_en)
+    p.R, p.filter_size_map, p.num_threads = R, filter_size_map, num_threads
+    for i in range(23):
+        p.limit[i] = limit
+    return p
+
+
+class OracleLio:
+    """IVox + ObsModel + IEKF update, CPU oracle."""
+
+    def __init__(self, **kw):
+        self.params = lio_params(**kw)
+        self.h = lib().orc_lio_create(C.byref(self.params))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_lio_destroy(self.h)
+            self.h = None
+
+    def insert(self, pts):
+        pts = _f32(pts)
+        return lib().orc_map_insert(self.h, _p(pts), pts.shape[0], pts.strides[0])
+
+    @property
+    def num_voxels(self):
+        return lib().orc_map_num_voxels(self.h)
+
+    @property
+    def num_points(self):
+        return lib().orc_map_num_points(self.h)
+
+    def knn5(self, q):
+        q = _f32(q)
+        n = q.shape[0]
+        idx = np.empty((n, 5), np.int32)
+        d = np.empty((n, 5), np.float32)
+        cnt = np.empty(n, np.int32)
+        lib().orc_map_knn5(self.h, _p(q), n, q.strides[0], _p(idx), _p(d), _p(cnt))
+        return idx, d, cnt
+
+    def knn_candidates(self, q):
+        q = _f32(q)
+        return lib().orc_map_knn_candidates(self.h, _p(q), q.shape[0], q.strides[0])
+
+    def update(self, scan, x, P):
+        scan = _f32(scan)
+        x = np.array(x, dtype=np.float64)
+        P = np.array(P, dtype=np.float64)
+        st = IekfStats()
+        rc = lib().orc_iekf_update(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(x), _p(P), C.byref(st))
+        return rc, x, P, st
+
+    def obs_model(self, scan, x, converge=True):
+        scan = _f32(scan)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        HtH = np.zeros((12, 12))
+        Hth = np.zeros(12)
+        ne = C.c_int32(0)
+        rc = lib().orc_obs_model(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(x), int(converge), _p(HtH), _p(Hth),
+                                 C.byref(ne))
+        return rc, HtH, Hth, ne.value
+
+    def point_state(self, n):
+        plane = np.empty((n, 4), np.float32)
+        res = np.empty(n, np.float32)
+        sel = np.empty(n, np.uint8)
+        nn = np.empty((n, 5), np.int32)
+        cnt = np.empty(n, np.int32)
+        lib().orc_point_state(self.h, n, _p(plane), _p(res), _p(sel), _p(nn), _p(cnt))
+        return dict(plane=plane, residual=res, selected=sel, nn_idx=nn, nn_count=cnt)
+
+    def last_rows(self, max_rows):
+        hx = np.zeros((max_rows, 12))
+        hv = np.zeros(max_rows)
+        n = lib().orc_last_rows(self.h, _p(hx), _p(hv), max_rows)
+        return hx[:min(n, max_rows)], hv[:min(n, max_rows)], n
+
+    def map_incremental(self, scan, x, ekf_inited=True):
+        scan = _f32(scan)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        na, nd = C.c_int32(0), C.c_int32(0)
+        tot = lib().orc_map_incremental(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(x), int(ekf_inited),
+                                        C.byref(na), C.byref(nd))
+        return tot, na.value, nd.value
+
+
+def esti_plane(pts, thr=0.1):
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    plane = np.zeros(4, np.float32)
+    ok = lib().orc_esti_plane(_p(pts), pts.shape[0], thr, _p(plane))
+    return bool(ok), plane
+
+
+def boxplus(x, dx):
+    x = np.array(x, dtype=np.float64)
+    dx = np.ascontiguousarray(dx, dtype=np.float64)
+    lib().orc_state_boxplus(_p(x), _p(dx))
+    return x
+
+
+def boxminus(x, y):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    d = np.zeros(23)
+    lib().orc_state_boxminus(_p(x), _p(y), _p(d))
+    return d
+
+
+def inverse(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    out = np.empty_like(A)
+    lib().orc_inverse(_p(A), A.shape[0], _p(out))
+    return out
+
+
+def ndt_params(resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=35, search=7, min_pts=6,
+               eig_ratio=0.01, num_threads=0) -> NdtParams:
+    p = NdtParams()
+    p.resolution, p.step_size, p.outlier_ratio, p.trans_eps = resolution, step_size, outlier_ratio, trans_eps
+    p.max_iter, p.search, p.min_pts, p.eig_ratio, p.num_threads = max_iter, search, min_pts, eig_ratio, num_threads
+    return p
+
+
+class OracleNdt:
+    def __init__(self, **kw):
+        self.params = ndt_params(**kw)
+        self.h = lib().orc_ndt_create(C.byref(self.params))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ndt_destroy(self.h)
+            self.h = None
+
+    def set_target(self, pts):
+        pts = _f32(pts)
+        return lib().orc_ndt_set_target(self.h, _p(pts), pts.shape[0], pts.strides[0])
+
+    def set_source(self, pts):
+        pts = _f32(pts)
+        lib().orc_ndt_set_source(self.h, _p(pts), pts.shape[0], pts.strides[0])
+
+    def leaves(self):
+        n = lib().orc_ndt_leaves(self.h, 0, None, None, None, None, None)
+        ids = np.empty(n, np.int64)
+        npts = np.empty(n, np.int32)
+        mean = np.empty((n, 3))
+        cov = np.empty((n, 3, 3))
+        icov = np.empty((n, 3, 3))
+        lib().orc_ndt_leaves(self.h, n, _p(ids), _p(npts), _p(mean), _p(cov), _p(icov))
+        return dict(ids=ids, npts=npts, mean=mean, cov=cov, icov=icov)
+
+    def grid(self):
+        mn = np.zeros(3, np.int32)
+        dv = np.zeros(3, np.int32)
+        lib().orc_ndt_grid(self.h, _p(mn), _p(dv))
+        return mn, dv
+
+    def derivatives(self, p6, compute_hessian=True):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        g = np.zeros(6)
+        H = np.zeros((6, 6))
+        s = lib().orc_ndt_derivatives(self.h, _p(p6), _p(g), _p(H), int(compute_hessian))
+        return s, g, H
+
+    def hessian(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        H = np.zeros((6, 6))
+        lib().orc_ndt_hessian(self.h, _p(p6), _p(H))
+        return H
+
+    def align(self, guess):
+        g = np.ascontiguousarray(np.asarray(guess, dtype=np.float32).T)  # column-major bytes
+        out = np.zeros((4, 4), np.float32)
+        r = NdtResult()
+        rc = lib().orc_ndt_align(self.h, _p(g), _p(out), C.byref(r))
+        return rc, out.T.copy(), r
+
+    def score_batch(self, poses_cm16):
+        poses = np.ascontiguousarray(poses_cm16, dtype=np.float32)
+        s = np.zeros(poses.shape[0])
+        lib().orc_ndt_score_batch(self.h, _p(poses), poses.shape[0], _p(s))
+        return s
+
+    def nbhd_total(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        return lib().orc_ndt_nbhd_total(self.h, _p(p6))
+
+
+def euler_from_matrix(M):
+    m = np.ascontiguousarray(np.asarray(M, dtype=np.float32).T)
+    r = np.zeros(3, np.float32)
+    lib().orc_euler_from_matrix(_p(m), _p(r))
+    return r
+
+
+def matrix_from_pose(p6):
+    p6 = np.ascontiguousarray(p6, dtype=np.float64)
+    m = np.zeros((4, 4), np.float32)
+    lib().orc_matrix_from_pose(_p(p6), _p(m))
+    return m.T.copy()

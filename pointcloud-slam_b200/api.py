@@ -1,0 +1,377 @@
+"""ctypes view of the b200reg C ABI (include/b200reg.h) with the reference's interface names.
+
+This is the Python mirror used by tests/ and bench.py; the C++ mirror a ROS package would compile
+lives in host/*.hpp.  Class and method names follow the reference:
+  IVox.AddPoints / GetClosestPoint / NumValidGrids              (jueying_lio ivox3d.h:53-88)
+  Esekf.update_iterated_dyn_share_modified / get_x / get_P      (IKFoM esekfom.hpp:1526,1836-1848)
+  LaserMappingCore.MapIncremental                               (jueying_lio laser_mapping.cc:525)
+  NormalDistributionsTransform.setInputTarget / align / ...     (pclomp ndt_omp.h:117-261)
+There is no CPU fallback: if libb200reg.so is missing or no CUDA device exists, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+B200_MAX_PASSES = 8
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class MapParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("nearby", C.c_int32), ("capacity_voxels", C.c_uint64),
+                ("max_range", C.c_float), ("max_points", C.c_uint64)]
+
+
+class IekfParams(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("plane_thr", C.c_float), ("extrinsic_est_en", C.c_int32), ("R", C.c_double),
+                ("limit", C.c_double * 23), ("filter_size_map", C.c_double)]
+
+
+class IekfStats(C.Structure):
+    _fields_ = [("status", C.c_int32), ("passes", C.c_int32), ("knn_passes", C.c_int32), ("converged", C.c_int32),
+                ("n_eff", C.c_int32 * B200_MAX_PASSES), ("knn", C.c_int32 * B200_MAX_PASSES), ("gpu_ms", C.c_float)]
+
+
+class NdtParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+                ("trans_eps", C.c_double), ("max_iter", C.c_int32), ("search", C.c_int32), ("min_pts", C.c_int32),
+                ("eig_ratio", C.c_double)]
+
+
+class NdtResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iters", C.c_int32), ("evals", C.c_int32), ("hess_evals", C.c_int32),
+                ("trans_probability", C.c_double), ("hessian", C.c_double * 36), ("score", C.c_double),
+                ("p_final", C.c_double * 6), ("gpu_ms", C.c_float)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libb200reg.so")
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libb200reg.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.append("-s")
+    subprocess.check_call(cmd)
+    return lib_path()
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B200Error(f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.b200_version.restype = C.c_char_p
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_kernel_launches.restype = i64
+    L.b200_map_create.argtypes = [C.POINTER(MapParams), i32, C.POINTER(vp)]
+    L.b200_map_destroy.argtypes = [vp]
+    L.b200_map_insert.argtypes = [vp, vp, i64, i64]
+    L.b200_map_knn5.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    L.b200_map_num_voxels.restype = i64
+    L.b200_map_num_voxels.argtypes = [vp]
+    L.b200_map_num_points.restype = i64
+    L.b200_map_num_points.argtypes = [vp]
+    L.b200_iekf_create.argtypes = [C.POINTER(IekfParams), vp, C.POINTER(vp)]
+    L.b200_iekf_destroy.argtypes = [vp]
+    L.b200_iekf_update.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(IekfStats)]
+    L.b200_iekf_update_device.argtypes = [vp, vp, i64, vp, vp, C.POINTER(IekfStats)]
+    L.b200_iekf_last_HtH.argtypes = [vp, i32, vp, vp, vp]
+    L.b200_iekf_obs_model.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, vp]
+    L.b200_iekf_point_state.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.b200_iekf_map_incremental.argtypes = [vp, vp, i32, vp, vp]
+    if hasattr(L, "b200_ndt_create"):
+        L.b200_ndt_create.argtypes = [C.POINTER(NdtParams), i32, C.POINTER(vp)]
+        L.b200_ndt_destroy.argtypes = [vp]
+        L.b200_ndt_set_target.argtypes = [vp, vp, i64, i64]
+        L.b200_ndt_set_source.argtypes = [vp, vp, i64, i64]
+        L.b200_ndt_num_voxels.restype = i64
+        L.b200_ndt_num_voxels.argtypes = [vp]
+        L.b200_ndt_leaves.restype = i64
+        L.b200_ndt_leaves.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.b200_ndt_align.argtypes = [vp, vp, vp, C.POINTER(NdtResult)]
+        L.b200_ndt_derivatives.argtypes = [vp, vp, vp, vp, vp]
+        L.b200_ndt_hessian.argtypes = [vp, vp, vp]
+        L.b200_ndt_score_batch.argtypes = [vp, vp, i64, vp]
+        L.b200_comm_unique_id.argtypes = [vp]
+        L.b200_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
+        L.b200_comm_destroy.argtypes = [vp]
+        L.b200_reloc_argmin.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+    _LIB = L
+    return L
+
+
+def _check(rc: int, soft=(0,)):
+    """Negative codes are errors; positive codes are the reference's soft outcomes and are returned."""
+    if rc < 0:
+        raise B200Error(f"b200reg error {rc}: {lib().b200_last_error().decode()}")
+    return rc
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _cloud(a):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or a.strides[1] != 4:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def kernel_launches() -> int:
+    return int(lib().b200_kernel_launches())
+
+
+class IVox:
+    """GPU local map with jueying_lio::IVox's surface (ivox3d.h:53-88)."""
+
+    def __init__(self, resolution=0.2, nearby=6, capacity=1_000_000, device=0, max_points=0, max_range=5.0):
+        self.params = MapParams(resolution, nearby, capacity, max_range, max_points)
+        self.h = C.c_void_p()
+        _check(lib().b200_map_create(C.byref(self.params), device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_map_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def AddPoints(self, points):
+        pts = _cloud(points)
+        _check(lib().b200_map_insert(self.h, _p(pts), pts.shape[0], pts.strides[0]))
+
+    def GetClosestPoint(self, points):
+        """Batched GetClosestPoint(pt, out, 5, 5.0): returns (ordinals [n,5], sqdist [n,5], count [n])."""
+        q = _cloud(points)
+        n = q.shape[0]
+        idx = np.empty((n, 5), np.int32)
+        d2 = np.empty((n, 5), np.float32)
+        cnt = np.empty(n, np.int32)
+        _check(lib().b200_map_knn5(self.h, _p(q), n, q.strides[0], _p(idx), _p(d2), _p(cnt)))
+        return idx, d2, cnt
+
+    def NumValidGrids(self) -> int:
+        return int(lib().b200_map_num_voxels(self.h))
+
+    def NumPoints(self) -> int:
+        return int(lib().b200_map_num_points(self.h))
+
+
+class Esekf:
+    """Device-resident esekf + ObsModel with the reference's call names (esekfom.hpp:1526,1836-1848)."""
+
+    def __init__(self, ivox: IVox, max_iter=3, plane_thr=0.1, extrinsic_est_en=False, R=0.001, limit=0.001,
+                 filter_size_map=0.5):
+        p = IekfParams()
+        p.max_iter, p.plane_thr, p.extrinsic_est_en, p.R, p.filter_size_map = max_iter, plane_thr, int(extrinsic_est_en), R, filter_size_map
+        for i in range(23):
+            p.limit[i] = limit if np.isscalar(limit) else limit[i]
+        self.params = p
+        self.ivox = ivox
+        self.h = C.c_void_p()
+        _check(lib().b200_iekf_create(C.byref(p), ivox.h, C.byref(self.h)))
+        self.x = np.zeros(26)
+        self.P = np.eye(23)
+        self.stats = IekfStats()
+        self._n = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_iekf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def change_x(self, x):
+        self.x = np.array(x, dtype=np.float64)
+
+    def change_P(self, P):
+        self.P = np.array(P, dtype=np.float64)
+
+    def get_x(self):
+        return self.x
+
+    def get_P(self):
+        return self.P
+
+    def update_iterated_dyn_share_modified(self, scan_body):
+        """One IEKF measurement update on the downsampled body-frame scan; returns the status code."""
+        scan = _cloud(scan_body)
+        self._n = scan.shape[0]
+        rc = lib().b200_iekf_update(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(self.x), _p(self.P), C.byref(self.stats))
+        return _check(rc, soft=(0, 1))
+
+    def last_HtH(self, p):
+        HtH = np.zeros((12, 12))
+        Hth = np.zeros(12)
+        x_in = np.zeros(26)
+        _check(lib().b200_iekf_last_HtH(self.h, p, _p(HtH), _p(Hth), _p(x_in)))
+        return HtH, Hth, x_in
+
+    def ObsModel(self, scan_body, x, converge=True):
+        scan = _cloud(scan_body)
+        self._n = scan.shape[0]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        HtH = np.zeros((12, 12))
+        Hth = np.zeros(12)
+        ne = C.c_int32(0)
+        rc = lib().b200_iekf_obs_model(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(x), int(converge), _p(HtH), _p(Hth), C.byref(ne))
+        _check(rc, soft=(0, 1))
+        return rc, HtH, Hth, ne.value
+
+    def point_state(self, n=None):
+        n = self._n if n is None else n
+        plane = np.empty((n, 4), np.float32)
+        res = np.empty(n, np.float32)
+        sel = np.empty(n, np.uint8)
+        nn = np.empty((n, 5), np.int32)
+        cnt = np.empty(n, np.int32)
+        _check(lib().b200_iekf_point_state(self.h, n, _p(plane), _p(res), _p(sel), _p(nn), _p(cnt)))
+        return dict(plane=plane, residual=res, selected=sel, nn_idx=nn, nn_count=cnt)
+
+    def MapIncremental(self, x=None, ekf_inited=True):
+        x = np.ascontiguousarray(self.x if x is None else x, dtype=np.float64)
+        na, nd = C.c_int32(0), C.c_int32(0)
+        _check(lib().b200_iekf_map_incremental(self.h, _p(x), int(ekf_inited), C.byref(na), C.byref(nd)))
+        return na.value, nd.value
+
+
+class NormalDistributionsTransform:
+    """pclomp::NormalDistributionsTransform's surface (ndt_omp.h:117-261) on the GPU engine."""
+
+    def __init__(self, device=0):
+        self._p = NdtParams(1.0, 0.1, 0.55, 0.1, 35, 7, 6, 0.01)  # ctor defaults, ndt_omp_impl.hpp:47-65
+        self._device = device
+        self.h = None
+        self._target = None
+        self._source = None
+        self.result = NdtResult()
+        self._final = np.eye(4, dtype=np.float32)
+        self._dirty = True
+
+    def _handle(self):
+        if self.h is None or self._dirty:
+            if self.h is not None:
+                lib().b200_ndt_destroy(self.h)
+            self.h = C.c_void_p()
+            _check(lib().b200_ndt_create(C.byref(self._p), self._device, C.byref(self.h)))
+            self._dirty = False
+            if self._target is not None:
+                _check(lib().b200_ndt_set_target(self.h, _p(self._target), self._target.shape[0], self._target.strides[0]))
+            if self._source is not None:
+                _check(lib().b200_ndt_set_source(self.h, _p(self._source), self._source.shape[0], self._source.strides[0]))
+        return self.h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_ndt_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def setResolution(self, r):
+        self._p.resolution = r
+        self._dirty = True
+
+    def setStepSize(self, s):
+        self._p.step_size = s
+        self._dirty = True
+
+    def setOutlierRatio(self, o):
+        self._p.outlier_ratio = o
+        self._dirty = True
+
+    def setTransformationEpsilon(self, e):
+        self._p.trans_eps = e
+        self._dirty = True
+
+    def setMaximumIterations(self, n):
+        self._p.max_iter = n
+        self._dirty = True
+
+    def setNeighborhoodSearchMethod(self, m):
+        self._p.search = {"DIRECT1": 1, "DIRECT7": 7, "DIRECT26": 27}.get(m, m)
+        self._dirty = True
+
+    def setNumThreads(self, n):  # accepted for source compatibility; the device decides
+        pass
+
+    def setInputTarget(self, cloud):
+        self._target = _cloud(cloud)
+        if self.h is not None and not self._dirty:
+            _check(lib().b200_ndt_set_target(self.h, _p(self._target), self._target.shape[0], self._target.strides[0]))
+
+    def setInputSource(self, cloud):
+        self._source = _cloud(cloud)
+        if self.h is not None and not self._dirty:
+            _check(lib().b200_ndt_set_source(self.h, _p(self._source), self._source.shape[0], self._source.strides[0]))
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, dtype=np.float32)
+        gcm = np.ascontiguousarray(g.T)
+        out = np.zeros((4, 4), np.float32)
+        rc = lib().b200_ndt_align(self._handle(), _p(gcm), _p(out), C.byref(self.result))
+        _check(rc, soft=(0, 2))
+        self._final = out.T.copy()
+        return rc
+
+    def hasConverged(self):
+        return bool(self.result.converged)
+
+    def getFinalTransformation(self):
+        return self._final
+
+    def getFinalNumIteration(self):
+        return self.result.iters
+
+    def getTransformationProbability(self):
+        return self.result.trans_probability
+
+    def numVoxels(self):
+        return int(lib().b200_ndt_num_voxels(self._handle()))
+
+    def leaves(self):
+        h = self._handle()
+        n = lib().b200_ndt_leaves(h, 0, None, None, None, None, None)
+        ids = np.empty(n, np.int64)
+        npts = np.empty(n, np.int32)
+        mean = np.empty((n, 3))
+        cov = np.empty((n, 3, 3))
+        icov = np.empty((n, 3, 3))
+        lib().b200_ndt_leaves(h, n, _p(ids), _p(npts), _p(mean), _p(cov), _p(icov))
+        return dict(ids=ids, npts=npts, mean=mean, cov=cov, icov=icov)
+
+    def computeDerivatives(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        s = C.c_double(0)
+        g = np.zeros(6)
+        H = np.zeros((6, 6))
+        _check(lib().b200_ndt_derivatives(self._handle(), _p(p6), C.byref(s), _p(g), _p(H)))
+        return s.value, g, H
+
+    def computeHessian(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        H = np.zeros((6, 6))
+        _check(lib().b200_ndt_hessian(self._handle(), _p(p6), _p(H)))
+        return H
+
+    def calculateScore(self, poses_cm16):
+        poses = np.ascontiguousarray(poses_cm16, dtype=np.float32).reshape(-1, 16)
+        s = np.zeros(poses.shape[0])
+        _check(lib().b200_ndt_score_batch(self._handle(), _p(poses), poses.shape[0], _p(s)))
+        return s

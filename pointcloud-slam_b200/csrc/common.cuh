@@ -1,0 +1,118 @@
+// b200reg — shared device/host helpers.  sm_100a only; compiled with -fmad=false so every
+// fp32 op is a separately rounded IEEE op (the reference is built without FMA,
+// jueying_lio/CMakeLists.txt:10-11, and neighbour sets must be bit-exact).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/b200reg.h"
+
+namespace b200 {
+
+extern thread_local std::string g_last_error;
+extern int64_t g_kernel_launches;  // counted by every launch site (bench.py "gpu_launches")
+
+inline int32_t fail(int32_t code, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s (%s:%d)", what, file, line);
+    g_last_error = buf;
+    return code;
+}
+#define B200_FAIL(code, what) return ::b200::fail((code), (what), __FILE__, __LINE__)
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define LAUNCH_COUNT(n) (::b200::g_kernel_launches += (n))
+
+template <class T>
+struct DevBuf {  // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 4 + 64;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    // grow but keep the first `keep` elements
+    cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t s) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 2 + 64;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return e;
+            cudaStreamSynchronize(s);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 4 + 64;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, ncap * sizeof(T));
+        cap = e == cudaSuccess ? ncap : 0;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---- voxel keys: three 21-bit biased cell coordinates packed into 63 bits ----------------
+constexpr int kKeyBias = 1 << 20;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+__host__ __device__ inline bool cell_in_range(int x, int y, int z) {
+    return (unsigned)(x + kKeyBias) < (1u << 21) && (unsigned)(y + kKeyBias) < (1u << 21) && (unsigned)(z + kKeyBias) < (1u << 21);
+}
+__host__ __device__ inline uint64_t pack_key(int x, int y, int z) {
+    return ((uint64_t)(uint32_t)(x + kKeyBias) << 42) | ((uint64_t)(uint32_t)(y + kKeyBias) << 21) | (uint64_t)(uint32_t)(z + kKeyBias);
+}
+__host__ __device__ inline uint32_t hash_key(uint64_t k) {  // murmur3 finalizer
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+// Pass a strided host cloud through a pinned staging buffer as packed float4 (x,y,z,0).
+inline void pack_xyz_float4(const float* xyz, int64_t n, int64_t stride, float4* dst) {
+    const char* src = (const char*)xyz;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = (const float*)(src + i * stride);
+        dst[i] = make_float4(p[0], p[1], p[2], 0.0f);
+    }
+}
+
+}  // namespace b200

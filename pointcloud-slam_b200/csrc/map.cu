@@ -1,0 +1,334 @@
+// b200reg — local map: build / incremental insert / k=5 stencil search.  See map.cuh for the layout.
+#include "map.cuh"
+
+#include <cub/cub.cuh>
+
+namespace b200 {
+
+thread_local std::string g_last_error;
+int64_t g_kernel_launches = 0;
+
+// ------------------------------------------------------------------ insert kernels
+// 1. voxel key of every incoming point (IVox::Pos2Grid, ivox3d.h:284-286)
+__global__ void k_point_keys(const float4* __restrict__ pts, int n, float inv_res, uint64_t* __restrict__ keys,
+                             int32_t* __restrict__ vals, MapCounters* ctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pts[i];
+    int cx = pos2cell(p.x, inv_res), cy = pos2cell(p.y, inv_res), cz = pos2cell(p.z, inv_res);
+    if (!cell_in_range(cx, cy, cz) || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+        atomicAdd(&ctr->err_range, 1u);
+        cx = cy = cz = 0;
+    }
+    keys[i] = pack_key(cx, cy, cz);
+    vals[i] = i;
+}
+
+// 2. one thread per run of equal keys: find-or-create the voxel, reserve room for the run.
+//    run_dst[r]   = pool index where the run's first new point goes
+//    run_reloc[r] = old start if the voxel had to move (its old points are copied by k_relocate), else -1
+__global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* __restrict__ cnt, const int32_t* __restrict__ nruns,
+                              uint64_t* keys, int4* vox, uint32_t tmask, uint64_t pool_cap, uint32_t capacity_voxels,
+                              uint32_t stamp, MapCounters* ctr, int32_t* __restrict__ run_dst, int32_t* __restrict__ run_reloc,
+                              int32_t* __restrict__ run_oldcnt) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    const uint64_t key = uniq[r];
+    const int c = cnt[r];
+    uint32_t slot = hash_key(key) & tmask;
+    bool created = false;
+    while (true) {
+        uint64_t k = keys[slot];
+        if (k == key) break;
+        if (k == kEmptyKey) {
+            uint64_t old = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (old == kEmptyKey) { created = true; break; }
+            if (old == key) break;
+        }
+        slot = (slot + 1) & tmask;
+    }
+    int4 v = created ? make_int4(0, 0, 0, 0) : vox[slot];
+    if (created) {
+        unsigned nv = atomicAdd(&ctr->num_voxels, 1u) + 1u;
+        if (nv >= capacity_voxels) atomicAdd(&ctr->err_capacity, 1u);
+    }
+    const int newcount = v.y + c;
+    int reloc = -1;
+    if (newcount > v.z) {
+        int newcap = v.z == 0 ? newcount : max(2 * v.z, newcount);
+        unsigned long long st = atomicAdd(&ctr->pool_top, (unsigned long long)newcap);
+        if (st + (unsigned long long)newcap > pool_cap) {
+            atomicAdd(&ctr->err_pool, 1u);
+            run_dst[r] = -1;
+            run_reloc[r] = -1;
+            return;
+        }
+        if (v.y > 0) reloc = v.x;
+        v.x = (int)st;
+        v.z = newcap;
+    }
+    run_dst[r] = v.x + v.y;
+    run_reloc[r] = reloc;
+    run_oldcnt[r] = v.y;
+    atomicAdd(&ctr->live_points, (unsigned long long)c);
+    v.y = newcount;
+    v.w = (int)stamp;
+    vox[slot] = v;
+}
+
+// 3. voxels that moved: copy their old points to the new slot (one thread per run, old runs are short)
+__global__ void k_relocate(const int32_t* __restrict__ nruns, const int32_t* __restrict__ run_dst, const int32_t* __restrict__ run_reloc,
+                            const int32_t* __restrict__ run_oldcnt, float4* pool) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    int src = run_reloc[r];
+    if (src < 0) return;
+    int oc = run_oldcnt[r];
+    int dst = run_dst[r] - oc;
+    for (int j = 0; j < oc; ++j) pool[dst + j] = pool[src + j];
+}
+
+// 4. scatter the sorted batch into the pool: element i of the sorted order belongs to run
+//    r = upper_bound(run_off, i) - 1 and lands at run_dst[r] + (i - run_off[r]).
+__global__ void k_scatter_points(const float4* __restrict__ pts, const int32_t* __restrict__ sorted_vals, int n,
+                                 const int32_t* __restrict__ nruns, const int32_t* __restrict__ run_off,
+                                 const int32_t* __restrict__ run_dst, int base_ord, float4* pool) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = *nruns;  // find last r with run_off[r] <= i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(run_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    int dst0 = run_dst[lo];
+    if (dst0 < 0) return;
+    int src = sorted_vals[i];
+    float4 p = pts[src];
+    p.w = __int_as_float(base_ord + src);
+    pool[dst0 + (i - run_off[lo])] = p;
+}
+
+__global__ void k_fill_keys(uint64_t* keys, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = kEmptyKey;
+}
+
+// pool compaction: every live voxel gets a fresh exact-fit run in a new pool
+__global__ void k_compact_plan(const uint64_t* __restrict__ keys, int4* vox, uint32_t tsize, unsigned long long* top,
+                               const float4* __restrict__ old_pool, float4* new_pool) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= tsize) return;
+    if (keys[s] == kEmptyKey) return;
+    int4 v = vox[s];
+    if (v.y == 0) return;
+    int slack = v.y < 4 ? v.y : v.y / 2;  // leave growth room so the next insert does not move everything again
+    unsigned long long st = atomicAdd(top, (unsigned long long)(v.y + slack));
+    for (int j = 0; j < v.y; ++j) new_pool[st + j] = old_pool[v.x + j];
+    v.x = (int)st;
+    v.z = v.y + slack;
+    vox[s] = v;
+}
+
+// ------------------------------------------------------------------ standalone k=5 search
+template <int G>
+__global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                               float* __restrict__ d2, int32_t* __restrict__ cnt) {
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lg = threadIdx.x % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    if (gid >= n) return;  // whole groups leave together
+    float4 p = __ldg(q + gid);
+    uint64_t win[5];
+    float4 mine;
+    int c = knn5_group<G>(m, p.x, p.y, p.z, lg, gmask, win, mine);
+    if (lg < 5) {
+        uint64_t w = win[0];
+#pragma unroll
+        for (int r = 1; r < 5; ++r)
+            if (lg == r) w = win[r];
+        idx[gid * 5 + lg] = __float_as_int(mine.w);
+        d2[gid * 5 + lg] = (w == kInfKey) ? 0.0f : __uint_as_float((uint32_t)(w >> 32));
+    }
+    if (lg == 0) cnt[gid] = c;
+}
+
+// ------------------------------------------------------------------ host side
+static uint32_t next_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int32_t Map::init(const b200_map_params* p, int dev) {
+    prm = *p;
+    if (!(prm.resolution > 0.f)) B200_FAIL(B200_ERR_ARG, "resolution must be > 0");
+    if (prm.max_range <= 0.f) prm.max_range = 5.0f;
+    if (prm.capacity_voxels == 0) prm.capacity_voxels = 1000000;
+    if (prm.max_points == 0) prm.max_points = 8u << 20;
+    device = dev;
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    inv_res = (float)(1.0 / (double)prm.resolution);  // ivox3d.h:65
+    nstencil = prm.nearby == 0 ? 1 : prm.nearby == 6 ? 7 : prm.nearby == 26 ? 27 : 19;
+    tsize = next_pow2(2 * prm.capacity_voxels);
+    CUDA_TRY(cudaMalloc(&d_keys, (size_t)tsize * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&d_vox, (size_t)tsize * sizeof(int4)));
+    pool_cap = 4 * prm.max_points;
+    CUDA_TRY(cudaMalloc(&d_pool, pool_cap * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&d_ctr, sizeof(MapCounters)));
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(MapCounters), stream));
+    CUDA_TRY(cudaMemsetAsync(d_vox, 0, (size_t)tsize * sizeof(int4), stream));
+    k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(d_keys, tsize);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(h_ctr_pin.reserve(1));
+    CUDA_TRY(d_nruns.reserve(1));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    memset(&h_ctr, 0, sizeof h_ctr);
+    return B200_OK;
+}
+
+void Map::destroy() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(d_keys); cudaFree(d_vox); cudaFree(d_pool); cudaFree(d_ctr);
+    in_pts.release(); k_in.release(); k_out.release(); k_uniq.release();
+    v_in.release(); v_out.release(); run_cnt.release(); run_off.release(); run_dst.release(); run_reloc.release();
+    d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
+    q_idx.release(); q_cnt.release(); q_d2.release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+}
+
+int32_t Map::grow_pool(uint64_t min_cap) {
+    // compaction into a new (possibly larger) pool
+    uint64_t live = h_ctr.live_points;
+    uint64_t ncap = 4 * live + 4 * min_cap + (1u << 20);
+    if (ncap < pool_cap) ncap = pool_cap;
+    float4* np = nullptr;
+    CUDA_TRY(cudaMalloc(&np, ncap * sizeof(float4)));
+    CUDA_TRY(cudaMemsetAsync(&d_ctr->pool_top, 0, sizeof(unsigned long long), stream));
+    k_compact_plan<<<(tsize + 255) / 256, 256, 0, stream>>>(d_keys, d_vox, tsize, &d_ctr->pool_top, d_pool, np);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaMemcpyAsync(h_ctr_pin.p, d_ctr, sizeof(MapCounters), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h_ctr.pool_top = h_ctr_pin.p->pool_top;
+    cudaFree(d_pool);
+    d_pool = np;
+    pool_cap = ncap;
+    return B200_OK;
+}
+
+int32_t Map::insert_device(const float4* d_pts, int64_t n) {
+    if (n == 0) return B200_OK;
+    if (n > (int64_t)0x3fffffff) B200_FAIL(B200_ERR_ARG, "batch too large");
+    CUDA_TRY(cudaSetDevice(device));
+    // worst case for this batch: every touched voxel relocates and doubles -> <= 2*(live + n) new slots
+    if (h_ctr.pool_top + 2 * (h_ctr.live_points + (uint64_t)n) > pool_cap) {
+        int32_t rc = grow_pool((uint64_t)n);
+        if (rc) return rc;
+    }
+    CUDA_TRY(k_in.reserve(n)); CUDA_TRY(k_out.reserve(n)); CUDA_TRY(k_uniq.reserve(n));
+    CUDA_TRY(v_in.reserve(n)); CUDA_TRY(v_out.reserve(n));
+    CUDA_TRY(run_cnt.reserve(n)); CUDA_TRY(run_off.reserve(n)); CUDA_TRY(run_dst.reserve(n)); CUDA_TRY(run_reloc.reserve(2 * n));
+    const int nb = (int)((n + 255) / 256);
+    k_point_keys<<<nb, 256, 0, stream>>>(d_pts, (int)n, inv_res, k_in.p, v_in.p, d_ctr);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63, stream);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t2, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, run_cnt.p, run_off.p, (int)n, stream);
+    size_t tmp = t1 > t2 ? t1 : t2;
+    tmp = tmp > t3 ? tmp : t3;
+    CUDA_TRY(cub_tmp.reserve(tmp));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63, stream));
+    CUDA_TRY(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, tmp, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream));
+    // exclusive scan over all n slots (entries past nruns are garbage and never read)
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, run_cnt.p, run_off.p, (int)n, stream));
+    ++stamp;
+    int32_t* run_oldcnt = run_reloc.p + n;
+    k_upsert_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_cnt.p, d_nruns.p, d_keys, d_vox, tsize - 1, pool_cap,
+                                          (uint32_t)prm.capacity_voxels, stamp, d_ctr, run_dst.p, run_reloc.p, run_oldcnt);
+    k_relocate<<<nb, 256, 0, stream>>>(d_nruns.p, run_dst.p, run_reloc.p, run_oldcnt, d_pool);
+    k_scatter_points<<<nb, 256, 0, stream>>>(d_pts, v_out.p, (int)n, d_nruns.p, run_off.p, run_dst.p, (int)next_ord, d_pool);
+    LAUNCH_COUNT(4);  // own kernels (cub's sort/RLE/scan passes are not counted)
+    CUDA_TRY(cudaMemcpyAsync(h_ctr_pin.p, d_ctr, sizeof(MapCounters), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h_ctr = *h_ctr_pin.p;
+    next_ord += n;
+    h_ctr.num_points = (unsigned long long)next_ord;
+    if (h_ctr.err_range) B200_FAIL(B200_ERR_RANGE, "point outside the voxel key range or non-finite");
+    if (h_ctr.err_pool) B200_FAIL(B200_ERR_NOMEM, "point pool exhausted");
+    if (h_ctr.err_capacity) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity reached (LRU eviction not implemented)");
+    return B200_OK;
+}
+
+int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
+    if (n < 0 || (n > 0 && !xyz) || stride < 12) B200_FAIL(B200_ERR_ARG, "bad point buffer");
+    if (n == 0) return B200_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(h_stage.reserve(n));
+    CUDA_TRY(in_pts.reserve(n));
+    pack_xyz_float4(xyz, n, stride, h_stage.p);
+    CUDA_TRY(cudaMemcpyAsync(in_pts.p, h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    return insert_device(in_pts.p, n);
+}
+
+int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt) {
+    if (n < 0 || (n > 0 && (!xyz || !idx || !d2 || !cnt)) || stride < 12) B200_FAIL(B200_ERR_ARG, "bad query buffer");
+    if (n == 0) return B200_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(h_stage.reserve(n));
+    CUDA_TRY(in_pts.reserve(n));
+    CUDA_TRY(q_idx.reserve(n * 5)); CUDA_TRY(q_d2.reserve(n * 5)); CUDA_TRY(q_cnt.reserve(n));
+    pack_xyz_float4(xyz, n, stride, h_stage.p);
+    CUDA_TRY(cudaMemcpyAsync(in_pts.p, h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    constexpr int G = 8;
+    const int64_t threads = n * G;
+    k_knn5<G><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(idx, q_idx.p, n * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(d2, q_d2.p, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(cnt, q_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return B200_OK;
+}
+
+}  // namespace b200
+
+// ------------------------------------------------------------------ C ABI (B1)
+
+extern "C" {
+
+const char* b200_version(void) { return "b200reg 0.1 (sm_100a)"; }
+const char* b200_last_error(void) { return b200::g_last_error.c_str(); }
+int64_t b200_kernel_launches(void) { return b200::g_kernel_launches; }
+
+int32_t b200_map_create(const b200_map_params* params, int32_t device, b200_map** out) {
+    if (!params || !out) B200_FAIL(B200_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B200_FAIL(B200_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) B200_FAIL(B200_ERR_ARG, "bad device ordinal");
+    b200_map* h = new b200_map();
+    int32_t rc = h->m.init(params, device);
+    if (rc != B200_OK) { h->m.destroy(); delete h; return rc; }
+    *out = h;
+    return B200_OK;
+}
+int32_t b200_map_destroy(b200_map* map) {
+    if (!map) return B200_OK;
+    map->m.destroy();
+    delete map;
+    return B200_OK;
+}
+int32_t b200_map_insert(b200_map* map, const float* xyz, int64_t n, int64_t stride_bytes) {
+    if (!map) B200_FAIL(B200_ERR_ARG, "null map");
+    return map->m.insert_host(xyz, n, stride_bytes);
+}
+int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist, int32_t* count) {
+    if (!map) B200_FAIL(B200_ERR_ARG, "null map");
+    return map->m.knn5_host(xyz_world, n, stride_bytes, idx, sqdist, count);
+}
+int64_t b200_map_num_voxels(b200_map* map) { return map ? (int64_t)map->m.h_ctr.num_voxels : 0; }
+int64_t b200_map_num_points(b200_map* map) { return map ? (int64_t)map->m.h_ctr.live_points : 0; }
+
+}  // extern "C"

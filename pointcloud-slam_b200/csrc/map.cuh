@@ -1,0 +1,204 @@
+// b200reg — GPU-resident local map index (replaces jueying_lio::IVox, ivox3d.h:53-286).
+//
+// Layout in HBM
+//   keys[T]   uint64   open-addressing table of packed voxel keys (T = pow2 >= 2*capacity)
+//   vox[T]    int4     {start, count, cap, stamp}: the voxel's run inside the point pool
+//   pool[]    float4   points, voxel-contiguous, in-voxel order = insertion order;
+//                      .w carries the global insertion ordinal (int bits)
+// A voxel is one contiguous, 16-byte-aligned run, so a stencil search is <= 27 table probes
+// followed by <= 27 contiguous gathers.  Insert = radix sort of the batch by key + run-length
+// segmentation + per-run upsert (bump allocation, relocation with doubling when a run outgrows
+// its slot); the pool is compacted when it fills up.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct MapCounters {
+    unsigned long long pool_top;
+    unsigned int num_voxels;
+    unsigned int err_range;    // a point fell outside the key range
+    unsigned int err_pool;     // pool exhausted during insert (host compacts / grows and retries)
+    unsigned int err_capacity; // voxel capacity reached
+    unsigned long long num_points;
+    unsigned long long live_points;  // sum of run counts (== num_points while nothing is evicted)
+};
+
+struct MapView {  // what kernels see
+    const uint64_t* keys;
+    const int4* vox;
+    const float4* pool;
+    uint32_t tmask;
+    float inv_res;
+    int nstencil;
+    float max_range2;
+};
+
+// stencil enumeration order of IVox::GenerateNearbyGrids (ivox3d.h:213-231): NEARBY6 is a prefix
+// of NEARBY18 which is a prefix of NEARBY26.
+static __constant__ signed char c_stencil[27][4] = {
+    {0, 0, 0, 0},   {-1, 0, 0, 0}, {1, 0, 0, 0},   {0, 1, 0, 0},   {0, -1, 0, 0},  {0, 0, -1, 0},  {0, 0, 1, 0},
+    {1, 1, 0, 0},   {-1, 1, 0, 0}, {1, -1, 0, 0},  {-1, -1, 0, 0}, {1, 0, 1, 0},   {-1, 0, 1, 0},  {1, 0, -1, 0},
+    {-1, 0, -1, 0}, {0, 1, 1, 0},  {0, -1, 1, 0},  {0, 1, -1, 0},  {0, -1, -1, 0}, {1, 1, 1, 0},   {-1, 1, 1, 0},
+    {1, -1, 1, 0},  {1, 1, -1, 0}, {-1, -1, 1, 0}, {-1, 1, -1, 0}, {1, -1, -1, 0}, {-1, -1, -1, 0}};
+
+// IVox::Pos2Grid (ivox3d.h:284-286): round(p * inv_res) with std::round semantics.
+__device__ __forceinline__ int pos2cell(float v, float inv_res) { return (int)roundf(__fmul_rn(v, inv_res)); }
+
+__device__ __forceinline__ int2 map_find(const MapView& m, uint64_t key) {
+    uint32_t slot = hash_key(key) & m.tmask;
+    while (true) {
+        uint64_t k = __ldg(m.keys + slot);
+        if (k == key) {
+            int4 v = __ldg(m.vox + slot);
+            return make_int2(v.x, v.y);
+        }
+        if (k == kEmptyKey) return make_int2(0, 0);
+        slot = (slot + 1) & m.tmask;
+    }
+}
+
+constexpr uint64_t kInfKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kRankBits = 26;  // in-voxel index bits inside the tie-break rank
+
+// sorted insert of k into ascending t[0..4]
+__device__ __forceinline__ void top5_insert(uint64_t (&t)[5], uint64_t k) {
+    if (k < t[4]) {
+        t[4] = k;
+#pragma unroll
+        for (int i = 4; i > 0; --i) {
+            if (t[i] < t[i - 1]) {
+                uint64_t a = t[i];
+                t[i] = t[i - 1];
+                t[i - 1] = a;
+            }
+        }
+    }
+}
+
+// One query handled by a group of G lanes (G = 8): IVox::GetClosestPoint(pt, out, 5, max_range)
+// (ivox3d.h:132-204) + IVoxNode::KNNPointByCondition (ivox3d_node.hpp:140-205).
+// Candidate total order = (float d2 bits, stencil index, in-voxel index) — the "stable selection"
+// contract of SURVEY.md §7.  Returns the number found (0..5); win[] holds the composite keys in
+// ascending order on every lane of the group; lanes r < count also return winner r's pool entry.
+template <int G>
+__device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, float qz, int lg, unsigned gmask,
+                                          uint64_t (&win)[5], float4& mine) {
+    constexpr int SLOTS = (27 + G - 1) / G;
+    int cstart[SLOTS], ccount[SLOTS];
+    const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+        int s = lg + G * t;
+        cstart[t] = 0;
+        ccount[t] = 0;
+        if (s < m.nstencil) {
+            int cx = kx + c_stencil[s][0], cy = ky + c_stencil[s][1], cz = kz + c_stencil[s][2];
+            if (cell_in_range(cx, cy, cz)) {
+                int2 r = map_find(m, pack_key(cx, cy, cz));
+                cstart[t] = r.x;
+                ccount[t] = r.y;
+            }
+        }
+    }
+    uint64_t top[5] = {kInfKey, kInfKey, kInfKey, kInfKey, kInfKey};
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+        const int s = lg + G * t;
+        const float4* run = m.pool + cstart[t];
+        const int cnt = ccount[t];
+        for (int j = 0; j < cnt; ++j) {
+            float4 p = __ldg(run + j);
+            // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
+            float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < m.max_range2) {
+                uint64_t k = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)((s << kRankBits) | j);
+                top5_insert(top, k);
+            }
+        }
+    }
+    // merge the G sorted lists: 5 rounds of group-min + pop
+    int count = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        uint64_t mn = top[0];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            uint64_t other = __shfl_xor_sync(gmask, mn, o);
+            mn = other < mn ? other : mn;
+        }
+        win[r] = mn;
+        if (mn != kInfKey) {
+            ++count;
+            if (top[0] == mn) {
+                top[0] = top[1]; top[1] = top[2]; top[2] = top[3]; top[3] = top[4]; top[4] = kInfKey;
+            }
+        }
+    }
+    // fetch the winners: lane r loads winner r
+    mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    {
+        uint64_t w = win[0];
+#pragma unroll
+        for (int r = 1; r < 5; ++r)
+            if (lg == r) w = win[r];
+        const uint32_t lo = (uint32_t)w;
+        const int s = (int)(lo >> kRankBits), j = (int)(lo & ((1u << kRankBits) - 1));
+        const int owner = s % G, slot = s / G;
+        // every lane must take part in the shuffles
+        int st = 0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            int v = __shfl_sync(gmask, cstart[t], (owner & (G - 1)) + ((threadIdx.x & 31) / G) * G);
+            if (slot == t) st = v;
+        }
+        if (lg < 5 && w != kInfKey) mine = __ldg(m.pool + st + j);
+    }
+    return count;
+}
+
+// ------------------------------------------------------------------ host-side object
+struct Map {
+    b200_map_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float inv_res = 0.f;
+    int nstencil = 19;
+    uint32_t tsize = 0;
+    uint64_t* d_keys = nullptr;
+    int4* d_vox = nullptr;
+    float4* d_pool = nullptr;
+    uint64_t pool_cap = 0;
+    MapCounters* d_ctr = nullptr;
+    MapCounters h_ctr{};   // mirror after the last insert
+    int64_t next_ord = 0;
+    uint32_t stamp = 0;
+    // scratch
+    DevBuf<float4> in_pts;
+    DevBuf<uint64_t> k_in, k_out, k_uniq;
+    DevBuf<int32_t> v_in, v_out, run_cnt, run_off, run_dst, run_reloc, d_nruns;
+    DevBuf<uint8_t> cub_tmp;
+    PinnedBuf<float4> h_stage;
+    PinnedBuf<MapCounters> h_ctr_pin;
+    // knn scratch
+    DevBuf<int32_t> q_idx, q_cnt;
+    DevBuf<float> q_d2;
+
+    MapView view() const {
+        MapView v;
+        v.keys = d_keys; v.vox = d_vox; v.pool = d_pool; v.tmask = tsize - 1; v.inv_res = inv_res;
+        v.nstencil = nstencil; v.max_range2 = prm.max_range * prm.max_range;
+        return v;
+    }
+    int32_t init(const b200_map_params* p, int dev);
+    void destroy();
+    int32_t insert_device(const float4* d_pts, int64_t n);  // points already on the device (x,y,z,*)
+    int32_t insert_host(const float* xyz, int64_t n, int64_t stride);
+    int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt);
+    int32_t grow_pool(uint64_t min_cap);
+};
+
+}  // namespace b200
+
+struct b200_map { b200::Map m; };
