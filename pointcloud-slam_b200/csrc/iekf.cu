@@ -15,39 +15,16 @@
 #include "map.cuh"
 #include "manifold.cuh"
 #include "pointmath.cuh"
+#include "solve.cuh"
 
 #include <cub/cub.cuh>
 #include <vector>
 
 namespace b200 {
 
-constexpr int NS = 23;          // state DOF
-constexpr int NPART = 91;       // 78 + 12 + count
-constexpr int OBS_THREADS = 256;
+constexpr int OBS_THREADS = 512;
 constexpr int KNN_G = 8;        // lanes per query in a search pass
 constexpr int KNN_TILE = OBS_THREADS / KNN_G;
-
-struct Ctl {
-    // inputs (H2D header)
-    double x[26];
-    double P[NS * NS];
-    int n, prev_n;
-    int pad0[2];
-    // loop state
-    double x_prop[26];
-    double P_prop[NS * NS];
-    int iter;      // loop variable i of esekfom.hpp:1539
-    int converge;  // dyn_share.converge
-    int done;
-    int t;
-    // stats
-    int passes, knn_passes, any_valid, converged;
-    int n_eff[B200_MAX_PASSES], knn[B200_MAX_PASSES];
-    PassConsts pc;
-    double x_in[B200_MAX_PASSES][26];
-    double HtH[B200_MAX_PASSES][144];
-    double Hth[B200_MAX_PASSES][12];
-};
 
 struct PointState {  // per-point arrays that persist across passes and scans (laser_mapping.cc:335-339)
     float4* plane;   // plane_coef_
@@ -56,26 +33,6 @@ struct PointState {  // per-point arrays that persist across passes and scans (l
     uint8_t* nn_cnt; // nearest_points_[i].size()
     float4* nn;      // nearest_points_[i][0..4] (xyz + ordinal)
 };
-
-__constant__ unsigned char c_pair_a[78];
-__constant__ unsigned char c_pair_b[78];
-
-__device__ inline void make_pass_consts(const double* x, PassConsts& pc) {
-    using namespace mf;
-    const Q rot = ldq(x + 3), offR = ldq(x + 7);
-    const Q qd = qmul(rot, offR);
-    pc.qx = (float)qd.x; pc.qy = (float)qd.y; pc.qz = (float)qd.z; pc.qw = (float)qd.w;
-    double td[3];
-    qrot(rot, x + 11, td);
-    pc.tx = (float)(td[0] + x[0]); pc.ty = (float)(td[1] + x[1]); pc.tz = (float)(td[2] + x[2]);
-    double Ro[9], Rr[9];
-    qtoR(offR, Ro);
-    qtoR(rot, Rr);
-    for (int i = 0; i < 9; ++i) pc.offR[i] = (float)Ro[i];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) pc.Rt[i * 3 + j] = (float)Rr[j * 3 + i];
-    for (int i = 0; i < 3; ++i) pc.offt[i] = (float)x[11 + i];
-}
 
 // ------------------------------------------------------------------ init
 // hdr: the {x, P, n, prev_n} header as it arrived from the host (either inside the staged scan block or
@@ -101,6 +58,7 @@ __global__ void k_iekf_init(Ctl* ctl, const Ctl* hdr, PointState ps, int force_c
             ctl->converge = force_converge;
             ctl->done = 0;
             ctl->t = 0;
+            ctl->ticket = 0;
             ctl->passes = ctl->knn_passes = ctl->any_valid = ctl->converged = 0;
             for (int i = 0; i < B200_MAX_PASSES; ++i) { ctl->n_eff[i] = 0; ctl->knn[i] = 0; }
             make_pass_consts(ctl->x, ctl->pc);
@@ -167,10 +125,36 @@ struct ObsSmem {
     int nbc[KNN_TILE];
 };
 
-__global__ void __launch_bounds__(OBS_THREADS) k_obs(MapView map, const float4* __restrict__ scan, PointState ps, const Ctl* __restrict__ ctl,
-                                                     float thr, int ext, double* __restrict__ partials) {
+union ObsSolveSmem {
+    ObsSmem obs;
+    SolveSmem solve;
+};
+
+// One IEKF pass = one launch.  Block 0 is the filter block: it prepares the state-only half of the
+// filter step while blocks 1.. measure the scan and publish fp64 partial sums, waits for their
+// tickets, then finishes the step.  (Blocks 1.. never wait on block 0, so there is no deadlock; with
+// one block per SM every block of the grid is resident.)
+__global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(MapView map, const float4* __restrict__ scan, PointState ps, Ctl* ctl, float thr,
+                                                        int ext, double* partials, int max_iter, double Rcov,
+                                                        const double* __restrict__ limit, int single_pass) {
     if (ctl->done) return;
-    __shared__ ObsSmem sm;
+    __shared__ ObsSolveSmem smu;
+    if (blockIdx.x == 0) {
+        const int nworkers = (int)gridDim.x - 1;
+        if (!single_pass) iekf_presolve(ctl, Rcov, ext, smu.solve);
+        else if (threadIdx.x < 26) smu.solve.x[threadIdx.x] = ctl->x[threadIdx.x];
+        if (threadIdx.x == 0) {
+            volatile unsigned int* tk = &ctl->ticket;
+            while (*tk < (unsigned)nworkers) __nanosleep(100);
+            ctl->ticket = 0;
+        }
+        __syncthreads();
+        __threadfence();
+        iekf_postsolve(ctl, partials, nworkers, max_iter, limit, ext, single_pass, smu.solve);
+        return;
+    }
+    const int wblock = (int)blockIdx.x - 1, wgrid = (int)gridDim.x - 1;  // worker index / count
+    ObsSmem& sm = smu.obs;
     const int tid = threadIdx.x;
     const int n = ctl->n;
     const bool searched = ctl->converge != 0;
@@ -178,17 +162,19 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(MapView map, const float4* 
     if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
     __syncthreads();
 
-    // accumulator of this thread's (a,b) pair / h column across all tiles of the block
+    // Accumulators: the block's queries are cut into NSLICE contiguous slices per tile; thread
+    // (slice, col) owns column col (78 HTH pairs, 12 HTh entries, 1 count) of its slice across all tiles.
+    constexpr int NSLICE = OBS_THREADS / NPART;  // 5
+    const int slice = tid / NPART, col = tid % NPART;
     double acc = 0.0;
     int pa = 0, pb_ = 0;
-    const int npairs = 78;
-    if (tid < npairs) { pa = c_pair_a[tid]; pb_ = c_pair_b[tid]; }
-    else if (tid < 90) { pa = tid - 78; pb_ = 12; }
-    const bool pair_active = tid < 90 && (ext || (pa < 6 && (pb_ < 6 || pb_ == 12)));
-    int cnt_acc = 0;
+    if (col < 78) { pa = c_pair_a[col]; pb_ = c_pair_b[col]; }
+    else if (col < 90) { pa = col - 78; pb_ = 12; }
+    const bool slice_active = slice < NSLICE;
+    const bool pair_active = slice_active && col < 90 && (ext || (pa < 6 && (pb_ < 6 || pb_ == 12)));
 
     const int tile = searched ? KNN_TILE : OBS_THREADS;
-    for (int base = blockIdx.x * tile; base < n; base += gridDim.x * tile) {
+    for (int base = wblock * tile; base < n; base += wgrid * tile) {
         int q_here;  // queries in this tile
         if (searched) {
             // phase 1: 8 lanes per query search the stencil
@@ -225,295 +211,33 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs(MapView map, const float4* 
             }
         }
         __syncthreads();
-        // phase 3: fp64 accumulation in query order (deterministic)
-        if (pair_active) {
-            for (int q = 0; q < q_here; ++q)
-                if (sm.eff[q]) acc += (double)sm.rows[q][pa] * (double)sm.rows[q][pb_];
-        } else if (tid == 90) {
-            for (int q = 0; q < q_here; ++q) cnt_acc += sm.eff[q];
-        }
-        __syncthreads();
-    }
-    // column-major by block so the solve kernel reads each column coalesced
-    if (tid < 90) partials[(size_t)tid * gridDim.x + blockIdx.x] = acc;
-    if (tid == 90) partials[(size_t)90 * gridDim.x + blockIdx.x] = (double)cnt_acc;
-}
-
-// ------------------------------------------------------------------ solve
-struct SolveSmem {
-    double P[NS * NS];
-    double L[NS * NS];
-    double aug[NS * 2 * NS];
-    double HTH[144];
-    double HTh[12];
-    double Kx[NS * 12];
-    double Kh[NS];
-    double dx[NS], dxn[NS], dxu[NS];
-    double prow[2 * NS], scol[NS];
-    double J3[2][9];  // A(dx)^T for rot / offR
-    double J2[4];     // Nx * Mx for grav
-    int piv;
-    int n_eff;
-    int finalize;
-};
-
-// in-place inverse of the NS x NS matrix M (row-major, shared) by Gauss-Jordan with partial pivoting
-__device__ void block_inverse(double* M, SolveSmem& s) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    constexpr int W = 2 * NS;
-    for (int idx = tid; idx < NS * W; idx += nt) {
-        int r = idx / W, c = idx % W;
-        s.aug[idx] = c < NS ? M[r * NS + c] : (c - NS == r ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    for (int k = 0; k < NS; ++k) {
-        if (tid < 32) {
-            double v = -1.0;
-            int r = k + tid;
-            if (r < NS) v = fabs(s.aug[r * W + k]);
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                int orr = __shfl_xor_sync(0xffffffffu, r, o);
-                if (ov > v || (ov == v && orr < r)) { v = ov; r = orr; }
-            }
-            if (tid == 0) s.piv = r;
-        }
-        __syncthreads();
-        const int p = s.piv;
-        if (p != k && tid < W) {
-            double a = s.aug[k * W + tid];
-            s.aug[k * W + tid] = s.aug[p * W + tid];
-            s.aug[p * W + tid] = a;
-        }
-        __syncthreads();
-        const double pivot = s.aug[k * W + k];
-        if (tid < W) s.prow[tid] = s.aug[k * W + tid] / pivot;
-        else if (tid >= 64 && tid < 64 + NS) s.scol[tid - 64] = s.aug[(tid - 64) * W + k];
-        __syncthreads();
-        for (int idx = tid; idx < NS * W; idx += nt) {
-            int r = idx / W, c = idx % W;
-            s.aug[idx] = (r == k) ? s.prow[c] : s.aug[idx] - s.scol[r] * s.prow[c];
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < NS * NS; idx += nt) {
-        int r = idx / NS, c = idx % NS;
-        M[idx] = s.aug[r * W + NS + c];
-    }
-    __syncthreads();
-}
-
-// M <- J M (rows idx..idx+d-1) for the block-diagonal J made of J3[0] (3), J3[1] (6), J2 (21)
-__device__ void project_rows(double* dst, const double* src, const SolveSmem& s, int which /*0,1 SO3; 2 S2*/, int ncols_stride) {
-    const int tid = threadIdx.x;
-    if (tid >= NS) return;
-    const int c = tid;
-    if (which < 2) {
-        const int idx = which == 0 ? 3 : 6;
-        const double* J = s.J3[which];
-        double a = src[idx * ncols_stride + c], b = src[(idx + 1) * ncols_stride + c], d = src[(idx + 2) * ncols_stride + c];
-        for (int r = 0; r < 3; ++r) dst[(idx + r) * ncols_stride + c] = J[r * 3] * a + J[r * 3 + 1] * b + J[r * 3 + 2] * d;
-    } else {
-        const int idx = 21;
-        double a = src[idx * ncols_stride + c], b = src[(idx + 1) * ncols_stride + c];
-        dst[idx * ncols_stride + c] = s.J2[0] * a + s.J2[1] * b;
-        dst[(idx + 1) * ncols_stride + c] = s.J2[2] * a + s.J2[3] * b;
-    }
-}
-// M <- M J^T (columns idx..)
-__device__ void project_cols(double* M, const SolveSmem& s, int which) {
-    const int tid = threadIdx.x;
-    if (tid >= NS) return;
-    const int i = tid;
-    if (which < 2) {
-        const int idx = which == 0 ? 3 : 6;
-        const double* J = s.J3[which];
-        double a = M[i * NS + idx], b = M[i * NS + idx + 1], d = M[i * NS + idx + 2];
-        for (int r = 0; r < 3; ++r) M[i * NS + idx + r] = a * J[r * 3] + b * J[r * 3 + 1] + d * J[r * 3 + 2];
-    } else {
-        const int idx = 21;
-        double a = M[i * NS + idx], b = M[i * NS + idx + 1];
-        M[i * NS + idx] = a * s.J2[0] + b * s.J2[1];
-        M[i * NS + idx + 1] = a * s.J2[2] + b * s.J2[3];
-    }
-}
-
-// thread 0: Jacobians of the (+)/(-) re-linearisation for a tangent increment d (esekfom.hpp:1561-1601 / 1739-1789)
-__device__ void make_projection(SolveSmem& s, const double* d, const double* x_cur, const double* x_prop) {
-    for (int k = 0; k < 2; ++k) {
-        double A[9];
-        mf::A_matrix(d + (k == 0 ? 3 : 6), A);
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) s.J3[k][r * 3 + c] = A[c * 3 + r];
-    }
-    double Nx[6], Mx[6];
-    mf::S2_Nx_yy(x_cur + 23, Nx);
-    mf::S2_Mx(x_prop + 23, d + 21, Mx);
-    for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 2; ++c) s.J2[r * 2 + c] = Nx[r * 3] * Mx[c] + Nx[r * 3 + 1] * Mx[2 + c] + Nx[r * 3 + 2] * Mx[4 + c];
-}
-
-__global__ void __launch_bounds__(256) k_solve(Ctl* ctl, const double* __restrict__ partials, int nblocks, int max_iter, double Rcov,
-                                                const double* __restrict__ limit, int single_pass) {
-    if (ctl->done) return;
-    __shared__ SolveSmem s;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // 1. deterministic reduction of the per-block partial sums
-    //    (warp w owns columns w, w+8, ...; lane-strided sums in block order, then a fixed shuffle tree)
-    for (int col = tid / 32; col < NPART; col += nt / 32) {
-        double sum = 0.0;
-        for (int b = tid % 32; b < nblocks; b += 32) sum += partials[(size_t)col * nblocks + b];
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (tid % 32 == 0) {
-            if (col < 78) {
-                int a = c_pair_a[col], b = c_pair_b[col];
-                s.HTH[a * 12 + b] = sum;
-                s.HTH[b * 12 + a] = sum;
-            } else if (col < 90) {
-                s.HTh[col - 78] = sum;
-            } else {
-                s.n_eff = (int)(sum + 0.5);
+        // phase 3: fp64 accumulation, fixed slice boundaries and query order (deterministic)
+        {
+            const int per = (q_here + NSLICE - 1) / NSLICE;
+            const int q0 = slice * per, q1 = min(q_here, q0 + per);
+            if (pair_active) {
+                for (int q = q0; q < q1; ++q)
+                    if (sm.eff[q]) acc += (double)sm.rows[q][pa] * (double)sm.rows[q][pb_];
+            } else if (slice_active && col == 90) {
+                for (int q = q0; q < q1; ++q) acc += (double)sm.eff[q];
             }
         }
-    }
-    __syncthreads();
-    const int pass = ctl->passes;
-    const int conv_in = ctl->converge;
-    const int iter = ctl->iter;
-    if (pass < B200_MAX_PASSES) {
-        for (int i = tid; i < 144; i += nt) ctl->HtH[pass][i] = s.HTH[i];
-        if (tid < 12) ctl->Hth[pass][tid] = s.HTh[tid];
-        if (tid < 26) ctl->x_in[pass][tid] = ctl->x[tid];
-        if (tid == 0) { ctl->n_eff[pass] = s.n_eff; ctl->knn[pass] = conv_in; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        ctl->passes = pass + 1;
-        ctl->knn_passes += conv_in ? 1 : 0;
-    }
-    if (single_pass) {  // parity primitive: one ObsModel evaluation, no filter step
-        if (tid == 0) ctl->done = 1;
-        return;
-    }
-    if (s.n_eff < 1) {  // ekfom_data.valid == false -> `continue` (esekfom.hpp:1543-1545)
-        if (tid == 0) {
-            ctl->iter = iter + 1;
-            if (iter + 1 >= max_iter) ctl->done = 1;
-        }
-        return;
-    }
-    // 2. dx = x (-) x_prop and the projection Jacobians
-    if (tid == 0) {
-        ctl->any_valid = 1;
-        mf::state_boxminus(ctl->x, ctl->x_prop, s.dx);
-        make_projection(s, s.dx, ctl->x, ctl->x_prop);
-        for (int i = 0; i < NS; ++i) s.dxn[i] = s.dx[i];
-        for (int k = 0; k < 2; ++k) {
-            const int idx = k == 0 ? 3 : 6;
-            double a = s.dxn[idx], b = s.dxn[idx + 1], c = s.dxn[idx + 2];
-            for (int r = 0; r < 3; ++r) s.dxn[idx + r] = s.J3[k][r * 3] * a + s.J3[k][r * 3 + 1] * b + s.J3[k][r * 3 + 2] * c;
-        }
-        double a = s.dxn[21], b = s.dxn[22];
-        s.dxn[21] = s.J2[0] * a + s.J2[1] * b;
-        s.dxn[22] = s.J2[2] * a + s.J2[3] * b;
-    }
-    for (int i = tid; i < NS * NS; i += nt) s.P[i] = ctl->P_prop[i];
-    __syncthreads();
-    // 3. P = J P_prop J^T, block by block as the reference does (rows then columns of each block)
-    for (int which = 0; which < 3; ++which) {
-        project_rows(s.P, s.P, s, which, NS);
-        __syncthreads();
-        project_cols(s.P, s, which);
         __syncthreads();
     }
-    // 4. P_inv = ((P / R)^-1 + [HTH 0; 0 0])^-1   (esekfom.hpp:1685-1706)
-    for (int i = tid; i < NS * NS; i += nt) s.L[i] = s.P[i] / Rcov;
+    // combine the slices in a fixed order, then publish column-major by block so the filter block
+    // reads each column coalesced
+    double* red = (double*)&sm.rows[0][0];
+    if (slice_active) red[slice * NPART + col] = acc;
     __syncthreads();
-    block_inverse(s.L, s);
-    for (int i = tid; i < 144; i += nt) s.L[(i / 12) * NS + (i % 12)] += s.HTH[i];
-    __syncthreads();
-    block_inverse(s.L, s);
-    // 5. K_h = P_inv[:, :12] H^T h ; K_x[:, :12] = P_inv[:, :12] HTH   (:1708-1713)
-    for (int idx = tid; idx < NS * 13; idx += nt) {
-        const int r = idx / 13, c = idx % 13;
-        double sum = 0.0;
-        if (c < 12) {
-            for (int k = 0; k < 12; ++k) sum += s.L[r * NS + k] * s.HTH[k * 12 + c];
-            s.Kx[r * 12 + c] = sum;
-        } else {
-            for (int k = 0; k < 12; ++k) sum += s.L[r * NS + k] * s.HTh[k];
-            s.Kh[r] = sum;
-        }
+    if (tid < NPART) {
+        double v = red[tid];
+#pragma unroll
+        for (int sl = 1; sl < NSLICE; ++sl) v += red[sl * NPART + tid];
+        __stcg(partials + (size_t)tid * wgrid + wblock, v);
     }
+    __threadfence();
     __syncthreads();
-    // 6. dx_ = K_h + (K_x - I) dx_new   (:1719)
-    if (tid < NS) {
-        double sum = 0.0;
-        for (int c = 0; c < NS; ++c) {
-            double kx = c < 12 ? s.Kx[tid * 12 + c] : 0.0;
-            sum += (kx - (c == tid ? 1.0 : 0.0)) * s.dxn[c];
-        }
-        s.dxu[tid] = s.Kh[tid] + sum;
-    }
-    __syncthreads();
-    // 7. x (+)= dx_ ; convergence bookkeeping (:1720-1735)
-    if (tid == 0) {
-        mf::state_boxplus(ctl->x, s.dxu);
-        int conv = 1;
-        for (int i = 0; i < NS; ++i)
-            if (fabs(s.dxu[i]) > limit[i]) { conv = 0; break; }
-        int t = ctl->t;
-        if (conv) t++;
-        if (!t && iter == max_iter - 2) conv = 1;
-        ctl->t = t;
-        ctl->converge = conv;
-        s.finalize = (t > 1 || iter == max_iter - 1) ? 1 : 0;
-        if (s.finalize) make_projection(s, s.dxu, ctl->x, ctl->x_prop);
-    }
-    __syncthreads();
-    if (s.finalize) {  // :1735-1831
-        for (int i = tid; i < NS * NS; i += nt) s.L[i] = s.P[i];
-        __syncthreads();
-        for (int which = 0; which < 3; ++which) {
-            project_rows(s.L, s.P, s, which, NS);  // L rows <- J * P rows
-            if (tid >= 32 && tid < 32 + 12) {      // K_x rows <- J * K_x rows
-                const int c = tid - 32;
-                if (which < 2) {
-                    const int idx = which == 0 ? 3 : 6;
-                    const double* J = s.J3[which];
-                    double a = s.Kx[idx * 12 + c], b = s.Kx[(idx + 1) * 12 + c], d = s.Kx[(idx + 2) * 12 + c];
-                    for (int r = 0; r < 3; ++r) s.Kx[(idx + r) * 12 + c] = J[r * 3] * a + J[r * 3 + 1] * b + J[r * 3 + 2] * d;
-                } else {
-                    double a = s.Kx[21 * 12 + c], b = s.Kx[22 * 12 + c];
-                    s.Kx[21 * 12 + c] = s.J2[0] * a + s.J2[1] * b;
-                    s.Kx[22 * 12 + c] = s.J2[2] * a + s.J2[3] * b;
-                }
-            }
-            __syncthreads();
-            project_cols(s.L, s, which);
-            __syncthreads();
-            project_cols(s.P, s, which);
-            __syncthreads();
-        }
-        for (int idx = tid; idx < NS * NS; idx += nt) {
-            const int r = idx / NS, c = idx % NS;
-            double sum = 0.0;
-            for (int k = 0; k < 12; ++k) sum += s.Kx[r * 12 + k] * s.P[k * NS + c];
-            ctl->P[idx] = s.L[idx] - sum;
-        }
-        if (tid == 0) {
-            ctl->done = 1;
-            ctl->converged = ctl->t > 1 ? 1 : 0;
-        }
-    } else {
-        // the covariance the filter holds when the loop ends without finalising is the projected P_
-        for (int i = tid; i < NS * NS; i += nt) ctl->P[i] = s.P[i];
-        if (tid == 0) {
-            ctl->iter = iter + 1;
-            make_pass_consts(ctl->x, ctl->pc);
-            if (iter + 1 >= max_iter) ctl->done = 1;
-        }
-    }
+    if (tid == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
 // ------------------------------------------------------------------ MapIncremental (laser_mapping.cc:525-583)
@@ -615,7 +339,8 @@ int32_t Iekf::init(const b200_iekf_params* p, Map* m) {
     CUDA_TRY(cudaMemcpy(d_limit, prm.limit, sizeof(double) * NS, cudaMemcpyHostToDevice));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, m->device));
-    nblocks = prop.multiProcessorCount * 4;
+    nblocks = prop.multiProcessorCount;
+    if (nblocks > MAXB) nblocks = MAXB;
     CUDA_TRY(cudaMalloc(&d_partials, sizeof(double) * NPART * nblocks));
     CUDA_TRY(h_out.reserve(1));
     CUDA_TRY(cudaEventCreate(&ev0));
@@ -684,10 +409,10 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
     const MapView mv = map->view();
     const int npass = single_pass ? 1 : prm.max_iter + 1;
     for (int it = 0; it < npass; ++it) {
-        k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(mv, d_pts, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials);
-        k_solve<<<1, 256, 0, stream>>>(d_ctl, d_partials, nblocks, prm.max_iter, prm.R, d_limit, single_pass);
+        k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(mv, d_pts, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials, prm.max_iter,
+                                                   prm.R, d_limit, single_pass);
     }
-    LAUNCH_COUNT(1 + 2 * npass);
+    LAUNCH_COUNT(1 + npass);
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_out.p, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
@@ -774,6 +499,12 @@ int32_t b200_iekf_last_HtH(b200_iekf* ekf, int32_t pass, double* HtH, double* Ht
     if (HtH) memcpy(HtH, o.HtH[pass], sizeof(double) * 144);
     if (Hth) memcpy(Hth, o.Hth[pass], sizeof(double) * 12);
     if (x_in) memcpy(x_in, o.x_in[pass], sizeof(double) * 26);
+    return B200_OK;
+}
+
+int32_t b200_iekf_debug_stamps(b200_iekf* ekf, long long* out /*[B200_MAX_PASSES*16]*/) {
+    if (!ekf || !out) B200_FAIL(B200_ERR_ARG, "bad argument");
+    memcpy(out, ekf->k.h_out.p->dbg, sizeof(long long) * B200_MAX_PASSES * 16);
     return B200_OK;
 }
 
