@@ -262,8 +262,8 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
 }
 
 int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
-    if (n < 0 || (n > 0 && !xyz) || stride < 12) B200_FAIL(B200_ERR_ARG, "bad point buffer");
     if (n == 0) return B200_OK;
+    if (n < 0 || !xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "bad point buffer");
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(h_stage.reserve(n));
     CUDA_TRY(in_pts.reserve(n));
@@ -273,8 +273,8 @@ int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
 }
 
 int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt) {
-    if (n < 0 || (n > 0 && (!xyz || !idx || !d2 || !cnt)) || stride < 12) B200_FAIL(B200_ERR_ARG, "bad query buffer");
     if (n == 0) return B200_OK;
+    if (n < 0 || !xyz || !idx || !d2 || !cnt || stride < 12) B200_FAIL(B200_ERR_ARG, "bad query buffer");
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(h_stage.reserve(n));
     CUDA_TRY(in_pts.reserve(n));

@@ -1,0 +1,45 @@
+"""The C-ABI library loads and exports every symbol include/b200reg.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, have_gpu
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200reg.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ["b200_map_create", "b200_map_insert", "b200_map_knn5", "b200_iekf_update", "b200_iekf_map_incremental",
+              "b200_ndt_set_target", "b200_ndt_align", "b200_ndt_derivatives", "b200_ndt_score_batch", "b200_reloc_argmin"]:
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(api):
+    lib = ctypes.CDLL(api.lib_path())
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"libb200reg.so does not export: {missing}"
+
+
+def test_version_string(api):
+    assert b"sm_100a" in api.lib().b200_version()
+
+
+@pytest.mark.skipif(have_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_fails_loudly(api):
+    """There is no CPU fallback: without a device create() must return an error, not a working handle."""
+    with pytest.raises(api.B200Error):
+        api.IVox(resolution=0.5, nearby=18)
+
+
+def test_bad_arguments_are_rejected(api):
+    lib = api.lib()
+    assert lib.b200_map_create(None, 0, None) == -1  # B200_ERR_ARG
+    assert lib.b200_map_insert(None, None, 0, 12) == -1
+    assert b"null" in lib.b200_last_error()
