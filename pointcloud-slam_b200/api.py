@@ -93,6 +93,12 @@ def lib():
     L.b200_iekf_obs_model.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, vp]
     L.b200_iekf_point_state.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.b200_iekf_map_incremental.argtypes = [vp, vp, i32, vp, vp]
+    L.b200_iekf_set_profiling.argtypes = [vp, i32]
+    L.b200_iekf_set_graph.argtypes = [vp, i32]
+    L.b200_iekf_kernel_times.argtypes = [vp, vp, i32]
+    L.b200_iekf_io_bytes.argtypes = [vp, i64, vp, vp]
+    L.b200_map_stencil_points.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.b200_flush_l2.argtypes = [i32]
     if hasattr(L, "b200_ndt_create"):
         L.b200_ndt_create.argtypes = [C.POINTER(NdtParams), i32, C.POINTER(vp)]
         L.b200_ndt_destroy.argtypes = [vp]
@@ -132,6 +138,10 @@ def _cloud(a):
     return a
 
 
+def flush_l2(device=0):
+    _check(lib().b200_flush_l2(device))
+
+
 def kernel_launches() -> int:
     return int(lib().b200_kernel_launches())
 
@@ -164,6 +174,13 @@ class IVox:
         cnt = np.empty(n, np.int32)
         _check(lib().b200_map_knn5(self.h, _p(q), n, q.strides[0], _p(idx), _p(d2), _p(cnt)))
         return idx, d2, cnt
+
+    def stencil_points(self, points):
+        """(sum of map points, occupied cells) over the stencils of the queries — roofline bookkeeping."""
+        q = _cloud(points)
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(lib().b200_map_stencil_points(self.h, _p(q), q.shape[0], q.strides[0], C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def NumValidGrids(self) -> int:
         return int(lib().b200_map_num_voxels(self.h))
@@ -215,6 +232,25 @@ class Esekf:
         self._n = scan.shape[0]
         rc = lib().b200_iekf_update(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(self.x), _p(self.P), C.byref(self.stats))
         return _check(rc, soft=(0, 1))
+
+    def update_device(self, d_scan_ptr, n):
+        """Same update with the scan already on the device (float4 per point)."""
+        self._n = n
+        rc = lib().b200_iekf_update_device(self.h, C.c_void_p(d_scan_ptr), n, _p(self.x), _p(self.P), C.byref(self.stats))
+        return _check(rc, soft=(0, 1))
+
+    def set_profiling(self, on):
+        _check(lib().b200_iekf_set_profiling(self.h, int(on)))
+
+    def kernel_times_ms(self):
+        ms = (C.c_float * 17)()
+        k = lib().b200_iekf_kernel_times(self.h, ms, 17)
+        return [ms[i] for i in range(k)]
+
+    def io_bytes(self, n):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(lib().b200_iekf_io_bytes(self.h, n, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_HtH(self, p):
         HtH = np.zeros((12, 12))

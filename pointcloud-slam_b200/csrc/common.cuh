@@ -97,13 +97,12 @@ __host__ __device__ inline bool cell_in_range(int x, int y, int z) {
 __host__ __device__ inline uint64_t pack_key(int x, int y, int z) {
     return ((uint64_t)(uint32_t)(x + kKeyBias) << 42) | ((uint64_t)(uint32_t)(y + kKeyBias) << 21) | (uint64_t)(uint32_t)(z + kKeyBias);
 }
-__host__ __device__ inline uint32_t hash_key(uint64_t k) {  // murmur3 finalizer
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return (uint32_t)k;
+__host__ __device__ inline uint32_t hash_key(uint64_t k) {  // 32-bit multiply-xorshift mix of the two key halves
+    uint32_t h = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
 }
 
 // Pass a strided host cloud through a pinned staging buffer as packed float4 (x,y,z,0).

@@ -118,12 +118,34 @@ __device__ __forceinline__ bool point_measure(const PassConsts& pc, const float4
     return sel;
 }
 
+constexpr int QCAP = 256;  // queries a worker block handles per round (20k-point scan / 147 workers = 137)
 struct ObsSmem {
-    float rows[OBS_THREADS][13];
-    unsigned char eff[OBS_THREADS];
-    float4 nb[KNN_TILE][5];
-    int nbc[KNN_TILE];
+    float rows[QCAP][13];
+    unsigned char eff[QCAP];
 };
+
+// Stencil search of a pass (dyn_share.converge == true): 8 lanes per scan point, one wave over the
+// whole scan at high occupancy.  Results go to a scratch array that k_obs consumes; the kernel is a
+// no-op when the pass reuses the previous neighbours (decided on the device).
+__global__ void __launch_bounds__(256, 5) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+                                                float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
+    if (ctl->done || !ctl->converge) return;
+    __shared__ PassConsts pc;
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
+    __syncthreads();
+    const int n = ctl->n;
+    const int q = (blockIdx.x * blockDim.x + tid) / KNN_G, lg = tid % KNN_G;
+    if (q >= n) return;
+    const unsigned gmask = ((1u << KNN_G) - 1u) << ((tid & 31) / KNN_G * KNN_G);
+    const float4 pbody = __ldg(scan + q);
+    const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
+    uint64_t win[5];
+    float4 mine;
+    const int c = knn5_group<KNN_G>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), win, mine);
+    if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
+    if (lg == 0) nbc_out[q] = (unsigned char)c;
+}
 
 union ObsSolveSmem {
     ObsSmem obs;
@@ -134,19 +156,27 @@ union ObsSolveSmem {
 // filter step while blocks 1.. measure the scan and publish fp64 partial sums, waits for their
 // tickets, then finishes the step.  (Blocks 1.. never wait on block 0, so there is no deadlock; with
 // one block per SM every block of the grid is resident.)
-__global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(MapView map, const float4* __restrict__ scan, PointState ps, Ctl* ctl, float thr,
+__global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict__ scan, const float4* __restrict__ nb_new,
+                                                        const unsigned char* __restrict__ nbc_new, PointState ps, Ctl* ctl, float thr,
                                                         int ext, double* partials, int max_iter, double Rcov,
                                                         const double* __restrict__ limit, int single_pass) {
     if (ctl->done) return;
     __shared__ ObsSolveSmem smu;
     if (blockIdx.x == 0) {
         const int nworkers = (int)gridDim.x - 1;
+        const int pass_f = ctl->passes;
+        const long long tf0 = clock64();
         if (!single_pass) iekf_presolve(ctl, Rcov, ext, smu.solve);
         else if (threadIdx.x < 26) smu.solve.x[threadIdx.x] = ctl->x[threadIdx.x];
+        const long long tf1 = clock64();
         if (threadIdx.x == 0) {
             volatile unsigned int* tk = &ctl->ticket;
             while (*tk < (unsigned)nworkers) __nanosleep(100);
             ctl->ticket = 0;
+            if (pass_f < B200_MAX_PASSES) {
+                ctl->dbg[pass_f][8] = tf1 - tf0;         // presolve cycles
+                ctl->dbg[pass_f][9] = clock64() - tf1;   // wait-for-workers cycles
+            }
         }
         __syncthreads();
         __threadfence();
@@ -173,35 +203,20 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(MapView map, const float
     const bool slice_active = slice < NSLICE;
     const bool pair_active = slice_active && col < 90 && (ext || (pa < 6 && (pb_ < 6 || pb_ == 12)));
 
-    const int tile = searched ? KNN_TILE : OBS_THREADS;
-    for (int base = wblock * tile; base < n; base += wgrid * tile) {
-        int q_here;  // queries in this tile
-        if (searched) {
-            // phase 1: 8 lanes per query search the stencil
-            const int ql = tid / KNN_G, lg = tid % KNN_G;
-            const int i = base + ql;
-            if (i < n) {
-                const unsigned gmask = ((1u << KNN_G) - 1u) << ((tid & 31) / KNN_G * KNN_G);
-                const float4 pbody = __ldg(scan + i);
-                const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
-                uint64_t win[5];
-                float4 mine;
-                const int c = knn5_group<KNN_G>(map, pw.x, pw.y, pw.z, lg, gmask, win, mine);
-                if (lg < 5) sm.nb[ql][lg] = mine;
-                if (lg == 0) sm.nbc[ql] = c;
-            }
-            __syncthreads();
-            q_here = min(KNN_TILE, n - base);
-        } else {
-            q_here = min(OBS_THREADS, n - base);
-        }
+    long long tw0 = clock64(), tw1 = tw0, tw2 = tw0, tw3 = tw0;
+    // each worker owns one contiguous chunk of the scan, processed in rounds of <= QCAP queries
+    const int chunk = (n + wgrid - 1) / wgrid;
+    const int c_begin = wblock * chunk, c_end = min(n, c_begin + chunk);
+    for (int base = c_begin; base < c_end; base += QCAP) {
+        const int q_here = min(QCAP, c_end - base);
+        tw1 = clock64();
         // phase 2: one thread per query
         if (tid < q_here) {
             const int i = base + tid;
             const float4 pbody = __ldg(scan + i);
             const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
             float row[12], h = 0.f;
-            const bool eff = point_measure(pc, pbody, pw, searched, searched ? sm.nbc[tid] : 0, sm.nb[searched ? tid : 0], ps, i, thr,
+            const bool eff = point_measure(pc, pbody, pw, searched, searched ? (int)nbc_new[i] : 0, nb_new + (size_t)i * 5, ps, i, thr,
                                            ext != 0, row, h);
             sm.eff[tid] = eff ? 1 : 0;
             if (eff) {
@@ -211,6 +226,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(MapView map, const float
             }
         }
         __syncthreads();
+        tw2 = clock64();
         // phase 3: fp64 accumulation, fixed slice boundaries and query order (deterministic)
         {
             const int per = (q_here + NSLICE - 1) / NSLICE;
@@ -237,6 +253,15 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(MapView map, const float
     }
     __threadfence();
     __syncthreads();
+    tw3 = clock64();
+    if (tid == 0 && wblock == 0) {
+        const int pw_ = ctl->passes;
+        if (pw_ < B200_MAX_PASSES) {
+            ctl->dbg[pw_][10] = tw1 - tw0;  // search phase (last round)
+            ctl->dbg[pw_][11] = tw2 - tw1;  // measure phase
+            ctl->dbg[pw_][12] = tw3 - tw2;  // accumulate + publish
+        }
+    }
     if (tid == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
@@ -296,12 +321,32 @@ struct Iekf {
     int nblocks = 0;
     PointState ps{};
     size_t ps_cap = 0;
-    DevBuf<float4> d_scan;
+    DevBuf<float4> d_scan, d_nb;
+    DevBuf<unsigned char> d_nbc;
     int last_n = 0;       // size the per-point arrays were last resized to
     const float4* last_scan = nullptr;
     PinnedBuf<uint8_t> h_stage;  // [Ctl header | float4 points]
     PinnedBuf<Ctl> h_out;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // the kernel sequence of one update is captured once into a CUDA graph and replayed (the control flow
+    // lives on the device, so the sequence never changes); re-captured only when a buffer moves
+    struct GraphKey {
+        const void *pts, *hdr, *ent, *pool, *plane, *nb;
+        unsigned search_grid;
+        int single, force;
+        bool operator==(const GraphKey& o) const {
+            return pts == o.pts && hdr == o.hdr && ent == o.ent && pool == o.pool && plane == o.plane && nb == o.nb &&
+                   search_grid == o.search_grid && single == o.single && force == o.force;
+        }
+    };
+    GraphKey gkey{};
+    cudaGraphExec_t gexec = nullptr;
+    int use_graph = 1;
+    int profiling = 0;  // record an event after every kernel (disables the graph path)
+    cudaEvent_t evk[2 * B200_MAX_PASSES + 2] = {};
+    float kernel_ms[2 * B200_MAX_PASSES + 1] = {};
+    int n_kernels = 0;
+    int32_t enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_grid, int single_pass, int force_converge, bool events);
     // map-incremental scratch
     DevBuf<float4> d_world, d_sel_pts;
     DevBuf<uint8_t> d_flag, d_flag2, cub_tmp;
@@ -345,6 +390,7 @@ int32_t Iekf::init(const b200_iekf_params* p, Map* m) {
     CUDA_TRY(h_out.reserve(1));
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
+    for (auto& e : evk) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(h_count.reserve(4));
     CUDA_TRY(h_x.reserve(32));
     CUDA_TRY(d_x.reserve(32));
@@ -357,9 +403,11 @@ void Iekf::destroy() {
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(d_ctl); cudaFree(d_limit); cudaFree(d_partials);
     cudaFree(ps.plane); cudaFree(ps.resid); cudaFree(ps.sel); cudaFree(ps.nn_cnt); cudaFree(ps.nn);
-    d_scan.release(); h_stage.release(); h_out.release();
+    d_scan.release(); d_nb.release(); d_nbc.release(); h_stage.release(); h_out.release();
     d_world.release(); d_sel_pts.release(); d_flag.release(); d_flag2.release(); cub_tmp.release(); d_count.release(); d_x.release();
     h_count.release(); h_x.release();
+    if (gexec) cudaGraphExecDestroy(gexec);
+    for (auto& e : evk) if (e) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
 }
@@ -389,11 +437,32 @@ int32_t Iekf::ensure_points(size_t n) {
 
 // d_pts: device scan (float4).  d_hdr: device copy of the Ctl header (x, P, n, prev_n) staged with the
 // scan, or null to upload it from x/P here.
+int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_grid, int single_pass, int force_converge, bool events) {
+    int e = 0;
+    if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
+    k_iekf_init<<<8, 256, 0, stream>>>(d_ctl, d_hdr, ps, force_converge);
+    if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
+    const MapView mv = map->view();
+    const int npass = single_pass ? 1 : prm.max_iter + 1;
+    for (int it = 0; it < npass; ++it) {
+        k_search<<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
+        if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
+        k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(d_pts, d_nb.p, d_nbc.p, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials,
+                                                   prm.max_iter, prm.R, d_limit, single_pass);
+        if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
+    }
+    n_kernels = events ? e - 1 : 0;
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
 int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, double* P, b200_iekf_stats* st, int single_pass,
                   int force_converge) {
     CUDA_TRY(cudaSetDevice(map->device));
     int32_t rc = ensure_points((size_t)n);
     if (rc) return rc;
+    CUDA_TRY(d_nb.reserve((size_t)n * 5));
+    CUDA_TRY(d_nbc.reserve((size_t)n));
     if (!d_hdr) {
         CUDA_TRY(h_stage.reserve(offsetof(Ctl, x_prop)));
         Ctl* hc = (Ctl*)h_stage.p;
@@ -404,15 +473,32 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
         CUDA_TRY(cudaMemcpyAsync(d_ctl, hc, offsetof(Ctl, x_prop), cudaMemcpyHostToDevice, stream));
         d_hdr = d_ctl;
     }
-    CUDA_TRY(cudaEventRecord(ev0, stream));
-    k_iekf_init<<<8, 256, 0, stream>>>(d_ctl, d_hdr, ps, force_converge);
-    const MapView mv = map->view();
+    // search grid sized for the scan rounded up to 8192 points (blocks past ctl->n exit at once), so scans of
+    // similar size replay the same graph
+    const unsigned search_grid = (unsigned)((((size_t)n + 8191) / 8192 * 8192 * KNN_G + 255) / 256);
     const int npass = single_pass ? 1 : prm.max_iter + 1;
-    for (int it = 0; it < npass; ++it) {
-        k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(mv, d_pts, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials, prm.max_iter,
-                                                   prm.R, d_limit, single_pass);
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    if (profiling || !use_graph) {
+        rc = enqueue(d_pts, d_hdr, search_grid, single_pass, force_converge, profiling != 0);
+        if (rc) return rc;
+    } else {
+        const MapView mv0 = map->view();
+        GraphKey key{d_pts, d_hdr, mv0.ent, mv0.pool, ps.plane, d_nb.p, search_grid, single_pass, force_converge};
+        if (!gexec || !(key == gkey)) {
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue(d_pts, d_hdr, search_grid, single_pass, force_converge, false);
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            if (rc) return rc;
+            CUDA_TRY(ce);
+            CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
+            cudaGraphDestroy(graph);
+            gkey = key;
+        }
+        CUDA_TRY(cudaGraphLaunch(gexec, stream));
     }
-    LAUNCH_COUNT(1 + npass);
+    LAUNCH_COUNT(1 + 2 * npass);
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_out.p, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
@@ -434,6 +520,7 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
         for (int i = 0; i < B200_MAX_PASSES; ++i) { st->n_eff[i] = o.n_eff[i]; st->knn[i] = o.knn[i]; }
         cudaEventElapsedTime(&st->gpu_ms, ev0, ev1);
     }
+    for (int i = 0; i < n_kernels; ++i) cudaEventElapsedTime(&kernel_ms[i], evk[i], evk[i + 1]);
     return status;
 }
 
@@ -499,6 +586,34 @@ int32_t b200_iekf_last_HtH(b200_iekf* ekf, int32_t pass, double* HtH, double* Ht
     if (HtH) memcpy(HtH, o.HtH[pass], sizeof(double) * 144);
     if (Hth) memcpy(Hth, o.Hth[pass], sizeof(double) * 12);
     if (x_in) memcpy(x_in, o.x_in[pass], sizeof(double) * 26);
+    return B200_OK;
+}
+
+/* profiling aid: on = record a CUDA event after every kernel of an update (and launch without the graph) */
+int32_t b200_iekf_set_profiling(b200_iekf* ekf, int32_t on) {
+    if (!ekf) B200_FAIL(B200_ERR_ARG, "bad argument");
+    ekf->k.profiling = on;
+    return B200_OK;
+}
+int32_t b200_iekf_set_graph(b200_iekf* ekf, int32_t on) {
+    if (!ekf) B200_FAIL(B200_ERR_ARG, "bad argument");
+    ekf->k.use_graph = on;
+    return B200_OK;
+}
+/* durations (ms) of the kernels of the last profiled update: init, then (search, obs) per pass */
+int32_t b200_iekf_kernel_times(b200_iekf* ekf, float* ms, int32_t max) {
+    if (!ekf || !ms) B200_FAIL(B200_ERR_ARG, "bad argument");
+    int n = ekf->k.n_kernels < max ? ekf->k.n_kernels : max;
+    for (int i = 0; i < n; ++i) ms[i] = ekf->k.kernel_ms[i];
+    return n;
+}
+
+/* bytes moved per b200_iekf_update call for an n-point scan (bench.py "e2e") */
+int32_t b200_iekf_io_bytes(b200_iekf* ekf, int64_t n, int64_t* h2d, int64_t* d2h) {
+    if (!ekf) B200_FAIL(B200_ERR_ARG, "bad argument");
+    const size_t hdr_pad = (offsetof(Ctl, x_prop) + 255) / 256 * 256;
+    if (h2d) *h2d = (int64_t)(hdr_pad + (size_t)n * sizeof(float4));
+    if (d2h) *d2h = (int64_t)sizeof(Ctl);
     return B200_OK;
 }
 

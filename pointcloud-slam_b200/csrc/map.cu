@@ -28,7 +28,7 @@ __global__ void k_point_keys(const float4* __restrict__ pts, int n, float inv_re
 //    run_dst[r]   = pool index where the run's first new point goes
 //    run_reloc[r] = old start if the voxel had to move (its old points are copied by k_relocate), else -1
 __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* __restrict__ cnt, const int32_t* __restrict__ nruns,
-                              uint64_t* keys, int4* vox, uint32_t tmask, uint64_t pool_cap, uint32_t capacity_voxels,
+                              MapEntry* ent, int2* aux, uint32_t tmask, uint64_t pool_cap, uint32_t capacity_voxels,
                               uint32_t stamp, MapCounters* ctr, int32_t* __restrict__ run_dst, int32_t* __restrict__ run_reloc,
                               int32_t* __restrict__ run_oldcnt) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,16 +38,16 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     uint32_t slot = hash_key(key) & tmask;
     bool created = false;
     while (true) {
-        uint64_t k = keys[slot];
+        uint64_t k = ent[slot].key;
         if (k == key) break;
         if (k == kEmptyKey) {
-            uint64_t old = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
+            uint64_t old = atomicCAS((unsigned long long*)&ent[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
             if (old == kEmptyKey) { created = true; break; }
             if (old == key) break;
         }
         slot = (slot + 1) & tmask;
     }
-    int4 v = created ? make_int4(0, 0, 0, 0) : vox[slot];
+    int4 v = created ? make_int4(0, 0, 0, 0) : make_int4(ent[slot].start, ent[slot].count, aux[slot].x, aux[slot].y);
     if (created) {
         unsigned nv = atomicAdd(&ctr->num_voxels, 1u) + 1u;
         if (nv >= capacity_voxels) atomicAdd(&ctr->err_capacity, 1u);
@@ -73,7 +73,9 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     atomicAdd(&ctr->live_points, (unsigned long long)c);
     v.y = newcount;
     v.w = (int)stamp;
-    vox[slot] = v;
+    ent[slot].start = v.x;
+    ent[slot].count = v.y;
+    aux[slot] = make_int2(v.z, v.w);
 }
 
 // 3. voxels that moved: copy their old points to the new slot (one thread per run, old runs are short)
@@ -108,25 +110,31 @@ __global__ void k_scatter_points(const float4* __restrict__ pts, const int32_t* 
     pool[dst0 + (i - run_off[lo])] = p;
 }
 
-__global__ void k_fill_keys(uint64_t* keys, uint32_t n) {
+__global__ void k_fill_keys(MapEntry* ent, int2* aux, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = kEmptyKey;
+    if (i < n) {
+        MapEntry e;
+        e.key = kEmptyKey;
+        e.start = 0;
+        e.count = 0;
+        ent[i] = e;
+        aux[i] = make_int2(0, 0);
+    }
 }
 
 // pool compaction: every live voxel gets a fresh exact-fit run in a new pool
-__global__ void k_compact_plan(const uint64_t* __restrict__ keys, int4* vox, uint32_t tsize, unsigned long long* top,
+__global__ void k_compact_plan(MapEntry* ent, int2* aux, uint32_t tsize, unsigned long long* top,
                                const float4* __restrict__ old_pool, float4* new_pool) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= tsize) return;
-    if (keys[s] == kEmptyKey) return;
-    int4 v = vox[s];
+    if (ent[s].key == kEmptyKey) return;
+    int4 v = make_int4(ent[s].start, ent[s].count, aux[s].x, aux[s].y);
     if (v.y == 0) return;
     int slack = v.y < 4 ? v.y : v.y / 2;  // leave growth room so the next insert does not move everything again
     unsigned long long st = atomicAdd(top, (unsigned long long)(v.y + slack));
     for (int j = 0; j < v.y; ++j) new_pool[st + j] = old_pool[v.x + j];
-    v.x = (int)st;
-    v.z = v.y + slack;
-    vox[s] = v;
+    ent[s].start = (int)st;
+    aux[s].x = v.y + slack;
 }
 
 // ------------------------------------------------------------------ standalone k=5 search
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restric
     float4 p = __ldg(q + gid);
     uint64_t win[5];
     float4 mine;
-    int c = knn5_group<G>(m, p.x, p.y, p.z, lg, gmask, win, mine);
+    int c = knn5_group<G>(m, p.x, p.y, p.z, lg, gmask, lane_stencil<G>(lg, m.nstencil), win, mine);
     if (lg < 5) {
         uint64_t w = win[0];
 #pragma unroll
@@ -150,6 +158,43 @@ __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restric
         d2[gid * 5 + lg] = (w == kInfKey) ? 0.0f : __uint_as_float((uint32_t)(w >> 32));
     }
     if (lg == 0) cnt[gid] = c;
+}
+
+// number of map points resident in the occupied stencil cells of every query (the sum C_i of the roofline's
+// algorithmic-byte formula), and the number of occupied cells
+__global__ void k_stencil_points(MapView m, const float4* __restrict__ q, int n, unsigned long long* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long pts = 0, cells = 0;
+    if (i < n) {
+        const float4 p = q[i];
+        const int kx = pos2cell(p.x, m.inv_res), ky = pos2cell(p.y, m.inv_res), kz = pos2cell(p.z, m.inv_res);
+        for (int s = 0; s < m.nstencil; ++s) {
+            const int cx = kx + c_stencil[s][0], cy = ky + c_stencil[s][1], cz = kz + c_stencil[s][2];
+            if (!cell_in_range(cx, cy, cz)) continue;
+            const uint64_t key = pack_key(cx, cy, cz);
+            uint32_t slot = hash_key(key) & m.tmask;
+            MapEntry e = ld_entry(m.ent + slot);
+            while (e.key != key && e.key != kEmptyKey) {
+                slot = (slot + 1) & m.tmask;
+                e = ld_entry(m.ent + slot);
+            }
+            if (e.key == key) { pts += (unsigned long long)e.count; cells += 1; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        pts += __shfl_xor_sync(0xffffffffu, pts, o);
+        cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, pts);
+        atomicAdd(out + 1, cells);
+    }
+}
+
+__global__ void k_flush_fill(float4* buf, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_float4(v, v, v, v);
 }
 
 // ------------------------------------------------------------------ host side
@@ -171,14 +216,13 @@ int32_t Map::init(const b200_map_params* p, int dev) {
     inv_res = (float)(1.0 / (double)prm.resolution);  // ivox3d.h:65
     nstencil = prm.nearby == 0 ? 1 : prm.nearby == 6 ? 7 : prm.nearby == 26 ? 27 : 19;
     tsize = next_pow2(2 * prm.capacity_voxels);
-    CUDA_TRY(cudaMalloc(&d_keys, (size_t)tsize * sizeof(uint64_t)));
-    CUDA_TRY(cudaMalloc(&d_vox, (size_t)tsize * sizeof(int4)));
+    CUDA_TRY(cudaMalloc(&d_ent, (size_t)tsize * sizeof(MapEntry)));
+    CUDA_TRY(cudaMalloc(&d_aux, (size_t)tsize * sizeof(int2)));
     pool_cap = 4 * prm.max_points;
     CUDA_TRY(cudaMalloc(&d_pool, pool_cap * sizeof(float4)));
     CUDA_TRY(cudaMalloc(&d_ctr, sizeof(MapCounters)));
     CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(MapCounters), stream));
-    CUDA_TRY(cudaMemsetAsync(d_vox, 0, (size_t)tsize * sizeof(int4), stream));
-    k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(d_keys, tsize);
+    k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize);
     LAUNCH_COUNT(1);
     CUDA_TRY(h_ctr_pin.reserve(1));
     CUDA_TRY(d_nruns.reserve(1));
@@ -190,7 +234,7 @@ int32_t Map::init(const b200_map_params* p, int dev) {
 void Map::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    cudaFree(d_keys); cudaFree(d_vox); cudaFree(d_pool); cudaFree(d_ctr);
+    cudaFree(d_ent); cudaFree(d_aux); cudaFree(d_pool); cudaFree(d_ctr);
     in_pts.release(); k_in.release(); k_out.release(); k_uniq.release();
     v_in.release(); v_out.release(); run_cnt.release(); run_off.release(); run_dst.release(); run_reloc.release();
     d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
@@ -207,7 +251,7 @@ int32_t Map::grow_pool(uint64_t min_cap) {
     float4* np = nullptr;
     CUDA_TRY(cudaMalloc(&np, ncap * sizeof(float4)));
     CUDA_TRY(cudaMemsetAsync(&d_ctr->pool_top, 0, sizeof(unsigned long long), stream));
-    k_compact_plan<<<(tsize + 255) / 256, 256, 0, stream>>>(d_keys, d_vox, tsize, &d_ctr->pool_top, d_pool, np);
+    k_compact_plan<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize, &d_ctr->pool_top, d_pool, np);
     LAUNCH_COUNT(1);
     CUDA_TRY(cudaMemcpyAsync(h_ctr_pin.p, d_ctr, sizeof(MapCounters), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -245,7 +289,7 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, run_cnt.p, run_off.p, (int)n, stream));
     ++stamp;
     int32_t* run_oldcnt = run_reloc.p + n;
-    k_upsert_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_cnt.p, d_nruns.p, d_keys, d_vox, tsize - 1, pool_cap,
+    k_upsert_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_cnt.p, d_nruns.p, d_ent, d_aux, tsize - 1, pool_cap,
                                           (uint32_t)prm.capacity_voxels, stamp, d_ctr, run_dst.p, run_reloc.p, run_oldcnt);
     k_relocate<<<nb, 256, 0, stream>>>(d_nruns.p, run_dst.p, run_reloc.p, run_oldcnt, d_pool);
     k_scatter_points<<<nb, 256, 0, stream>>>(d_pts, v_out.p, (int)n, d_nruns.p, run_off.p, run_dst.p, (int)next_ord, d_pool);
@@ -328,6 +372,43 @@ int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t 
     if (!map) B200_FAIL(B200_ERR_ARG, "null map");
     return map->m.knn5_host(xyz_world, n, stride_bytes, idx, sqdist, count);
 }
+/* bench/roofline helper: total map points and occupied cells in the stencils of n queries */
+int32_t b200_map_stencil_points(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int64_t* points, int64_t* cells) {
+    if (!map || !xyz_world || n < 1 || stride_bytes < 12) B200_FAIL(B200_ERR_ARG, "bad argument");
+    b200::Map& m = map->m;
+    CUDA_TRY(cudaSetDevice(m.device));
+    CUDA_TRY(m.h_stage.reserve(n));
+    CUDA_TRY(m.in_pts.reserve(n));
+    b200::pack_xyz_float4(xyz_world, n, stride_bytes, m.h_stage.p);
+    CUDA_TRY(cudaMemcpyAsync(m.in_pts.p, m.h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, m.stream));
+    unsigned long long* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 16));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 16, m.stream));
+    b200::k_stencil_points<<<(unsigned)((n + 255) / 256), 256, 0, m.stream>>>(m.view(), m.in_pts.p, (int)n, d_out);
+    unsigned long long h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, m.stream));
+    CUDA_TRY(cudaStreamSynchronize(m.stream));
+    cudaFree(d_out);
+    if (points) *points = (int64_t)h[0];
+    if (cells) *cells = (int64_t)h[1];
+    return B200_OK;
+}
+
+/* bench helper: evict the L2 by streaming a buffer larger than it (256 MiB) on `device` */
+int32_t b200_flush_l2(int32_t device) {
+    static float4* buf[16] = {};
+    const size_t n = (256u << 20) / sizeof(float4);
+    if (device < 0 || device >= 16) B200_FAIL(B200_ERR_ARG, "bad device");
+    CUDA_TRY(cudaSetDevice(device));
+    if (!buf[device]) CUDA_TRY(cudaMalloc(&buf[device], n * sizeof(float4)));
+    static float v = 0.f;
+    v += 1.f;
+    b200::k_flush_fill<<<1184, 256>>>(buf[device], n, v);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return B200_OK;
+}
+
 int64_t b200_map_num_voxels(b200_map* map) { return map ? (int64_t)map->m.h_ctr.num_voxels : 0; }
 int64_t b200_map_num_points(b200_map* map) { return map ? (int64_t)map->m.h_ctr.live_points : 0; }
 

@@ -1,8 +1,9 @@
 // b200reg — GPU-resident local map index (replaces jueying_lio::IVox, ivox3d.h:53-286).
 //
 // Layout in HBM
-//   keys[T]   uint64   open-addressing table of packed voxel keys (T = pow2 >= 2*capacity)
-//   vox[T]    int4     {start, count, cap, stamp}: the voxel's run inside the point pool
+//   ent[T]    16 B     open-addressing table (T = pow2 >= 2*capacity): {packed voxel key, start, count};
+//                      one 16-byte load resolves a stencil probe to the voxel's run in the point pool
+//   aux[T]    int2     {cap, stamp}: slot capacity / last-touch stamp, only read by insert
 //   pool[]    float4   points, voxel-contiguous, in-voxel order = insertion order;
 //                      .w carries the global insertion ordinal (int bits)
 // A voxel is one contiguous, 16-byte-aligned run, so a stencil search is <= 27 table probes
@@ -24,9 +25,14 @@ struct MapCounters {
     unsigned long long live_points;  // sum of run counts (== num_points while nothing is evicted)
 };
 
+struct __align__(16) MapEntry {
+    uint64_t key;
+    int start;
+    int count;
+};
+
 struct MapView {  // what kernels see
-    const uint64_t* keys;
-    const int4* vox;
+    const MapEntry* ent;
     const float4* pool;
     uint32_t tmask;
     float inv_res;
@@ -45,17 +51,13 @@ static __constant__ signed char c_stencil[27][4] = {
 // IVox::Pos2Grid (ivox3d.h:284-286): round(p * inv_res) with std::round semantics.
 __device__ __forceinline__ int pos2cell(float v, float inv_res) { return (int)roundf(__fmul_rn(v, inv_res)); }
 
-__device__ __forceinline__ int2 map_find(const MapView& m, uint64_t key) {
-    uint32_t slot = hash_key(key) & m.tmask;
-    while (true) {
-        uint64_t k = __ldg(m.keys + slot);
-        if (k == key) {
-            int4 v = __ldg(m.vox + slot);
-            return make_int2(v.x, v.y);
-        }
-        if (k == kEmptyKey) return make_int2(0, 0);
-        slot = (slot + 1) & m.tmask;
-    }
+__device__ __forceinline__ MapEntry ld_entry(const MapEntry* e) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(e));
+    MapEntry r;
+    r.key = ((uint64_t)v.y << 32) | v.x;
+    r.start = (int)v.z;
+    r.count = (int)v.w;
+    return r;
 }
 
 constexpr uint64_t kInfKey = 0xFFFFFFFFFFFFFFFFull;
@@ -81,40 +83,81 @@ __device__ __forceinline__ void top5_insert(uint64_t (&t)[5], uint64_t k) {
 // Candidate total order = (float d2 bits, stencil index, in-voxel index) — the "stable selection"
 // contract of SURVEY.md §7.  Returns the number found (0..5); win[] holds the composite keys in
 // ascending order on every lane of the group; lanes r < count also return winner r's pool entry.
+//
+// Memory-level parallelism is the whole game here (a probe and a gather are both dependent L2/HBM
+// round trips): a lane first issues the table loads of all its stencil cells, then walks its runs as
+// one flat candidate sequence, four 16-byte gathers in flight at a time.
+// packed stencil offsets of lane lg: byte t of the result = (dx+1) | (dy+1)<<2 | (dz+1)<<4 for cell lg + G*t,
+// 0xFF when that cell is beyond the stencil.  Computed once per thread.
 template <int G>
-__device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, float qz, int lg, unsigned gmask,
+__device__ __forceinline__ uint32_t lane_stencil(int lg, int nstencil) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int t = 0; t < (27 + G - 1) / G; ++t) {
+        const int s = lg + G * t;
+        uint32_t b = 0xFFu;
+        if (s < nstencil) b = (uint32_t)(c_stencil[s][0] + 1) | ((uint32_t)(c_stencil[s][1] + 1) << 2) | ((uint32_t)(c_stencil[s][2] + 1) << 4);
+        r |= b << (8 * t);
+    }
+    return r;
+}
+
+template <int G>
+__device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, float qz, int lg, unsigned gmask, uint32_t lst,
                                           uint64_t (&win)[5], float4& mine) {
     constexpr int SLOTS = (27 + G - 1) / G;
+    static_assert(SLOTS <= 4, "lane_stencil packs four cells per lane");
     int cstart[SLOTS], ccount[SLOTS];
+    uint64_t ckey[SLOTS];
+    uint32_t cslot[SLOTS];
+    MapEntry ce[SLOTS];
     const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
 #pragma unroll
-    for (int t = 0; t < SLOTS; ++t) {
-        int s = lg + G * t;
-        cstart[t] = 0;
-        ccount[t] = 0;
-        if (s < m.nstencil) {
-            int cx = kx + c_stencil[s][0], cy = ky + c_stencil[s][1], cz = kz + c_stencil[s][2];
+    for (int t = 0; t < SLOTS; ++t) {  // all first probes in flight together
+        const uint32_t b = (lst >> (8 * t)) & 0xFFu;
+        ckey[t] = kEmptyKey;
+        ce[t].key = kEmptyKey;
+        ce[t].start = 0;
+        ce[t].count = 0;
+        cslot[t] = 0;
+        if (b != 0xFFu) {
+            const int cx = kx + (int)(b & 3u) - 1, cy = ky + (int)((b >> 2) & 3u) - 1, cz = kz + (int)((b >> 4) & 3u) - 1;
             if (cell_in_range(cx, cy, cz)) {
-                int2 r = map_find(m, pack_key(cx, cy, cz));
-                cstart[t] = r.x;
-                ccount[t] = r.y;
+                ckey[t] = pack_key(cx, cy, cz);
+                cslot[t] = hash_key(ckey[t]) & m.tmask;
+                ce[t] = ld_entry(m.ent + cslot[t]);
             }
         }
+    }
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {  // collisions: keep probing linearly (rare at load factor <= 0.5)
+        while (ce[t].key != ckey[t] && ce[t].key != kEmptyKey) {
+            cslot[t] = (cslot[t] + 1) & m.tmask;
+            ce[t] = ld_entry(m.ent + cslot[t]);
+        }
+        const bool hit = ckey[t] != kEmptyKey && ce[t].key == ckey[t];
+        cstart[t] = ce[t].start;
+        ccount[t] = hit ? ce[t].count : 0;
     }
     uint64_t top[5] = {kInfKey, kInfKey, kInfKey, kInfKey, kInfKey};
 #pragma unroll
     for (int t = 0; t < SLOTS; ++t) {
-        const int s = lg + G * t;
         const float4* run = m.pool + cstart[t];
         const int cnt = ccount[t];
-        for (int j = 0; j < cnt; ++j) {
-            float4 p = __ldg(run + j);
-            // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
-            float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
-            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (d2 < m.max_range2) {
-                uint64_t k = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)((s << kRankBits) | j);
-                top5_insert(top, k);
+        const uint32_t rbase = (uint32_t)(lg + G * t) << kRankBits;
+        for (int j0 = 0; j0 < cnt; j0 += 4) {  // four gathers in flight
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < cnt) p[u] = __ldg(run + j0 + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u < cnt) {
+                    // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
+                    const float dx = __fsub_rn(p[u].x, qx), dy = __fsub_rn(p[u].y, qy), dz = __fsub_rn(p[u].z, qz);
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d2 < m.max_range2) top5_insert(top, ((uint64_t)__float_as_uint(d2) << 32) | (rbase | (uint32_t)(j0 + u)));
+                }
             }
         }
     }
@@ -125,7 +168,7 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
         uint64_t mn = top[0];
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
-            uint64_t other = __shfl_xor_sync(gmask, mn, o);
+            const uint64_t other = __shfl_xor_sync(gmask, mn, o);
             mn = other < mn ? other : mn;
         }
         win[r] = mn;
@@ -146,11 +189,10 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
         const uint32_t lo = (uint32_t)w;
         const int s = (int)(lo >> kRankBits), j = (int)(lo & ((1u << kRankBits) - 1));
         const int owner = s % G, slot = s / G;
-        // every lane must take part in the shuffles
         int st = 0;
 #pragma unroll
-        for (int t = 0; t < SLOTS; ++t) {
-            int v = __shfl_sync(gmask, cstart[t], (owner & (G - 1)) + ((threadIdx.x & 31) / G) * G);
+        for (int t = 0; t < SLOTS; ++t) {  // every lane takes part in the shuffles
+            const int v = __shfl_sync(gmask, cstart[t], (owner & (G - 1)) + ((threadIdx.x & 31) / G) * G);
             if (slot == t) st = v;
         }
         if (lg < 5 && w != kInfKey) mine = __ldg(m.pool + st + j);
@@ -166,8 +208,8 @@ struct Map {
     float inv_res = 0.f;
     int nstencil = 19;
     uint32_t tsize = 0;
-    uint64_t* d_keys = nullptr;
-    int4* d_vox = nullptr;
+    MapEntry* d_ent = nullptr;
+    int2* d_aux = nullptr;
     float4* d_pool = nullptr;
     uint64_t pool_cap = 0;
     MapCounters* d_ctr = nullptr;
@@ -187,7 +229,7 @@ struct Map {
 
     MapView view() const {
         MapView v;
-        v.keys = d_keys; v.vox = d_vox; v.pool = d_pool; v.tmask = tsize - 1; v.inv_res = inv_res;
+        v.ent = d_ent; v.pool = d_pool; v.tmask = tsize - 1; v.inv_res = inv_res;
         v.nstencil = nstencil; v.max_range2 = prm.max_range * prm.max_range;
         return v;
     }

@@ -20,4 +20,18 @@ st = (C.c_longlong * (8 * 16))()
 api.lib().b200_iekf_debug_stamps(kf.h, st)
 for p in range(kf.stats.passes):
     v = [st[p * 16 + i] for i in range(8)]
-    print('pass', p, 'stage cycles', [v[i + 1] - v[i] for i in range(7)], 'total', v[7] - v[0])
+    print('pass', p, 'post', [v[i + 1] - v[i] for i in range(7)], 'tot', v[7] - v[0], '| pre', st[p*16+8], 'wait', st[p*16+9], '| search/measure/accum', st[p*16+10], st[p*16+11], st[p*16+12])
+# per-kernel event timing (no graph)
+api.lib().b200_iekf_set_profiling(kf.h, 1)
+for r in range(3):
+    kf.change_x(c['x_prop']); kf.change_P(c['P'])
+    kf.update_iterated_dyn_share_modified(c['scan'])
+    ms = (C.c_float * 17)()
+    k = api.lib().b200_iekf_kernel_times(kf.h, ms, 17)
+    print('profiled gpu_ms %.4f kernels(us):' % kf.stats.gpu_ms, ['%.1f' % (ms[i] * 1e3) for i in range(k)])
+api.lib().b200_iekf_set_profiling(kf.h, 0)
+api.lib().b200_iekf_set_graph(kf.h, 0)
+for r in range(2):
+    kf.change_x(c['x_prop']); kf.change_P(c['P'])
+    t = time.time(); kf.update_iterated_dyn_share_modified(c['scan']); dt = time.time() - t
+    print('no-graph gpu_ms %.4f wall %.3f' % (kf.stats.gpu_ms, dt * 1e3))
