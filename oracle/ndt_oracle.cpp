@@ -301,7 +301,10 @@ struct Ndt {
     static void pose_matrix(const double* p, float M[16] /*row-major 4x4*/) {
         // Translation * AngleAxis(x) * AngleAxis(y) * AngleAxis(z) in float (:129,749-753)
         float rx = (float)p[3], ry = (float)p[4], rz = (float)p[5];
-        float cx = std::cos(rx), sx = std::sin(rx), cy = std::cos(ry), sy = std::sin(ry), cz = std::cos(rz), sz = std::sin(rz);
+        // float sin/cos of AngleAxisf evaluated as the correctly rounded value (double evaluation, narrowed): libm's
+        // sinf/cosf differ from it by one ulp for a few percent of the arguments, platform by platform
+        float cx = (float)std::cos((double)rx), sx = (float)std::sin((double)rx), cy = (float)std::cos((double)ry),
+              sy = (float)std::sin((double)ry), cz = (float)std::cos((double)rz), sz = (float)std::sin((double)rz);
         float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
         float Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
         float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
@@ -490,16 +493,17 @@ static void euler_012(const float R[9], float res[3]) {
     const int i = 0, j = 1, k = 2;
     auto c = [&](int r, int cc) { return R[r * 3 + cc]; };
     const float pi = (float)M_PI;
-    res[0] = std::atan2(c(j, k), c(k, k));
+    // atan2f/sinf/cosf as correctly rounded floats (double evaluation, narrowed), see pose_matrix
+    res[0] = (float)std::atan2((double)c(j, k), (double)c(k, k));
     float c2 = std::sqrt(c(i, i) * c(i, i) + c(i, j) * c(i, j));
     if (res[0] > 0.0f) {  // even permutation: flip when res[0] > 0
         if (res[0] > 0.0f) res[0] -= pi; else res[0] += pi;
-        res[1] = std::atan2(-c(i, k), -c2);
+        res[1] = (float)std::atan2((double)-c(i, k), (double)-c2);
     } else {
-        res[1] = std::atan2(-c(i, k), c2);
+        res[1] = (float)std::atan2((double)-c(i, k), (double)c2);
     }
-    float s1 = std::sin(res[0]), c1 = std::cos(res[0]);
-    res[2] = std::atan2(s1 * c(k, i) - c1 * c(j, i), c1 * c(j, j) - s1 * c(k, j));
+    float s1 = (float)std::sin((double)res[0]), c1 = (float)std::cos((double)res[0]);
+    res[2] = (float)std::atan2((double)(s1 * c(k, i) - c1 * c(j, i)), (double)(c1 * c(j, j) - s1 * c(k, j)));
     res[0] = -res[0]; res[1] = -res[1]; res[2] = -res[2];
 }
 

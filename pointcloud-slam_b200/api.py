@@ -116,6 +116,13 @@ def lib():
         L.b200_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
         L.b200_comm_destroy.argtypes = [vp]
         L.b200_reloc_argmin.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+        L.b200_ndt_align_batch.argtypes = [vp, vp, i64, vp, vp]
+        L.b200_ndt_grid.argtypes = [vp, vp, vp]
+        L.b200_ndt_nbhd_total.restype = i64
+        L.b200_ndt_nbhd_total.argtypes = [vp, vp]
+        L.b200_ndt_last_ms.restype = C.c_float
+        L.b200_ndt_last_ms.argtypes = [vp]
+        L.b200_ndt_last_launches.argtypes = [vp]
     _LIB = L
     return L
 
@@ -407,7 +414,75 @@ class NormalDistributionsTransform:
         return H
 
     def calculateScore(self, poses_cm16):
+        """calculateScore (ndt_omp_impl.hpp:836-880) for a batch of poses ([h,16] column-major 4x4)."""
         poses = np.ascontiguousarray(poses_cm16, dtype=np.float32).reshape(-1, 16)
         s = np.zeros(poses.shape[0])
         _check(lib().b200_ndt_score_batch(self._handle(), _p(poses), poses.shape[0], _p(s)))
         return s
+
+    def alignBatch(self, guesses_cm16):
+        """align() from h independent initial guesses in one batch; returns (finals [h,4,4] row-major, results)."""
+        g = np.ascontiguousarray(guesses_cm16, dtype=np.float32).reshape(-1, 16)
+        h = g.shape[0]
+        out = np.zeros((h, 16), np.float32)
+        res = (NdtResult * h)()
+        _check(lib().b200_ndt_align_batch(self._handle(), _p(g), h, _p(out), res))
+        return out.reshape(h, 4, 4).transpose(0, 2, 1).copy(), res
+
+    def grid(self):
+        mn = np.zeros(3, np.int32)
+        dv = np.zeros(3, np.int32)
+        _check(lib().b200_ndt_grid(self._handle(), _p(mn), _p(dv)))
+        return mn, dv
+
+    def nbhd_total(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        return int(lib().b200_ndt_nbhd_total(self._handle(), _p(p6)))
+
+    def last_ms(self):
+        """Device time (CUDA events on the handle's stream) of the last set_target / align / score call."""
+        return float(lib().b200_ndt_last_ms(self._handle()))
+
+    def last_launches(self):
+        return int(lib().b200_ndt_last_launches(self._handle()))
+
+
+class Communicator:
+    """NCCL communicator over the ranks of a torch.distributed-style job (one process per GPU)."""
+
+    def __init__(self, nranks, rank, unique_id: bytes, device=0):
+        self.h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().b200_comm_init_rank(nranks, rank, buf, device, C.byref(self.h)))
+        self.nranks, self.rank = nranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib().b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_comm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def shard_range(h_total: int, nranks: int, rank: int):
+    """Contiguous slice [begin, end) of h_total hypotheses owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(h_total, nranks)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicator | None = None, h_begin=0):
+    """Global relocalization: scores this rank's hypothesis slice (poses_cm16 = the slice, h_begin = its offset in the
+    global grid) and returns (global best index, its score, device ms) - identical on every rank."""
+    poses = np.ascontiguousarray(poses_cm16, dtype=np.float32).reshape(-1, 16)
+    best, score, ms = C.c_int64(-1), C.c_double(0), C.c_float(0)
+    rc = lib().b200_reloc_argmin(comm.h if comm is not None else None, ndt._handle(), _p(poses) if len(poses) else None,
+                                 poses.shape[0], h_begin, C.byref(best), C.byref(score), C.byref(ms))
+    _check(rc)
+    return best.value, score.value, ms.value

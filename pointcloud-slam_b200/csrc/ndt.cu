@@ -1,0 +1,1170 @@
+// b200reg — NDT registration (B3): voxel-Gaussian map build, score/gradient/Hessian, Newton + More-Thuente
+// line search with the control flow resident on the device, batched hypothesis scoring for relocalization.
+//
+// Replaces pclomp::NormalDistributionsTransform (pointcloud_match/ndt_omp/include/pclomp/ndt_omp.h:117-261,
+// ndt_omp_impl.hpp:47-880) and pclomp::VoxelGridCovariance (voxel_grid_covariance_omp_impl.hpp:49-442).
+//
+// set_target  min/max reduction -> leaf id per point -> radix sort (point order preserved inside a leaf) ->
+//             run-length segments -> one warp per leaf accumulates sum(p), sum(p p^T) in fp64 *in input order*
+//             (9 lanes own the 9 sums, points are fetched 32 at a time) -> one thread per leaf: mean, covariance,
+//             3x3 eigen-decomposition, eigenvalue inflation, inverse -> dense cell -> leaf table.
+// align       k_ndt_eval is launched back to back; every launch evaluates score/gradient/Hessian (or the fp64
+//             Hessian) at the pose the control block asks for, and the last block to finish reduces the block
+//             partials in a fixed order and advances the Newton / More-Thuente state machine (computeTransformation
+//             + computeStepLengthMT) by one evaluation.  The host only polls a done flag every few launches.
+//             gridDim.y indexes independent alignments (hypotheses), each with its own control block.
+#include "ndt.cuh"
+
+#include <cub/cub.cuh>
+
+#include <cmath>
+#include <thread>
+#include <vector>
+
+namespace b200 {
+namespace ndt {
+
+constexpr int EVAL_THREADS = 256;
+constexpr int LAUNCH_BATCH = 8;   // evaluations enqueued between two polls of the done flag
+
+enum Phase : int { PH_SINGLE_DERIV = 0, PH_SINGLE_HESS, PH_INIT, PH_MT_FIRST, PH_MT_LOOP, PH_MT_HESS };
+enum Mode : int { MODE_DERIV_H = 0, MODE_DERIV_NOH, MODE_HESS_D };
+
+struct Ctl {  // one per alignment, global memory
+    // evaluation request, read by every block of a launch
+    float M[16];   // row-major transform the source is evaluated under
+    AngleTables tab;
+    int mode;
+    int done;
+    unsigned ticket;
+    int phase;
+    // computeTransformation state
+    double p[6], g[6], H[36], score;
+    int nr_iterations, converged, evals, hess_evals;
+    double trans_probability;
+    float final_T[16];  // row-major
+    // computeStepLengthMT state
+    double x_t[6], dir[6];
+    double a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_0, d_phi_0, phi_t, d_phi_t, psi_t, d_psi_t;
+    double step_min, step_max;
+    int step_iterations, interval_converged, open_interval;
+    long long solve_cycles, step_cycles;
+};
+
+struct AlignConsts {
+    double step_size, trans_eps;
+    int max_iter;
+    int n_src;
+};
+
+// ------------------------------------------------------------------ target build
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// pcl::getMinMax3D over the finite points (voxel_grid_covariance_omp_impl.hpp:72)
+__global__ void k_ndt_minmax(const float4* __restrict__ pts, int64_t n, int* __restrict__ mm /*[6]: min xyz, max xyz (ordered ints)*/) {
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(pts + i);
+        if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(mm + k, f2ord(mn[k]));
+            atomicMax(mm + 3 + k, f2ord(mx[k]));
+        }
+    }
+}
+__global__ void k_ndt_minmax_init(int* mm) {
+    if (threadIdx.x < 3) mm[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) mm[threadIdx.x] = (int)0x80000000;
+}
+
+struct GridDims {
+    int min_b[3], max_b[3], div_b[3], mul[3];
+    float inv_leaf;
+};
+
+// leaf id of every point (:218-223); non-finite points get the sentinel key and sort last
+__global__ void k_ndt_keys(const float4* __restrict__ pts, int n, GridDims gd, uint32_t sentinel, uint32_t* __restrict__ keys,
+                           int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    uint32_t key = sentinel;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = (int)(floorf(p.x * gd.inv_leaf) - (float)gd.min_b[0]);
+        const int i1 = (int)(floorf(p.y * gd.inv_leaf) - (float)gd.min_b[1]);
+        const int i2 = (int)(floorf(p.z * gd.inv_leaf) - (float)gd.min_b[2]);
+        key = (uint32_t)(i0 * gd.mul[0] + i1 * gd.mul[1] + i2 * gd.mul[2]);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// One warp per leaf: fp64 sums of p and p p^T in input order (:233-237).  Lane c < 3 owns sum(p_c); lanes 3..8 own
+// the six distinct products (p_a p_b is commutative, so the full 3x3 of the reference holds the same six values).
+// The reference's Leaf() starts cov_ at the identity (voxel_grid_covariance_omp.h:103-112) and accumulates on top.
+__global__ void __launch_bounds__(256) k_ndt_accumulate(const float4* __restrict__ pts, const int32_t* __restrict__ sorted_idx,
+                                                        const uint32_t* __restrict__ uniq, const int32_t* __restrict__ run_off,
+                                                        const int32_t* __restrict__ run_cnt, const int32_t* __restrict__ nruns,
+                                                        uint32_t sentinel, double* __restrict__ sums /*[nruns][9]*/) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int nr = *nruns;
+    // (a, b) component selectors of this lane: 0..2 = x,y,z, 3 = the constant 1
+    const int sa = lane < 3 ? lane : lane == 3 ? 0 : lane == 4 ? 0 : lane == 5 ? 0 : lane == 6 ? 1 : lane == 7 ? 1 : 2;
+    const int sb = lane < 3 ? 3 : lane == 3 ? 0 : lane == 4 ? 1 : lane == 5 ? 2 : lane == 6 ? 1 : lane == 7 ? 2 : 2;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nr; r += warps) {
+        if (uniq[r] == sentinel) continue;  // the non-finite bucket
+        const int off = run_off[r], cnt = run_cnt[r];
+        double acc = (lane == 3 || lane == 6 || lane == 8) ? 1.0 : 0.0;
+        for (int base = 0; base < cnt; base += 32) {
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + lane < cnt) p = __ldg(pts + __ldg(sorted_idx + off + base + lane));
+            const int m = min(32, cnt - base);
+            for (int j = 0; j < m; ++j) {
+                const float x = __shfl_sync(0xffffffffu, p.x, j), y = __shfl_sync(0xffffffffu, p.y, j), z = __shfl_sync(0xffffffffu, p.z, j);
+                const double a = (double)(sa == 0 ? x : sa == 1 ? y : z);
+                const double b = sb == 3 ? 1.0 : (double)(sb == 0 ? x : sb == 1 ? y : z);
+                acc += a * b;
+            }
+        }
+        if (lane < 9) sums[(size_t)r * 9 + lane] = acc;
+    }
+}
+
+// One thread per leaf: second pass of applyFilter (:282-367)
+__global__ void k_ndt_finalize(const uint32_t* __restrict__ uniq, const int32_t* __restrict__ run_cnt, const int32_t* __restrict__ nruns,
+                               uint32_t sentinel, const double* __restrict__ sums, int min_pts, double eig_ratio, LeafF* __restrict__ leafF,
+                               LeafD* __restrict__ leafD, double* __restrict__ covs, int32_t* __restrict__ npts, uint8_t* __restrict__ valid,
+                               int32_t* __restrict__ cell2leaf, int32_t* __restrict__ n_valid) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    valid[r] = 0;
+    const uint32_t id = uniq[r];
+    if (id == sentinel) { npts[r] = 0; return; }
+    const int n = run_cnt[r];
+    npts[r] = n;
+    const double* s = sums + (size_t)r * 9;
+    const double pt_sum[3] = {s[0], s[1], s[2]};
+    double mean[3];
+    for (int a = 0; a < 3; ++a) mean[a] = pt_sum[a] / n;
+    LeafD L;
+    for (int a = 0; a < 3; ++a) L.mean[a] = mean[a];
+    for (int a = 0; a < 9; ++a) L.icov[a] = 0.0;
+    if (n < min_pts) { leafD[r] = L; return; }
+    const double S[9] = {s[3], s[4], s[5], s[4], s[6], s[7], s[5], s[7], s[8]};
+    const double np = n;
+    double cov[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) cov[a * 3 + b] = (S[a * 3 + b] - 2 * (pt_sum[a] * mean[b])) / np + mean[a] * mean[b];
+    const double f = (np - 1.0) / np;
+    for (int a = 0; a < 9; ++a) cov[a] *= f;
+    double A[9], w[3], V[9];
+    for (int a = 0; a < 3; ++a)  // SelfAdjointEigenSolver reads the lower triangle
+        for (int b = 0; b < 3; ++b) A[a * 3 + b] = (a >= b) ? cov[a * 3 + b] : cov[b * 3 + a];
+    jacobi_eig<3>(A, w, V);
+    if (w[0] < 0 || w[1] < 0 || w[2] <= 0) { npts[r] = -1; leafD[r] = L; return; }
+    const double min_ev = eig_ratio * w[2];
+    if (w[0] < min_ev) {
+        w[0] = min_ev;
+        if (w[1] < min_ev) w[1] = min_ev;
+        double Vi[9], VL[9];
+        inverse3(V, Vi);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) VL[a * 3 + b] = V[a * 3 + b] * w[b];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) cov[a * 3 + b] = VL[a * 3] * Vi[b] + VL[a * 3 + 1] * Vi[3 + b] + VL[a * 3 + 2] * Vi[6 + b];
+    }
+    inverse3(cov, L.icov);
+    double mxc = L.icov[0], mnc = L.icov[0];
+    for (int a = 1; a < 9; ++a) { mxc = fmax(mxc, L.icov[a]); mnc = fmin(mnc, L.icov[a]); }
+    for (int a = 0; a < 9; ++a) covs[(size_t)r * 9 + a] = cov[a];
+    leafD[r] = L;
+    if (mxc == CUDART_INF || mnc == -CUDART_INF) { npts[r] = -1; return; }
+    LeafF F;
+    for (int a = 0; a < 3; ++a) F.mean[a] = mean[a];
+    for (int a = 0; a < 9; ++a) F.icov[a] = (float)L.icov[a];
+    F.pad = 0.f;
+    leafF[r] = F;
+    valid[r] = 1;
+    cell2leaf[id] = r;
+    atomicAdd(n_valid, 1);
+}
+
+// ------------------------------------------------------------------ Newton / More-Thuente state machine (thread 0 of the last block)
+// H x = rhs the way JacobiSVD(H).solve(rhs) answers it for symmetric H: eigen-decomposition, singular values |lambda|,
+// components below max|lambda| * 6 eps dropped (ndt_omp_impl.hpp:112-114)
+__device__ __noinline__ void svd_solve6(const double* H, const double* rhs, double* x) {
+    double A[36], w[6], V[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) A[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
+    jacobi_eig<6>(A, w, V);
+    double smax = 0.0;
+    for (int i = 0; i < 6; ++i) smax = fmax(smax, fabs(w[i]));
+    const double thr = fmax(smax * 6.0 * 2.220446049250313e-16, 2.2250738585072014e-308);
+    for (int i = 0; i < 6; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (fabs(w[k]) <= thr) continue;
+        double d = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) d += V[i * 6 + k] * rhs[i];
+        d /= w[k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + k] * d;
+    }
+}
+
+// updateIntervalMT (ndt_omp_impl.hpp:594-620)
+__device__ inline bool mt_update_interval(Ctl& c, double f_t, double g_t) {
+    const double a_t = c.a_t;
+    if (f_t > c.f_l) { c.a_u = a_t; c.f_u = f_t; c.g_u = g_t; return false; }
+    if (g_t * (c.a_l - a_t) > 0) { c.a_l = a_t; c.f_l = f_t; c.g_l = g_t; return false; }
+    if (g_t * (c.a_l - a_t) < 0) {
+        c.a_u = c.a_l; c.f_u = c.f_l; c.g_u = c.g_l;
+        c.a_l = a_t; c.f_l = f_t; c.g_l = g_t;
+        return false;
+    }
+    return true;
+}
+
+// trialValueSelectionMT (ndt_omp_impl.hpp:623-698): the four cases of More & Thuente's safeguarded cubic/quadratic step
+__device__ inline double mt_trial_value(const Ctl& c, double f_t, double g_t) {
+    const double a_l = c.a_l, f_l = c.f_l, g_l = c.g_l, a_u = c.a_u, f_u = c.f_u, g_u = c.g_u, a_t = c.a_t;
+    auto cubic_min = [](double a0, double f0, double g0, double a1, double f1, double g1) {
+        const double z = 3 * (f1 - f0) / (a1 - a0) - g1 - g0;
+        const double w = sqrt(z * z - g1 * g0);
+        return a0 + (a1 - a0) * (w - g0 - z) / (g1 - g0 + 2 * w);
+    };
+    if (f_t > f_l) {
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+        return fabs(a_c - a_l) < fabs(a_q - a_l) ? a_c : 0.5 * (a_q + a_c);
+    }
+    if (g_t * g_l < 0) {
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        return fabs(a_c - a_t) >= fabs(a_s - a_t) ? a_c : a_s;
+    }
+    if (fabs(g_t) <= fabs(g_l)) {
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        const double a_n = fabs(a_c - a_t) < fabs(a_s - a_t) ? a_c : a_s;
+        return a_t > a_l ? fmin(a_t + 0.66 * (a_u - a_t), a_n) : fmax(a_t + 0.66 * (a_u - a_t), a_n);
+    }
+    return cubic_min(a_u, f_u, g_u, a_t, f_t, g_t);
+}
+
+__device__ inline void request_eval(Ctl& c, const double* x, int mode) {
+    pose_matrix(x, c.M);
+    for (int i = 0; i < 16; ++i) c.final_T[i] = c.M[i];  // final_transformation_ follows every trial (:749-753,783-788)
+    angle_tables(x, c.tab);
+    c.mode = mode;
+}
+
+__device__ inline void finish(Ctl& c, const AlignConsts& k, bool converged) {
+    c.trans_probability = c.score / (double)k.n_src;
+    c.converged = converged ? 1 : 0;
+    c.done = 1;
+}
+
+// computeTransformation's loop body up to the first trial of the line search (:107-126, 701-760)
+__device__ inline void newton_step(Ctl& c, const AlignConsts& k) {
+    double ng[6], dp[6];
+    for (int i = 0; i < 6; ++i) ng[i] = -c.g[i];
+    const long long t0 = clock64();
+    svd_solve6(c.H, ng, dp);
+    c.solve_cycles += clock64() - t0;
+    double dn = 0;
+    for (int i = 0; i < 6; ++i) dn += dp[i] * dp[i];
+    dn = sqrt(dn);
+    if (dn == 0 || dn != dn) { finish(c, k, dn == dn); return; }
+    for (int i = 0; i < 6; ++i) c.dir[i] = dp[i] / dn;
+    // computeStepLengthMT prologue
+    c.phi_0 = -c.score;
+    double d_phi_0 = 0;
+    for (int i = 0; i < 6; ++i) d_phi_0 += c.g[i] * c.dir[i];
+    d_phi_0 = -d_phi_0;
+    if (d_phi_0 >= 0) {
+        if (d_phi_0 == 0) {  // no step: delta_p = 0 (:716-718)
+            c.a_t = 0;
+            c.step_iterations = 0;
+            c.phase = -1;
+            return;
+        }
+        d_phi_0 *= -1;
+        for (int i = 0; i < 6; ++i) c.dir[i] *= -1;
+    }
+    c.d_phi_0 = d_phi_0;
+    c.step_iterations = 0;
+    const double mu = 1.e-4;
+    c.step_max = k.step_size;
+    c.step_min = k.trans_eps / 2;
+    c.a_l = 0; c.a_u = 0;
+    c.f_l = c.phi_0 - c.phi_0 - mu * d_phi_0 * c.a_l;
+    c.g_l = d_phi_0 - mu * d_phi_0;
+    c.f_u = c.phi_0 - c.phi_0 - mu * d_phi_0 * c.a_u;
+    c.g_u = d_phi_0 - mu * d_phi_0;
+    c.interval_converged = (c.step_max - c.step_min) < 0;
+    c.open_interval = 1;
+    double a_t = dn;
+    a_t = fmin(a_t, c.step_max);
+    a_t = fmax(a_t, c.step_min);
+    c.a_t = a_t;
+    for (int i = 0; i < 6; ++i) c.x_t[i] = c.p[i] + c.dir[i] * a_t;
+    request_eval(c, c.x_t, MODE_DERIV_H);
+    c.phase = PH_MT_FIRST;
+}
+
+// tail of computeTransformation's loop body (:129-141)
+__device__ inline void finish_iteration(Ctl& c, const AlignConsts& k) {
+    const double dn = c.a_t;
+    for (int i = 0; i < 6; ++i) c.p[i] = c.p[i] + c.dir[i] * dn;
+    bool conv = false;
+    if (c.nr_iterations > k.max_iter || (c.nr_iterations && (fabs(dn) < k.trans_eps))) conv = true;
+    c.nr_iterations++;
+    if (conv) finish(c, k, true);
+    else newton_step(c, k);
+}
+
+// `res` = the 43 (or 36) reduced sums of the evaluation that just finished
+__device__ void advance(Ctl& c, const AlignConsts& k, const double* res) {
+    const double mu = 1.e-4, nu = 0.9;
+    const int mode = c.mode;
+    if (mode == MODE_HESS_D) {
+        c.hess_evals++;
+        for (int i = 0; i < 36; ++i) c.H[i] = res[i];
+    } else {
+        c.evals++;
+        c.score = res[0];
+        for (int i = 0; i < 6; ++i) c.g[i] = res[1 + i];
+        for (int i = 0; i < 36; ++i) c.H[i] = (mode == MODE_DERIV_H) ? res[7 + i] : 0.0;
+    }
+    switch (c.phase) {
+        case PH_SINGLE_DERIV:
+        case PH_SINGLE_HESS:
+            c.done = 1;
+            return;
+        case PH_INIT:
+            newton_step(c, k);
+            break;
+        case PH_MT_FIRST:
+        case PH_MT_LOOP: {
+            c.phi_t = -c.score;
+            double d = 0;
+            for (int i = 0; i < 6; ++i) d += c.g[i] * c.dir[i];
+            c.d_phi_t = -d;
+            c.psi_t = c.phi_t - c.phi_0 - mu * c.d_phi_0 * c.a_t;
+            c.d_psi_t = c.d_phi_t - mu * c.d_phi_0;
+            if (c.phase == PH_MT_LOOP) {  // rest of the while body after the evaluation (:793-823)
+                if (c.open_interval && (c.psi_t <= 0 && c.d_psi_t >= 0)) {
+                    c.open_interval = 0;
+                    c.f_l = c.f_l + c.phi_0 - mu * c.d_phi_0 * c.a_l;
+                    c.g_l = c.g_l + mu * c.d_phi_0;
+                    c.f_u = c.f_u + c.phi_0 - mu * c.d_phi_0 * c.a_u;
+                    c.g_u = c.g_u + mu * c.d_phi_0;
+                }
+                if (c.open_interval) c.interval_converged = mt_update_interval(c, c.psi_t, c.d_psi_t);
+                else c.interval_converged = mt_update_interval(c, c.phi_t, c.d_phi_t);
+                c.step_iterations++;
+            }
+            // while condition (:763)
+            if (!c.interval_converged && c.step_iterations < 10 && !(c.psi_t <= 0 && c.d_phi_t <= -nu * c.d_phi_0)) {
+                double a_t = c.open_interval ? mt_trial_value(c, c.psi_t, c.d_psi_t) : mt_trial_value(c, c.phi_t, c.d_phi_t);
+                a_t = fmin(a_t, c.step_max);
+                a_t = fmax(a_t, c.step_min);
+                c.a_t = a_t;
+                for (int i = 0; i < 6; ++i) c.x_t[i] = c.p[i] + c.dir[i] * a_t;
+                request_eval(c, c.x_t, MODE_DERIV_NOH);
+                c.phase = PH_MT_LOOP;
+            } else if (c.step_iterations) {  // computeHessian with the final trial's cloud (:830)
+                c.mode = MODE_HESS_D;
+                c.phase = PH_MT_HESS;
+            } else {
+                finish_iteration(c, k);
+            }
+            break;
+        }
+        case PH_MT_HESS:
+            finish_iteration(c, k);
+            break;
+    }
+    while (c.phase == -1 && !c.done) {  // zero directional derivative: the line search returns step length 0 (:716-718)
+        c.phase = -2;
+        finish_iteration(c, k);
+    }
+}
+
+// ------------------------------------------------------------------ evaluation kernel
+struct EvalSmem {
+    float M[12];
+    AngleTables tab;
+    int mode;
+    double red[EVAL_THREADS / 32][NACC];
+    double res[NACC];
+    int is_last;
+};
+
+__global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls, AlignConsts k, double* partials /*[h][NACC][nbx]*/) {
+    Ctl* ctl = ctls + blockIdx.y;
+    if (ctl->done) return;
+    __shared__ EvalSmem sm;
+    const int tid = threadIdx.x, nbx = gridDim.x;
+    if (tid < 12) sm.M[tid] = ctl->M[tid];
+    for (int i = tid; i < (int)(sizeof(AngleTables) / 4); i += EVAL_THREADS) ((int*)&sm.tab)[i] = ((const int*)&ctl->tab)[i];
+    if (tid == 0) sm.mode = ctl->mode;
+    __syncthreads();
+    const int mode = sm.mode;
+    const int nitems = v.n_src * v.nst;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    for (int item = blockIdx.x * EVAL_THREADS + tid; item < nitems; item += nbx * EVAL_THREADS) {
+        const int i = item / v.nst, s = item - i * v.nst;
+        const float4 p = __ldg(v.src + i);
+        float tx, ty, tz;
+        xform(sm.M, p.x, p.y, p.z, tx, ty, tz);
+        const int lf = nbr_leaf(v, tx, ty, tz, s);
+        if (lf < 0) continue;
+        if (mode == MODE_HESS_D) {
+            LeafD L;
+            const double2* src = reinterpret_cast<const double2*>(v.leafD + lf);
+            double2* dst = reinterpret_cast<double2*>(&L);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[q] = __ldg(src + q);
+            hessian_pair_d(v, sm.tab, L, p.x, p.y, p.z, tx, ty, tz, *reinterpret_cast<double(*)[36]>(&acc[0]));
+        } else {
+            LeafF L;
+            const float4* src = reinterpret_cast<const float4*>(v.leafF + lf);
+            float4* dst = reinterpret_cast<float4*>(&L);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = __ldg(src + q);
+            deriv_pair_f(v, sm.tab, L, p.x, p.y, p.z, tx, ty, tz, mode == MODE_DERIV_H, acc);
+        }
+    }
+    // block reduction in a fixed order: xor-tree inside the warp, warps in index order
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double a = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((tid & 31) == 0) sm.red[tid >> 5][i] = a;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double a = sm.red[0][tid];
+#pragma unroll
+        for (int w = 1; w < EVAL_THREADS / 32; ++w) a += sm.red[w][tid];
+        __stcg(partials + ((size_t)blockIdx.y * NACC + tid) * nbx + blockIdx.x, a);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&ctl->ticket, 1u);
+        sm.is_last = (t == (unsigned)nbx - 1u);
+    }
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    if (tid < NACC) {  // blocks in index order
+        const double* src = partials + ((size_t)blockIdx.y * NACC + tid) * nbx;
+        double a = 0.0;
+        for (int b = 0; b < nbx; ++b) a += __ldcg(src + b);
+        sm.res[tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ctl->ticket = 0;
+        const long long t0 = clock64();
+        advance(*ctl, k, sm.res);
+        ctl->step_cycles += clock64() - t0;
+    }
+}
+
+// one thread per alignment: computeTransformation prologue (:77-105)
+__global__ void k_ndt_init(Ctl* ctls, int h, const float* __restrict__ guesses /*h x 16 col-major*/, const double* __restrict__ p_in /*h x 6 or null*/,
+                           int phase) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= h) return;
+    Ctl& c = ctls[a];
+    c.done = 0; c.ticket = 0; c.phase = phase;
+    c.nr_iterations = 0; c.converged = 0; c.evals = 0; c.hess_evals = 0;
+    c.trans_probability = 0; c.score = 0; c.solve_cycles = 0; c.step_cycles = 0;
+    c.step_iterations = 0; c.a_t = 0;
+    for (int i = 0; i < 6; ++i) { c.g[i] = 0; c.dir[i] = 0; c.x_t[i] = 0; }
+    for (int i = 0; i < 36; ++i) c.H[i] = 0;
+    if (phase == PH_INIT) {
+        const float* G = guesses + (size_t)a * 16;
+        float T[16];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) T[i * 4 + j] = G[j * 4 + i];
+        // align() starts from final_transformation_ = I and pre-applies the guess when it is not the identity (:83-88)
+        for (int i = 0; i < 16; ++i) { c.M[i] = T[i]; c.final_T[i] = T[i]; }
+        const float R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+        float eul[3];
+        euler_012(R, eul);
+        c.p[0] = T[3]; c.p[1] = T[7]; c.p[2] = T[11];
+        c.p[3] = eul[0]; c.p[4] = eul[1]; c.p[5] = eul[2];
+        angle_tables(c.p, c.tab);
+        c.mode = MODE_DERIV_H;
+    } else {
+        for (int i = 0; i < 6; ++i) c.p[i] = p_in[(size_t)a * 6 + i];
+        pose_matrix(c.p, c.M);
+        for (int i = 0; i < 16; ++i) c.final_T[i] = c.M[i];
+        angle_tables(c.p, c.tab);
+        c.mode = (phase == PH_SINGLE_HESS) ? MODE_HESS_D : MODE_DERIV_H;
+    }
+}
+
+__global__ void k_ndt_count_done(const Ctl* ctls, int h, int* out) {
+    int cnt = 0;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < h; a += gridDim.x * blockDim.x) cnt += ctls[a].done ? 0 : 1;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+// ------------------------------------------------------------------ calculateScore for a batch of poses (:836-880)
+// One block per hypothesis; fp64 throughout like the reference.  Optionally packs (score, index) keys for the argmax.
+__global__ void __launch_bounds__(256) k_ndt_score_batch(View v, const float* __restrict__ poses /*h x 16 col-major*/, double* __restrict__ scores) {
+    __shared__ float M[12];
+    __shared__ double red[8];
+    const int h = blockIdx.x, tid = threadIdx.x;
+    if (tid < 12) M[tid] = poses[(size_t)h * 16 + (tid & 3) * 4 + (tid >> 2)];
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = tid; i < v.n_src; i += blockDim.x) {
+        const float4 p = __ldg(v.src + i);
+        float tx, ty, tz;
+        xform(M, p.x, p.y, p.z, tx, ty, tz);
+        int lf[27];
+        int cnt = 0;
+        for (int s = 0; s < v.nst; ++s) {
+            const int l = nbr_leaf(v, tx, ty, tz, s);
+            if (l >= 0) lf[cnt++] = l;
+        }
+        for (int c = 0; c < cnt; ++c) {
+            const double2* src = reinterpret_cast<const double2*>(v.leafD + lf[c]);
+            LeafD L;
+            double2* dst = reinterpret_cast<double2*>(&L);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[q] = __ldg(src + q);
+            const double xt[3] = {(double)tx - L.mean[0], (double)ty - L.mean[1], (double)tz - L.mean[2]};
+            double cx[3];
+            for (int kk = 0; kk < 3; ++kk) cx[kk] = L.icov[kk * 3] * xt[0] + L.icov[kk * 3 + 1] * xt[1] + L.icov[kk * 3 + 2] * xt[2];
+            const double e = exp(-v.d2 * (xt[0] * cx[0] + xt[1] * cx[1] + xt[2] * cx[2]) / 2);
+            const double inc = -v.d1 * e - v.d3;
+            acc += inc / cnt;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double a = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += red[w];
+        scores[h] = a / (double)v.n_src;
+    }
+}
+
+// number of (point, voxel) pairs and probes of one evaluation at the poses' transforms (roofline bookkeeping)
+__global__ void k_ndt_nbhd_total(View v, const float* __restrict__ M16_rowmajor, unsigned long long* out) {
+    unsigned long long cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_src; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(v.src + i);
+        float tx, ty, tz;
+        xform(M16_rowmajor, p.x, p.y, p.z, tx, ty, tz);
+        for (int s = 0; s < v.nst; ++s) cnt += nbr_leaf(v, tx, ty, tz, s) >= 0 ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+// Order-preserving map double -> uint64 (NaN -> 0, below every real score)
+__device__ __forceinline__ unsigned long long dbl_key(double s) {
+    if (s != s) return 0ull;
+    unsigned long long u = (unsigned long long)__double_as_longlong(s);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+// best[0] = max over this rank's slice of the score key
+__global__ void k_best_score(const double* __restrict__ scores, int64_t h, unsigned long long* best) {
+    unsigned long long b = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = dbl_key(scores[i]);
+        b = key > b ? key : b;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, b, o);
+        b = o2 > b ? o2 : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
+}
+// idx[0] = lowest global hypothesis index on this rank whose key equals the global best (else ~0)
+__global__ void k_best_index(const double* __restrict__ scores, int64_t h, int64_t h_begin, const unsigned long long* __restrict__ gbest,
+                             unsigned long long* idx) {
+    const unsigned long long g = *gbest;
+    unsigned long long b = ~0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h; i += (int64_t)gridDim.x * blockDim.x)
+        if (g != 0 && dbl_key(scores[i]) == g) { const unsigned long long v = (unsigned long long)(h_begin + i); b = v < b ? v : b; }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, b, o);
+        b = o2 < b ? o2 : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b != ~0ull) atomicMin(idx, b);
+}
+
+// ------------------------------------------------------------------ host object
+struct Ndt {
+    b200_ndt_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int eval_blocks_per_sm = 0;
+    // target
+    GridDims gd{};
+    int64_t ncells = 0;
+    int nruns = 0, n_valid = 0;
+    DevBuf<float4> d_tgt, d_src;
+    DevBuf<int32_t> d_cell2leaf;
+    DevBuf<LeafF> d_leafF;
+    DevBuf<LeafD> d_leafD;
+    DevBuf<double> d_cov, d_sums;
+    DevBuf<int32_t> d_npts, d_vals_in, d_vals_out, d_run_cnt, d_run_off, d_small;
+    DevBuf<uint32_t> d_keys_in, d_keys_out, d_uniq;
+    DevBuf<uint8_t> d_valid, cub_tmp;
+    PinnedBuf<float4> h_stage;
+    PinnedBuf<int32_t> h_small;
+    int n_src = 0;
+    bool have_target = false;
+    // align
+    DevBuf<Ctl> d_ctl;
+    DevBuf<double> d_partials, d_p_in, d_scores;
+    DevBuf<float> d_poses;
+    PinnedBuf<Ctl> h_ctl;
+    PinnedBuf<double> h_scores;
+    PinnedBuf<float> h_poses;
+    DevBuf<unsigned long long> d_best;
+    PinnedBuf<unsigned long long> h_best;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double d1 = 0, d2 = 0, d3 = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+
+    int32_t init(const b200_ndt_params* p, int dev);
+    void destroy();
+    void gauss();
+    View view() const;
+    int32_t upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>& dst);
+    int32_t set_target(const float* xyz, int64_t n, int64_t stride);
+    int32_t build_target(int64_t n);
+    int32_t set_source(const float* xyz, int64_t n, int64_t stride);
+    int32_t run(int h, const float* d_guesses, const double* d_p, int phase);
+    int32_t score_batch_device(const float* d_poses16, int64_t h, double* d_out);
+};
+
+int32_t Ndt::init(const b200_ndt_params* p, int dev) {
+    prm = *p;
+    if (!(prm.resolution > 0.f)) B200_FAIL(B200_ERR_ARG, "resolution must be > 0");
+    if (prm.search != 1 && prm.search != 27) prm.search = 7;
+    if (prm.min_pts <= 0) prm.min_pts = 6;
+    if (!(prm.eig_ratio > 0)) prm.eig_ratio = 0.01;
+    device = dev;
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(d_small.reserve(16));
+    CUDA_TRY(h_small.reserve(16));
+    CUDA_TRY(d_best.reserve(4));
+    CUDA_TRY(h_best.reserve(4));
+    gauss();
+    return B200_OK;
+}
+
+void Ndt::destroy() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    d_tgt.release(); d_src.release(); d_cell2leaf.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
+    d_npts.release(); d_vals_in.release(); d_vals_out.release(); d_run_cnt.release(); d_run_off.release(); d_small.release();
+    d_keys_in.release(); d_keys_out.release(); d_uniq.release(); d_valid.release(); cub_tmp.release();
+    h_stage.release(); h_small.release(); d_ctl.release(); d_partials.release(); d_p_in.release(); d_scores.release(); d_poses.release();
+    h_ctl.release(); h_scores.release(); h_poses.release(); d_best.release(); h_best.release();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+}
+
+void Ndt::gauss() {  // ndt_omp_impl.hpp:77-81
+    const double c1 = 10 * (1 - prm.outlier_ratio);
+    const double c2 = prm.outlier_ratio / std::pow((double)prm.resolution, 3);
+    d3 = -std::log(c2);
+    d1 = -std::log(c1 + c2) - d3;
+    d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / d1);
+}
+
+View Ndt::view() const {
+    View v;
+    v.src = d_src.p; v.n_src = n_src;
+    v.cell2leaf = d_cell2leaf.p; v.leafF = d_leafF.p; v.leafD = d_leafD.p;
+    for (int k = 0; k < 3; ++k) { v.min_b[k] = gd.min_b[k]; v.max_b[k] = gd.max_b[k]; v.mul[k] = gd.mul[k]; }
+    v.leaf = prm.resolution;
+    v.nst = prm.search;
+    v.d1 = d1; v.d2 = d2; v.d3 = d3;
+    return v;
+}
+
+// strided host cloud -> pinned float4 staging (a few host threads) -> device
+int32_t Ndt::upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>& dst) {
+    CUDA_TRY(h_stage.reserve((size_t)n));
+    CUDA_TRY(dst.reserve((size_t)n));
+    const int nt = n > (1 << 20) ? 8 : 1;
+    if (nt == 1) pack_xyz_float4(xyz, n, stride, h_stage.p);
+    else {
+        std::vector<std::thread> th;
+        const int64_t per = (n + nt - 1) / nt;
+        for (int t = 0; t < nt; ++t) {
+            const int64_t b = t * per, e = std::min<int64_t>(n, b + per);
+            if (b >= e) break;
+            th.emplace_back([=]() { pack_xyz_float4((const float*)((const char*)xyz + b * stride), e - b, stride, h_stage.p + b); });
+        }
+        for (auto& t : th) t.join();
+    }
+    CUDA_TRY(cudaMemcpyAsync(dst.p, h_stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    return B200_OK;
+}
+
+int32_t Ndt::set_target(const float* xyz, int64_t n, int64_t stride) {
+    if (n < 1 || !xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "bad target cloud");
+    if (n > (int64_t)0x7fffff00) B200_FAIL(B200_ERR_ARG, "target cloud too large");
+    CUDA_TRY(cudaSetDevice(device));
+    int32_t rc = upload(xyz, n, stride, d_tgt);
+    if (rc) return rc;
+    return build_target(n);
+}
+
+int32_t Ndt::build_target(int64_t n) {
+    have_target = false;
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    int* mm = d_small.p;
+    k_ndt_minmax_init<<<1, 32, 0, stream>>>(mm);
+    k_ndt_minmax<<<sm_count * 8, 256, 0, stream>>>(d_tgt.p, n, mm);
+    CUDA_TRY(cudaMemcpyAsync(h_small.p, mm, 6 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+        int a = h_small.p[k], b = h_small.p[3 + k];
+        a = a >= 0 ? a : a ^ 0x7fffffff;
+        b = b >= 0 ? b : b ^ 0x7fffffff;
+        memcpy(&mn[k], &a, 4);
+        memcpy(&mx[k], &b, 4);
+    }
+    if (!(mn[0] <= mx[0])) B200_FAIL(B200_ERR_ARG, "target cloud has no finite point");
+    // applyFilter (:67-103)
+    const float inv_leaf = 1.0f / prm.resolution;
+    const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv_leaf) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv_leaf) + 1,
+                  dz = (int64_t)((mx[2] - mn[2]) * inv_leaf) + 1;
+    if (dx * dy * dz > (int64_t)INT32_MAX) B200_FAIL(B200_ERR_RANGE, "leaf size too small for the target: integer leaf indices would overflow");
+    gd.inv_leaf = inv_leaf;
+    for (int k = 0; k < 3; ++k) {
+        gd.min_b[k] = (int)std::floor(mn[k] * inv_leaf);
+        gd.max_b[k] = (int)std::floor(mx[k] * inv_leaf);
+        gd.div_b[k] = gd.max_b[k] - gd.min_b[k] + 1;
+    }
+    gd.mul[0] = 1; gd.mul[1] = gd.div_b[0]; gd.mul[2] = gd.div_b[0] * gd.div_b[1];
+    ncells = (int64_t)gd.div_b[0] * gd.div_b[1] * gd.div_b[2];
+    if (ncells > ((int64_t)1 << 30)) B200_FAIL(B200_ERR_RANGE, "NDT grid too large for the dense cell table (> 2^30 cells)");
+    CUDA_TRY(d_cell2leaf.reserve((size_t)ncells));
+    CUDA_TRY(cudaMemsetAsync(d_cell2leaf.p, 0xFF, (size_t)ncells * sizeof(int32_t), stream));
+    CUDA_TRY(d_keys_in.reserve(n)); CUDA_TRY(d_keys_out.reserve(n)); CUDA_TRY(d_uniq.reserve(n));
+    CUDA_TRY(d_vals_in.reserve(n)); CUDA_TRY(d_vals_out.reserve(n)); CUDA_TRY(d_run_cnt.reserve(n)); CUDA_TRY(d_run_off.reserve(n));
+    const int nb = (int)((n + 255) / 256);
+    const uint32_t sentinel = (uint32_t)ncells;  // key of non-finite points: one past the last leaf id, sorts last
+    k_ndt_keys<<<nb, 256, 0, stream>>>(d_tgt.p, (int)n, gd, sentinel, d_keys_in.p, d_vals_in.p);
+    int end_bit = 1;
+    while (end_bit < 32 && ((int64_t)1 << end_bit) <= ncells) ++end_bit;
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    int32_t* d_nruns = d_small.p + 8;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, d_keys_in.p, d_keys_out.p, d_vals_in.p, d_vals_out.p, (int)n, 0, end_bit, stream);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t2, d_keys_out.p, d_uniq.p, d_run_cnt.p, d_nruns, (int)n, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, d_run_cnt.p, d_run_off.p, (int)n, stream);
+    size_t tmp = std::max(t1, std::max(t2, t3));
+    CUDA_TRY(cub_tmp.reserve(tmp));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, d_keys_in.p, d_keys_out.p, d_vals_in.p, d_vals_out.p, (int)n, 0, end_bit, stream));
+    CUDA_TRY(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, tmp, d_keys_out.p, d_uniq.p, d_run_cnt.p, d_nruns, (int)n, stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, d_run_cnt.p, d_run_off.p, (int)n, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_small.p, d_nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    nruns = h_small.p[0];
+    CUDA_TRY(d_sums.reserve((size_t)nruns * 9));
+    CUDA_TRY(d_leafF.reserve(nruns)); CUDA_TRY(d_leafD.reserve(nruns)); CUDA_TRY(d_cov.reserve((size_t)nruns * 9));
+    CUDA_TRY(d_npts.reserve(nruns)); CUDA_TRY(d_valid.reserve(nruns));
+    int32_t* d_nvalid = d_small.p + 9;
+    CUDA_TRY(cudaMemsetAsync(d_nvalid, 0, sizeof(int32_t), stream));
+    CUDA_TRY(cudaMemsetAsync(d_cov.p, 0, (size_t)nruns * 9 * sizeof(double), stream));
+    const int acc_blocks = std::min((nruns + 7) / 8, sm_count * 8);
+    k_ndt_accumulate<<<std::max(acc_blocks, 1), 256, 0, stream>>>(d_tgt.p, d_vals_out.p, d_uniq.p, d_run_off.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p);
+    k_ndt_finalize<<<(nruns + 127) / 128, 128, 0, stream>>>(d_uniq.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p, prm.min_pts, prm.eig_ratio, d_leafF.p,
+                                                            d_leafD.p, d_cov.p, d_npts.p, d_valid.p, d_cell2leaf.p, d_nvalid);
+    LAUNCH_COUNT(5);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_small.p, d_nvalid, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    n_valid = h_small.p[0];
+    cudaEventElapsedTime(&last_ms, ev0, ev1);
+    have_target = true;
+    return B200_OK;
+}
+
+int32_t Ndt::set_source(const float* xyz, int64_t n, int64_t stride) {
+    if (n < 1 || !xyz || stride < 12 || n > (1 << 28)) B200_FAIL(B200_ERR_ARG, "bad source cloud");
+    CUDA_TRY(cudaSetDevice(device));
+    int32_t rc = upload(xyz, n, stride, d_src);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    n_src = (int)n;
+    return B200_OK;
+}
+
+// Runs h independent state machines to completion.  d_guesses (h x 16, col-major) for PH_INIT, d_p (h x 6) otherwise.
+int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
+    if (!have_target) B200_FAIL(B200_ERR_ARG, "no target set");
+    if (n_src < 1) B200_FAIL(B200_ERR_ARG, "no source set");
+    CUDA_TRY(d_ctl.reserve(h));
+    CUDA_TRY(h_ctl.reserve(h));
+    const int64_t items = (int64_t)n_src * prm.search;
+    if (!eval_blocks_per_sm) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_blocks_per_sm, k_ndt_eval, EVAL_THREADS, 0));
+        if (eval_blocks_per_sm < 1) eval_blocks_per_sm = 1;
+    }
+    // one resident wave: blocks of all alignments together fill the SMs once (grid-stride inside)
+    int nbx = (int)std::min<int64_t>((items + EVAL_THREADS - 1) / EVAL_THREADS, (int64_t)std::max(1, eval_blocks_per_sm * sm_count / h));
+    if (nbx < 1) nbx = 1;
+    CUDA_TRY(d_partials.reserve((size_t)h * NACC * nbx));
+    gauss();  // recomputed at every computeTransformation (ndt_omp_impl.hpp:77-81)
+    const View v = view();
+    AlignConsts k{prm.step_size, prm.trans_eps, prm.max_iter, n_src};
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    k_ndt_init<<<(h + 63) / 64, 64, 0, stream>>>(d_ctl.p, h, d_guesses, d_p, phase);
+    int launches = 1;
+    const bool single = phase != PH_INIT;
+    int* d_left = d_small.p + 10;
+    // worst case per alignment: (max_iter + 2) iterations x (1 + 10 trials + 1 Hessian) evaluations
+    const int max_launches = single ? 1 : (prm.max_iter + 3) * 12 + 1;
+    while (launches - 1 < max_launches) {
+        const int batch = single ? 1 : LAUNCH_BATCH;
+        for (int b = 0; b < batch; ++b) k_ndt_eval<<<dim3(nbx, h), EVAL_THREADS, 0, stream>>>(v, d_ctl.p, k, d_partials.p);
+        launches += batch;
+        if (single) break;
+        CUDA_TRY(cudaMemsetAsync(d_left, 0, sizeof(int), stream));
+        k_ndt_count_done<<<std::min((h + 255) / 256, 64), 256, 0, stream>>>(d_ctl.p, h, d_left);
+        ++launches;
+        CUDA_TRY(cudaMemcpyAsync(h_small.p, d_left, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h_small.p[0] == 0) break;
+    }
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_ctl.p, d_ctl.p, (size_t)h * sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&last_ms, ev0, ev1);
+    LAUNCH_COUNT(launches);
+    last_launches = launches;
+    return B200_OK;
+}
+
+int32_t Ndt::score_batch_device(const float* d_poses16, int64_t h, double* d_out) {
+    if (!have_target) B200_FAIL(B200_ERR_ARG, "no target set");
+    if (n_src < 1) B200_FAIL(B200_ERR_ARG, "no source set");
+    gauss();
+    k_ndt_score_batch<<<(unsigned)h, 256, 0, stream>>>(view(), d_poses16, d_out);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+}  // namespace ndt
+}  // namespace b200
+
+// ------------------------------------------------------------------ NCCL communicator (loaded at run time)
+#include "comm.cuh"
+
+// ------------------------------------------------------------------ C ABI (B3)
+using namespace b200;
+using b200::ndt::Ndt;
+struct b200_ndt { Ndt k; };
+
+static void fill_result(const ndt::Ctl& c, float* final16, b200_ndt_result* r, float ms) {
+    if (final16)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) final16[j * 4 + i] = c.final_T[i * 4 + j];
+    if (r) {
+        r->converged = c.converged;
+        r->iters = c.nr_iterations;
+        r->evals = c.evals;
+        r->hess_evals = c.hess_evals;
+        r->trans_probability = c.trans_probability;
+        memcpy(r->hessian, c.H, sizeof(double) * 36);
+        r->score = c.score;
+        memcpy(r->p_final, c.p, sizeof(double) * 6);
+        r->gpu_ms = ms;
+    }
+}
+
+extern "C" {
+
+int32_t b200_ndt_create(const b200_ndt_params* params, int32_t device, b200_ndt** out) {
+    if (!params || !out) B200_FAIL(B200_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B200_FAIL(B200_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) B200_FAIL(B200_ERR_ARG, "bad device ordinal");
+    b200_ndt* h = new b200_ndt();
+    int32_t rc = h->k.init(params, device);
+    if (rc != B200_OK) { h->k.destroy(); delete h; return rc; }
+    *out = h;
+    return B200_OK;
+}
+int32_t b200_ndt_destroy(b200_ndt* n) {
+    if (!n) return B200_OK;
+    n->k.destroy();
+    delete n;
+    return B200_OK;
+}
+int32_t b200_ndt_set_target(b200_ndt* n, const float* xyz, int64_t cnt, int64_t stride) {
+    if (!n) B200_FAIL(B200_ERR_ARG, "null handle");
+    return n->k.set_target(xyz, cnt, stride);
+}
+int32_t b200_ndt_set_source(b200_ndt* n, const float* xyz, int64_t cnt, int64_t stride) {
+    if (!n) B200_FAIL(B200_ERR_ARG, "null handle");
+    return n->k.set_source(xyz, cnt, stride);
+}
+int64_t b200_ndt_num_voxels(b200_ndt* n) { return n ? (int64_t)n->k.n_valid : 0; }
+float b200_ndt_last_ms(b200_ndt* n) { return n ? n->k.last_ms : 0.f; }
+int32_t b200_ndt_last_launches(b200_ndt* n) { return n ? n->k.last_launches : 0; }
+
+int64_t b200_ndt_leaves(b200_ndt* n, int64_t max, int64_t* ids, int32_t* npts, double* mean3, double* cov9, double* icov9) {
+    if (!n || !n->k.have_target) return 0;
+    Ndt& k = n->k;
+    cudaSetDevice(k.device);
+    const int nr = k.nruns;
+    std::vector<uint8_t> valid(nr);
+    std::vector<uint32_t> uniq(nr);
+    std::vector<int32_t> np(nr);
+    std::vector<ndt::LeafD> L(nr);
+    std::vector<double> cov((size_t)nr * 9);
+    cudaStreamSynchronize(k.stream);
+    cudaMemcpy(valid.data(), k.d_valid.p, nr, cudaMemcpyDeviceToHost);
+    cudaMemcpy(uniq.data(), k.d_uniq.p, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(np.data(), k.d_npts.p, nr * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(L.data(), k.d_leafD.p, nr * sizeof(ndt::LeafD), cudaMemcpyDeviceToHost);
+    cudaMemcpy(cov.data(), k.d_cov.p, (size_t)nr * 9 * sizeof(double), cudaMemcpyDeviceToHost);
+    int64_t cnt = 0;
+    for (int r = 0; r < nr; ++r) {  // runs are sorted by leaf id
+        if (!valid[r]) continue;
+        if (cnt < max) {
+            if (ids) ids[cnt] = (int64_t)uniq[r];
+            if (npts) npts[cnt] = np[r];
+            if (mean3) memcpy(mean3 + cnt * 3, L[r].mean, 24);
+            if (cov9) memcpy(cov9 + cnt * 9, &cov[(size_t)r * 9], 72);
+            if (icov9) memcpy(icov9 + cnt * 9, L[r].icov, 72);
+        }
+        ++cnt;
+    }
+    return cnt;
+}
+
+int32_t b200_ndt_grid(b200_ndt* n, int32_t* min_b3, int32_t* div_b3) {
+    if (!n || !n->k.have_target) B200_FAIL(B200_ERR_ARG, "no target set");
+    for (int k = 0; k < 3; ++k) {
+        if (min_b3) min_b3[k] = n->k.gd.min_b[k];
+        if (div_b3) div_b3[k] = n->k.gd.div_b[k];
+    }
+    return B200_OK;
+}
+
+int32_t b200_ndt_align(b200_ndt* n, const float* guess16, float* final16, b200_ndt_result* result) {
+    if (!n || !guess16 || !final16) B200_FAIL(B200_ERR_ARG, "null argument");
+    Ndt& k = n->k;
+    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_TRY(k.d_poses.reserve(16));
+    CUDA_TRY(k.h_poses.reserve(16));
+    memcpy(k.h_poses.p, guess16, 16 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
+    int32_t rc = k.run(1, k.d_poses.p, nullptr, ndt::PH_INIT);
+    if (rc) return rc;
+    const ndt::Ctl& c = k.h_ctl.p[0];
+    fill_result(c, final16, result, k.last_ms);
+    if (!c.done) { B200_FAIL(B200_NOT_CONVERGED, "evaluation budget exhausted"); }
+    return c.converged ? B200_OK : B200_NOT_CONVERGED;
+}
+
+/* align() for h independent initial guesses in one batch (global relocalization with refinement): results[h], finals h x 16 */
+int32_t b200_ndt_align_batch(b200_ndt* n, const float* guesses16, int64_t h, float* finals16, b200_ndt_result* results) {
+    if (!n || !guesses16 || h < 1 || h > 65535) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_TRY(k.d_poses.reserve((size_t)h * 16));
+    CUDA_TRY(k.h_poses.reserve((size_t)h * 16));
+    memcpy(k.h_poses.p, guesses16, (size_t)h * 16 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, (size_t)h * 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
+    int32_t rc = k.run((int)h, k.d_poses.p, nullptr, ndt::PH_INIT);
+    if (rc) return rc;
+    for (int64_t a = 0; a < h; ++a) fill_result(k.h_ctl.p[a], finals16 ? finals16 + a * 16 : nullptr, results ? results + a : nullptr, k.last_ms);
+    return B200_OK;
+}
+
+static int32_t single_eval(Ndt& k, const double* p6, int phase) {
+    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_TRY(k.d_p_in.reserve(6));
+    CUDA_TRY(k.h_scores.reserve(8));
+    memcpy(k.h_scores.p, p6, 6 * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(k.d_p_in.p, k.h_scores.p, 6 * sizeof(double), cudaMemcpyHostToDevice, k.stream));
+    return k.run(1, nullptr, k.d_p_in.p, phase);
+}
+
+int32_t b200_ndt_derivatives(b200_ndt* n, const double* p6, double* score, double* g6, double* H36) {
+    if (!n || !p6) B200_FAIL(B200_ERR_ARG, "null argument");
+    int32_t rc = single_eval(n->k, p6, ndt::PH_SINGLE_DERIV);
+    if (rc) return rc;
+    const ndt::Ctl& c = n->k.h_ctl.p[0];
+    if (score) *score = c.score;
+    if (g6) memcpy(g6, c.g, 48);
+    if (H36) memcpy(H36, c.H, 288);
+    return B200_OK;
+}
+
+int32_t b200_ndt_hessian(b200_ndt* n, const double* p6, double* H36) {
+    if (!n || !p6 || !H36) B200_FAIL(B200_ERR_ARG, "null argument");
+    int32_t rc = single_eval(n->k, p6, ndt::PH_SINGLE_HESS);
+    if (rc) return rc;
+    memcpy(H36, n->k.h_ctl.p[0].H, 288);
+    return B200_OK;
+}
+
+int32_t b200_ndt_score_batch(b200_ndt* n, const float* poses16, int64_t h, double* scores) {
+    if (!n || !poses16 || !scores || h < 1) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_TRY(k.d_poses.reserve((size_t)h * 16)); CUDA_TRY(k.h_poses.reserve((size_t)h * 16));
+    CUDA_TRY(k.d_scores.reserve(h)); CUDA_TRY(k.h_scores.reserve(h));
+    memcpy(k.h_poses.p, poses16, (size_t)h * 16 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, (size_t)h * 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
+    CUDA_TRY(cudaEventRecord(k.ev0, k.stream));
+    int32_t rc = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(k.ev1, k.stream));
+    CUDA_TRY(cudaMemcpyAsync(k.h_scores.p, k.d_scores.p, (size_t)h * sizeof(double), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    cudaEventElapsedTime(&k.last_ms, k.ev0, k.ev1);
+    memcpy(scores, k.h_scores.p, (size_t)h * sizeof(double));
+    return B200_OK;
+}
+
+/* roofline bookkeeping: number of (point, voxel) pairs one evaluation at pose p6 touches */
+int64_t b200_ndt_nbhd_total(b200_ndt* n, const double* p6) {
+    if (!n || !p6 || !n->k.have_target || n->k.n_src < 1) return -1;
+    Ndt& k = n->k;
+    cudaSetDevice(k.device);
+    // build the float matrix on the host the same way (only used for counting)
+    float M[16];
+    {
+        const float rx = (float)p6[3], ry = (float)p6[4], rz = (float)p6[5];
+        const float cx = (float)std::cos((double)rx), sx = (float)std::sin((double)rx), cy = (float)std::cos((double)ry),
+                    sy = (float)std::sin((double)ry), cz = (float)std::cos((double)rz), sz = (float)std::sin((double)rz);
+        const float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+        float T1[9], T2[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) T1[i * 3 + j] = (Rx[i * 3] * Ry[j] + Rx[i * 3 + 1] * Ry[3 + j]) + Rx[i * 3 + 2] * Ry[6 + j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) T2[i * 3 + j] = (T1[i * 3] * Rz[j] + T1[i * 3 + 1] * Rz[3 + j]) + T1[i * 3 + 2] * Rz[6 + j];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) M[i * 4 + j] = T2[i * 3 + j];
+            M[i * 4 + 3] = (float)p6[i];
+        }
+        M[12] = M[13] = M[14] = 0.f; M[15] = 1.f;
+    }
+    if (k.d_poses.reserve(16) != cudaSuccess || k.h_poses.reserve(16) != cudaSuccess) return -1;
+    memcpy(k.h_poses.p, M, sizeof M);
+    cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, sizeof M, cudaMemcpyHostToDevice, k.stream);
+    cudaMemsetAsync(k.d_best.p, 0, sizeof(unsigned long long), k.stream);
+    ndt::k_ndt_nbhd_total<<<k.sm_count, 256, 0, k.stream>>>(k.view(), k.d_poses.p, k.d_best.p);
+    cudaMemcpyAsync(k.h_best.p, k.d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, k.stream);
+    cudaStreamSynchronize(k.stream);
+    return (int64_t)k.h_best.p[0];
+}
+
+/* Global relocalization: score hypotheses h_begin .. h_begin+h-1 on this rank (calculateScore; the cost that is
+ * minimised is -score, i.e. the winner is the most likely pose), then an allreduce-argmin across ranks: one 8-byte
+ * ncclAllReduce(max) on the order-preserving score key, one 8-byte ncclAllReduce(min) on the index of the rank(s)
+ * holding that key - exact in fp64, ties to the lowest hypothesis index, identical result on every rank. */
+int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t* best, double* best_score,
+                          float* gpu_ms) {
+    if (!n || (h > 0 && !poses16) || h < 0 || h_begin < 0) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    CUDA_TRY(cudaSetDevice(k.device));
+    const int64_t hh = std::max<int64_t>(h, 1);
+    CUDA_TRY(k.d_poses.reserve((size_t)hh * 16)); CUDA_TRY(k.h_poses.reserve((size_t)hh * 16));
+    CUDA_TRY(k.d_scores.reserve(hh));
+    CUDA_TRY(k.d_best.reserve(4)); CUDA_TRY(k.h_best.reserve(4));
+    if (h) {
+        memcpy(k.h_poses.p, poses16, (size_t)h * 16 * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, (size_t)h * 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
+    }
+    unsigned long long* d = k.d_best.p;  // [0] local best key, [1] global best key, [2] local index, [3] global index
+    CUDA_TRY(cudaEventRecord(k.ev0, k.stream));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), k.stream));
+    CUDA_TRY(cudaMemsetAsync(d + 2, 0xFF, 2 * sizeof(unsigned long long), k.stream));
+    const unsigned nb = (unsigned)std::min<int64_t>((hh + 255) / 256, 64);
+    if (h) {
+        int32_t rc = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
+        if (rc) return rc;
+        ndt::k_best_score<<<nb, 256, 0, k.stream>>>(k.d_scores.p, h, d);
+    }
+    if (comm && comm->nranks > 1) {
+        int32_t rc = b200::comm_allreduce_u64(comm, d, d + 1, ncclMax, k.stream);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(d + 1, d, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
+    }
+    if (h) ndt::k_best_index<<<nb, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, d + 1, d + 2);
+    if (comm && comm->nranks > 1) {
+        int32_t rc = b200::comm_allreduce_u64(comm, d + 2, d + 3, ncclMin, k.stream);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(d + 3, d + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
+    }
+    LAUNCH_COUNT(h ? 2 : 0);
+    CUDA_TRY(cudaEventRecord(k.ev1, k.stream));
+    CUDA_TRY(cudaMemcpyAsync(k.h_best.p, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&k.last_ms, k.ev0, k.ev1);
+    if (gpu_ms) *gpu_ms = k.last_ms;
+    const unsigned long long key = k.h_best.p[1], idx = k.h_best.p[3];
+    if (key == 0 || idx == ~0ull) { if (best) *best = -1; if (best_score) *best_score = 0; return B200_NO_EFFECTIVE_POINTS; }
+    const unsigned long long u = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+    double sc;
+    memcpy(&sc, &u, 8);
+    if (best) *best = (int64_t)idx;
+    if (best_score) *best_score = sc;
+    return B200_OK;
+}
+
+}  // extern "C"

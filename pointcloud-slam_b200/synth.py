@@ -15,8 +15,10 @@ SEED = 20261018
 ROOM = np.array([[-60.0, -40.0, 0.0], [60.0, 40.0, 8.0]])
 
 
-def make_world(seed: int = SEED, n_obstacles: int = 40, offset=(0.0, 0.0, 0.0)):
-    """Returns (room[2,3], boxes[n,2,3]) — axis-aligned obstacle boxes standing on the floor."""
+def make_world(seed: int = SEED, n_obstacles: int = 40, offset=(0.0, 0.0, 0.0), beams: bool = False):
+    """Returns (room[2,3], boxes[n,2,3]) — axis-aligned obstacle boxes standing on the floor.
+    beams=True adds a roof truss (0.4 m x 0.8 m beams hanging from the ceiling every 6 m in x and 8 m in y) so that
+    an upward-looking scan, which sees mostly ceiling, still constrains x/y (used by the NDT configs)."""
     rng = np.random.default_rng(seed)
     size = rng.uniform(1.0, 6.0, size=(n_obstacles, 3))
     size[:, 2] = np.minimum(size[:, 2], 5.0)
@@ -24,6 +26,16 @@ def make_world(seed: int = SEED, n_obstacles: int = 40, offset=(0.0, 0.0, 0.0)):
                       rng.uniform(ROOM[0, 1] + 2, ROOM[1, 1] - 8, n_obstacles)], 1)
     lo = np.concatenate([lo_xy, np.zeros((n_obstacles, 1))], 1)
     boxes = np.stack([lo, lo + size], 1)
+    if beams:
+        bl = []
+        jit = rng.uniform(-1.0, 1.0, 64)
+        for k, x0 in enumerate(np.arange(ROOM[0, 0] + 3.0, ROOM[1, 0] - 1.0, 6.0)):
+            x0 = x0 + jit[k]
+            bl.append([[x0, ROOM[0, 1], ROOM[1, 2] - 0.8], [x0 + 0.4, ROOM[1, 1], ROOM[1, 2]]])
+        for k, y0 in enumerate(np.arange(ROOM[0, 1] + 4.0, ROOM[1, 1] - 1.0, 8.0)):
+            y0 = y0 + jit[32 + k]
+            bl.append([[ROOM[0, 0], y0, ROOM[1, 2] - 0.5], [ROOM[1, 0], y0 + 0.4, ROOM[1, 2]]])
+        boxes = np.concatenate([boxes, np.array(bl)], 0)
     off = np.asarray(offset, dtype=np.float64)
     return ROOM + off, boxes + off
 
@@ -48,15 +60,17 @@ def _faces(room, boxes):
 
     add_box(room[0], room[1], True)
     for b in boxes:
-        # the bottom face of an obstacle sits on the floor: skip it
+        # the face of an obstacle that lies in the floor (or, for a roof beam, in the ceiling) is not a surface: skip it
         lo, hi = b
+        on_floor = abs(lo[2] - room[0][2]) < 1e-9
+        on_ceiling = abs(hi[2] - room[1][2]) < 1e-9
         d = hi - lo
         for ax in range(3):
             u, v = (ax + 1) % 3, (ax + 2) % 3
             eu = np.zeros(3); eu[u] = d[u]
             ev = np.zeros(3); ev[v] = d[v]
             for side in (0, 1):
-                if ax == 2 and side == 0:
+                if ax == 2 and ((side == 0 and on_floor) or (side == 1 and on_ceiling)):
                     continue
                 o = lo.copy()
                 if side:
@@ -213,7 +227,7 @@ def prior_map(n_points=10_000_000, seed: int = SEED):
     per = n_points // 4
     tiles, worlds = [], []
     for k, (ox, oy) in enumerate([(0, 0), (120, 0), (0, 80), (120, 80)]):
-        w = make_world(seed + 100 * k, offset=(ox, oy, 0))
+        w = make_world(seed + 100 * k, offset=(ox, oy, 0), beams=True)
         worlds.append(w)
         tiles.append(sample_map(per if k < 3 else n_points - 3 * per, seed + 100 * k, world=w))
     return np.concatenate(tiles, 0), worlds

@@ -1,0 +1,164 @@
+"""Parity of the CUDA NDT path (through the C ABI) against the CPU oracle.
+
+Bars: voxel membership / point counts exact, leaf mean / covariance / inverse covariance bit-exact (the device
+accumulates each leaf in input order with the same fp64 op sequence); score / gradient / Hessian within 1e-6
+relative (north_star "H/b within 1e-6"); align() poses within 1e-4 m / 1e-4 rad with the same iteration and
+evaluation counts; calculateScore within 1e-12 relative and the same argmax.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H_TOL = 1e-6
+POSE_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ndt_small(synth):
+    world = synth.make_world(synth.SEED, beams=True)
+    mp = synth.sample_map(300_000, synth.SEED, world=world)
+    p_true = np.array([3.0, -2.0, 1.2, 0.0, 0.0, 0.6])
+    T = synth.pose_vec_to_matrix(p_true)
+    dirs = synth.livox_dirs(5000, synth.SEED)
+    scan = np.ascontiguousarray(synth.raycast(T[:3, 3], T[:3, :3], dirs, world, seed=synth.SEED)[:4000])
+    return dict(map=mp, scan=scan, p_true=p_true, T_true=T)
+
+
+def pair(oracle, api, cfg, **kw):
+    o = oracle.OracleNdt(**kw)
+    o.set_target(cfg["map"])
+    o.set_source(cfg["scan"])
+    g = api.NormalDistributionsTransform()
+    g.setResolution(kw.get("resolution", 1.0))
+    g.setTransformationEpsilon(kw.get("trans_eps", 0.01))
+    g.setStepSize(kw.get("step_size", 0.1))
+    g.setMaximumIterations(kw.get("max_iter", 35))
+    g.setNeighborhoodSearchMethod(kw.get("search", 7))
+    g.setInputTarget(cfg["map"])
+    g.setInputSource(cfg["scan"])
+    return o, g
+
+
+def relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("res", [0.5, 1.0, 2.0])
+def test_voxel_leaves_bit_exact(oracle, api, ndt_small, res):
+    o, g = pair(oracle, api, ndt_small, resolution=res)
+    Lo, Lg = o.leaves(), g.leaves()
+    assert g.numVoxels() == len(Lo["ids"])
+    gm, gd = g.grid()
+    om, od = o.grid()
+    assert list(gm) == list(om) and list(gd) == list(od)
+    np.testing.assert_array_equal(Lg["ids"], Lo["ids"])
+    np.testing.assert_array_equal(Lg["npts"], Lo["npts"])
+    np.testing.assert_array_equal(Lg["mean"], Lo["mean"])
+    np.testing.assert_array_equal(Lg["cov"], Lo["cov"])
+    np.testing.assert_array_equal(Lg["icov"], Lo["icov"])
+
+
+def test_target_with_nonfinite_and_sparse_points(oracle, api, ndt_small):
+    mp = ndt_small["map"][:40_000].copy()
+    mp[5] = [np.nan, 0, 0]
+    mp[77] = [0, np.inf, 0]
+    cfg = dict(map=mp, scan=ndt_small["scan"])
+    o, g = pair(oracle, api, cfg, resolution=1.0)   # 40k points: most voxels hold fewer than 6 points
+    Lo, Lg = o.leaves(), g.leaves()
+    np.testing.assert_array_equal(Lg["ids"], Lo["ids"])
+    np.testing.assert_array_equal(Lg["icov"], Lo["icov"])
+
+
+@pytest.mark.parametrize("search", [1, 7, 27])
+def test_derivatives_parity(oracle, api, ndt_small, search):
+    o, g = pair(oracle, api, ndt_small, search=search)
+    for d in ([0, 0, 0, 0, 0, 0], [0.12, -0.08, 0.03, 0.004, -0.006, 0.01], [0.4, 0.3, -0.1, 0.02, 0.03, -0.05]):
+        p = ndt_small["p_true"] + np.array(d)
+        s0, g0, H0 = o.derivatives(p)
+        s1, g1, H1 = g.computeDerivatives(p)
+        assert abs(s1 - s0) <= H_TOL * abs(s0)
+        assert relerr(g1, g0) <= H_TOL
+        assert relerr(H1, H0) <= H_TOL
+        assert g.nbhd_total(p) == o.nbhd_total(p)
+
+
+def test_double_hessian_parity(oracle, api, ndt_small):
+    o, g = pair(oracle, api, ndt_small)
+    p = ndt_small["p_true"] + np.array([0.05, 0.02, -0.01, 0.003, -0.002, 0.02])
+    H0 = o.hessian(p)
+    H1 = g.computeHessian(p)
+    assert relerr(H1, H0) <= 1e-10
+
+
+@pytest.mark.parametrize("start", [[0.05, -0.04, 0.02, 0.0, 0.0, 0.005], [0.3, -0.25, 0.0, 0.0, 0.0, 0.035], [0, 0, 0, 0, 0, 0]])
+def test_align_parity(oracle, api, synth, ndt_small, start):
+    o, g = pair(oracle, api, ndt_small)
+    guess = synth.pose_vec_to_matrix(ndt_small["p_true"] + np.array(start)).astype(np.float32)
+    rc0, T0, r0 = o.align(guess)
+    rc1 = g.align(guess)
+    r1 = g.result
+    assert rc1 == rc0 and r1.converged == r0.converged
+    assert (r1.iters, r1.evals, r1.hess_evals) == (r0.iters, r0.evals, r0.hess_evals)
+    dp = np.array(r1.p_final) - np.array(r0.p_final)
+    assert np.abs(dp[:3]).max() < POSE_TOL and np.abs(dp[3:]).max() < POSE_TOL
+    np.testing.assert_allclose(g.getFinalTransformation(), T0, atol=POSE_TOL)
+    assert abs(r1.trans_probability - r0.trans_probability) <= 1e-6 * abs(r0.trans_probability)
+    assert relerr(np.array(r1.hessian), np.array(r0.hessian)) <= 1e-5
+    assert g.hasConverged() and g.getFinalNumIteration() == r0.iters
+
+
+def test_align_identity_guess(oracle, api, ndt_small):
+    T = ndt_small["T_true"]
+    ws = (ndt_small["scan"].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    cfg = dict(map=ndt_small["map"], scan=ws)
+    o, g = pair(oracle, api, cfg)
+    rc0, T0, r0 = o.align(np.eye(4, dtype=np.float32))
+    rc1 = g.align(None)
+    assert rc1 == rc0 and g.result.iters == r0.iters
+    np.testing.assert_allclose(g.getFinalTransformation(), T0, atol=POSE_TOL)
+
+
+def test_align_batch_equals_single(api, synth, ndt_small):
+    g = api.NormalDistributionsTransform()
+    g.setTransformationEpsilon(0.01)
+    g.setInputTarget(ndt_small["map"])
+    g.setInputSource(ndt_small["scan"])
+    starts = [[0.05, -0.04, 0.02, 0, 0, 0.005], [0.3, -0.25, 0, 0, 0, 0.035], [-0.2, 0.1, 0.05, 0, 0, -0.02], [0, 0, 0, 0, 0, 0]]
+    guesses = [synth.pose_vec_to_matrix(ndt_small["p_true"] + np.array(s)).astype(np.float32) for s in starts]
+    finals, res = g.alignBatch(np.stack([m.T.reshape(16) for m in guesses]))
+    for k, m in enumerate(guesses):
+        g.align(m)
+        assert (res[k].iters, res[k].evals, res[k].converged) == (g.result.iters, g.result.evals, g.result.converged)
+        np.testing.assert_allclose(finals[k], g.getFinalTransformation(), atol=1e-6)
+
+
+def test_score_batch_and_argmax(oracle, api, synth, ndt_small):
+    o, g = pair(oracle, api, ndt_small)
+    poses = synth.hypothesis_grid(ndt_small["p_true"], nx=6, ny=6, nyaw=4, pitch=1.0)
+    s0 = o.score_batch(poses)
+    s1 = g.calculateScore(poses)
+    np.testing.assert_allclose(s1, s0, rtol=1e-12, atol=1e-14)
+    assert int(np.argmax(s1)) == int(np.argmax(s0)) == (3 * 6 + 3) * 4
+    best, score, ms = api.relocalize(g, poses)
+    assert best == int(np.argmax(s0))
+    assert score == s1[best]
+    # sharded the way the multi-GPU path does it: the winner of the slices is the global winner
+    wins = []
+    for r in range(3):
+        b, e = api.shard_range(len(poses), 3, r)
+        wins.append(api.relocalize(g, poses[b:e], h_begin=b)[:2])
+    assert max(wins, key=lambda w: (w[1], -w[0]))[0] == best
+
+
+def test_ndt_errors(api, ndt_small):
+    g = api.NormalDistributionsTransform()
+    g.setInputSource(ndt_small["scan"])
+    with pytest.raises(api.B200Error):
+        g.computeDerivatives(np.zeros(6))      # no target yet
+    big = np.array([[0, 0, 0], [1e9, 1e9, 1e9]], np.float32)
+    g2 = api.NormalDistributionsTransform()
+    g2.setResolution(0.01)
+    g2.setInputTarget(big)
+    with pytest.raises(api.B200Error):
+        g2.numVoxels()                          # leaf indices would overflow (applyFilter's guard)
