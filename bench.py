@@ -17,6 +17,15 @@ e2e        same metric through the C-ABI call a ROS node makes (b200_iekf_update
 roofline   dominant kernel by bytes = the stencil k-NN search (k_search): algorithmic bytes / CUDA-event duration.
 cpu_baseline / --impl reference
            the CPU oracle port of the reference path (oracle/), OpenMP on the box's host cores.
+
+Two more objects ride on the same JSON line (the other workloads BASELINE.json's metric names):
+ndt        configs[1]: pclomp NDT of the 20k-point scan against a 10M-point prior map (1 m voxels): setInputTarget
+           (voxel-Gaussian build), one computeDerivatives, one full align(); device ms by CUDA events, e2e = wall clock
+           of the C-ABI call with host buffers, and the roofline of the derivative kernel.
+reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicated 10M-point map, hypotheses sharded
+           over the N ranks (strong scaling: 4096 in total), NCCL allreduce-argmin; hypotheses/s = 4096 / max-over-ranks
+           device time, the winner checked against the oracle's argmax at N=1.
+Skip them with --no-ndt (they add ~30 s of synthetic-map generation).
 """
 from __future__ import annotations
 
@@ -127,6 +136,166 @@ def cpu_oracle_run(data, prm, steps, warmup, budget_s=25.0):
     return ms, os.cpu_count(), t_insert, out
 
 
+N_PRIOR, N_HYP = 10_000_000, 4096
+NDT_KW = dict(resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=35, search=7)
+
+
+def ndt_cpu(cfg, poses, budget_s=20.0, want_build=True):
+    """NDT legs on the CPU oracle (OpenMP derivatives as pclomp does; serial voxel build as the reference)."""
+    from oracle import binding as ob
+    o = ob.OracleNdt(**NDT_KW)
+    t0 = time.perf_counter()
+    o.set_target(cfg["map"])
+    t_build = time.perf_counter() - t0
+    o.set_source(cfg["scan"])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        s, g, H = o.derivatives(cfg["p_guess"])
+    t_der = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    rc, T, r = o.align(cfg["guess"])
+    t_align = time.perf_counter() - t0
+    # reloc: a bounded sample of the hypothesis grid (every k-th hypothesis), all threads
+    n_s = 256
+    sel = np.arange(0, len(poses), max(1, len(poses) // n_s))[:n_s]
+    t0 = time.perf_counter()
+    sc = o.score_batch(poses[sel])
+    t_sc = time.perf_counter() - t0
+    return dict(oracle=o, build_s=t_build, deriv_ms=t_der * 1e3, align_ms=t_align * 1e3, align=(rc, T, r),
+                score_s=t_sc, score_n=len(sel), score_sel=sel, scores=sc, deriv=(s, g, H))
+
+
+def ndt_legs(args, rank, local_rank, world, api, synth, torch):
+    """configs[1] (single-GPU NDT) on rank 0 and configs[3] (sharded relocalization) on all ranks."""
+    import ctypes
+    dist = torch.distributed if world > 1 else None
+    cfg = synth.config2(N_PRIOR, N_SCAN) if rank == 0 else None
+    comm = None
+    if world > 1:
+        ident = [api.Communicator.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        comm = api.Communicator(world, rank, ident[0], device=local_rank)
+        small = [dict(scan=cfg["scan"], p_true=cfg["p_true"], p_guess=cfg["p_guess"], guess=cfg["guess"]) if rank == 0 else None]
+        dist.broadcast_object_list(small, src=0)
+        if rank != 0:
+            cfg = small[0]
+    g = api.NormalDistributionsTransform(device=local_rank)
+    g.setTransformationEpsilon(NDT_KW["trans_eps"])
+    out = {}
+    # ---- setInputTarget: rank 0 holds the cloud; replicas receive the packed points over NVLink
+    build_wall, build_dev = [], []
+    for k in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world > 1:
+            g.setInputTargetReplicated(comm, cfg.get("map") if rank == 0 else None, N_PRIOR)
+        else:
+            g.setInputTarget(cfg["map"])
+            g._handle()
+        build_wall.append((time.perf_counter() - t0) * 1e3)
+        build_dev.append(g.last_ms())
+    g.setInputSource(cfg["scan"])
+    g._handle()
+    poses = synth.hypothesis_grid(cfg["p_true"], 32, 32, 4, 1.0)
+    n_vox = g.numVoxels()
+    launches0 = api.kernel_launches()
+
+    # ---- reloc: strong scaling over ranks
+    b, e = api.shard_range(len(poses), world, rank)
+    mine = np.ascontiguousarray(poses[b:e])
+    for _ in range(3):
+        best, score, ms = api.relocalize(g, mine, comm, h_begin=b)
+    dev, wall = [], []
+    if world > 1:
+        dist.barrier()
+    for _ in range(args.steps):
+        api.flush_l2(local_rank)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        best, score, ms = api.relocalize(g, mine, comm, h_begin=b)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        dev.append(ms)
+    t = torch.tensor([float(np.mean(dev)), float(np.mean(wall))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    reloc_dev_ms, reloc_wall_ms = float(t[0]), float(t[1])
+    reloc_launches = (api.kernel_launches() - launches0) // (args.steps + 3)
+    out["reloc"] = {
+        "metric": "relocalization hypotheses/sec", "value": len(poses) / (reloc_dev_ms * 1e-3), "unit": "hypotheses/s",
+        "n_gpus": world, "scaling": "strong", "hypotheses": len(poses), "per_rank": e - b, "ms_per_batch": reloc_dev_ms,
+        "e2e": {"value": len(poses) / (reloc_wall_ms * 1e-3), "unit": "hypotheses/s", "ms_per_batch": reloc_wall_ms,
+                "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": 32},
+        "best": int(best), "best_score": float(score), "true_index": (16 * 32 + 16) * 4, "gpu_launches_per_batch": int(reloc_launches),
+        "collective": "2 x 8-byte ncclAllReduce (max of score key, min of index)" if world > 1 else "none (single GPU)",
+        "workload": "configs[3]: 32x32x4 pose grid (1 m, 90 deg) vs 10M-pt prior map, calculateScore per hypothesis, map replicated per GPU",
+        "l2": "flushed between timed batches"}
+
+    if rank == 0:
+        # ---- configs[1]: derivatives and full align on one GPU
+        der_dev, der_wall = [], []
+        for k in range(args.steps + 3):
+            api.flush_l2(local_rank)
+            t0 = time.perf_counter()
+            s, gr, H = g.computeDerivatives(cfg["p_guess"])
+            if k >= 3:
+                der_wall.append((time.perf_counter() - t0) * 1e3)
+                der_dev.append(g.last_ms())
+        al_dev, al_wall = [], []
+        for k in range(args.steps + 3):
+            api.flush_l2(local_rank)
+            t0 = time.perf_counter()
+            rc = g.align(cfg["guess"])
+            if k >= 3:
+                al_wall.append((time.perf_counter() - t0) * 1e3)
+                al_dev.append(g.result.gpu_ms)
+        r = g.result
+        pairs = g.nbhd_total(cfg["p_guess"])
+        peak, peak_src = measured_peak()
+        # algorithmic bytes of one derivative evaluation (SURVEY.md 8d): N*16 (source point) + N*7*4 (one cell-table probe per
+        # neighbourhood cell; the dense table stores 4-byte slots) + 64 B per (point, voxel) pair (float-path leaf record)
+        der_bytes = N_SCAN * 16 + N_SCAN * 7 * 4 + 64 * pairs
+        der_ms = float(np.mean(der_dev))
+        out["ndt"] = {
+            "workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
+            "voxels": int(n_vox),
+            "set_target_ms": {"device": float(np.min(build_dev)), "e2e_wall": float(np.min(build_wall)),
+                              "points_per_s_device": N_PRIOR / (float(np.min(build_dev)) * 1e-3),
+                              "note": "device = min/max + key + radix sort + segmented fp64 sums + per-leaf eigen/inverse; e2e adds host pack + 160 MB H2D"
+                                      + (" + ncclBroadcast to the replicas" if world > 1 else "")},
+            "derivatives_ms": {"device": der_ms, "e2e_wall": float(np.mean(der_wall)), "pairs": int(pairs)},
+            "align_ms": {"device": float(np.mean(al_dev)), "e2e_wall": float(np.mean(al_wall)), "iters": r.iters, "evals": r.evals,
+                         "hess_evals": r.hess_evals, "launches": g.last_launches(), "converged": bool(r.converged),
+                         "points_per_s": N_SCAN / (float(np.mean(al_dev)) * 1e-3)},
+            "roofline": {"bound": "hbm", "kernel": "k_ndt_eval (one init + one evaluation launch, CUDA events around both)",
+                         "achieved": der_bytes / (der_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": der_bytes / (der_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(der_bytes), "traffic": None,
+                         "note": "20k points x <=7 voxels is ~9 MB per evaluation: the kernel is latency/launch bound, not bandwidth bound"},
+        }
+        if world == 1 and not args.no_cpu:
+            c = ndt_cpu(cfg, poses)
+            rc0, T0, r0 = c["align"]
+            s0, g0, H0 = c["deriv"]
+            s1 = g.calculateScore(poses[c["score_sel"]])
+            out["ndt"]["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(), "set_target_s": c["build_s"], "derivatives_ms": c["deriv_ms"],
+                                          "align_ms": c["align_ms"], "sample": "full size: 10M-pt voxel build (serial, as the reference), "
+                                          "3 derivative evaluations and 1 align on all threads"}
+            out["ndt"]["parity"] = {"align_dpos_m": float(np.abs(np.array(r.p_final)[:3] - np.array(r0.p_final)[:3]).max()),
+                                    "align_drot_rad": float(np.abs(np.array(r.p_final)[3:] - np.array(r0.p_final)[3:]).max()),
+                                    "iters_equal": bool(r.iters == r0.iters and r.evals == r0.evals),
+                                    "score_rel": float(abs(s - s0) / abs(s0)),
+                                    "g_rel": float(np.abs(gr - g0).max() / np.abs(g0).max()),
+                                    "H_rel": float(np.abs(H - H0).max() / np.abs(H0).max())}
+            out["reloc"]["cpu_baseline"] = {"value": c["score_n"] / c["score_s"], "unit": "hypotheses/s", "cores": os.cpu_count(), "kind": "port",
+                                            "sample": f"{c['score_n']} of the 4096 hypotheses (every 16th), one hypothesis per thread"}
+            out["reloc"]["parity"] = {"scores_rel": float(np.abs(s1 - c["scores"]).max() / np.abs(c["scores"]).max()),
+                                      "argmax_equal_on_sample": bool(int(np.argmax(s1)) == int(np.argmax(c["scores"])))}
+    g.close()
+    if comm is not None:
+        comm.close()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = its restatement in oracle/
     (the reference cannot be compiled here: no PCL/Eigen/Boost/TBB), all host threads."""
@@ -150,6 +319,19 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_ndt:
+        cfg = synth.config2(N_PRIOR, N_SCAN)
+        poses = synth.hypothesis_grid(cfg["p_true"], 32, 32, 4, 1.0)
+        c = ndt_cpu(cfg, poses)
+        rc0, T0, r0 = c["align"]
+        line["ndt"] = {"workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
+                       "set_target_ms": {"e2e_wall": c["build_s"] * 1e3}, "derivatives_ms": {"e2e_wall": c["deriv_ms"]},
+                       "align_ms": {"e2e_wall": c["align_ms"], "iters": r0.iters, "evals": r0.evals, "hess_evals": r0.hess_evals,
+                                    "points_per_s": N_SCAN / (c["align_ms"] * 1e-3)},
+                       "cpu_baseline": {"kind": "port", "cores": cores, "sample": "full size; voxel build serial as in the reference"}}
+        line["reloc"] = {"metric": "relocalization hypotheses/sec", "value": c["score_n"] / c["score_s"], "unit": "hypotheses/s",
+                         "hypotheses": len(poses), "cpu_baseline": {"kind": "port", "cores": cores,
+                                                                     "sample": f"{c['score_n']} of the 4096 hypotheses, one per thread"}}
     print(json.dumps(line), flush=True)
 
 
@@ -239,6 +421,10 @@ def run_b200(args, rank, local_rank, world):
                 obs_ms.append(t[2 + 2 * p])
     kf.set_profiling(False)
 
+    extra = {}
+    if not args.no_ndt:
+        extra = ndt_legs(args, rank, local_rank, world, api, synth, torch)
+
     ms_step = float(np.mean(dev_ms))
     ms_e2e = float(np.mean(e2e_ms))
     if world > 1:
@@ -285,7 +471,8 @@ def run_b200(args, rank, local_rank, world):
         "roofline": roofline,
         "kernels": kernels,
     }
-    if world == 1:
+    line.update(extra)
+    if world == 1 and not args.no_cpu:
         ms, cores, t_insert, out = cpu_oracle_run(data, prm, 20, 3, budget_s=25.0)
         cpu_ms = float(np.median(ms))
         line["cpu_baseline"] = {"value": n / (cpu_ms * 1e-3), "unit": "points/s", "cores": cores, "kind": "port",
@@ -314,8 +501,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--params", default="livox", choices=list(PARAMS))
+    ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] / configs[3] legs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--small", action="store_true", help="DEV ONLY: shrink the maps 10x (not a valid bench number)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
+    if args.small:
+        global N_MAP, N_PRIOR
+        N_MAP, N_PRIOR = N_MAP // 10, N_PRIOR // 10
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -159,16 +159,30 @@ int32_t b200_ndt_align(b200_ndt* ndt, const float* guess16, float* final16, b200
 int32_t b200_ndt_derivatives(b200_ndt* ndt, const double* p6, double* score, double* g6, double* H36);
 /* computeHessian (double path, ndt_omp_impl.hpp:499-560) */
 int32_t b200_ndt_hessian(b200_ndt* ndt, const double* p6, double* H36);
-/* calculateScore for h candidate poses (ndt_omp_impl.hpp:836-880) — global relocalization primitive */
+/* calculateScore for h <= 65535 candidate poses (ndt_omp_impl.hpp:836-880) — global relocalization primitive */
 int32_t b200_ndt_score_batch(b200_ndt* ndt, const float* poses16, int64_t h, double* scores);
-/* argmin over scores of this process's hypothesis slice; with a communicator the reduction spans all ranks */
+/* align() from h independent initial guesses in one batch (relocalization with refinement): finals16 h x 16, results[h] */
+int32_t b200_ndt_align_batch(b200_ndt* ndt, const float* guesses16, int64_t h, float* finals16, b200_ndt_result* results);
+/* min_b_ / div_b_ of the voxel grid (voxel_grid_covariance_omp_impl.hpp:86-96) */
+int32_t b200_ndt_grid(b200_ndt* ndt, int32_t* min_b3, int32_t* div_b3);
+
+/* ------------------------------------------------------------------------- *
+ * Sharded paths (one process per GPU, NCCL over NVLink).  The reference is single-process and has no
+ * counterpart: each hypothesis is scored with the reference's calculateScore arithmetic.
+ * ------------------------------------------------------------------------- */
 typedef struct b200_comm b200_comm;
 #define B200_NCCL_ID_BYTES 128
-int32_t b200_comm_unique_id(uint8_t* id128);
+int32_t b200_comm_unique_id(uint8_t* id128);   /* on one rank; ship the 128 bytes to the others out of band */
 int32_t b200_comm_init_rank(int32_t nranks, int32_t rank, const uint8_t* id128, int32_t device, b200_comm** out);
 int32_t b200_comm_destroy(b200_comm* comm);
-/* Hypotheses h_begin..h_begin+h-1 of a global grid are scored on this rank; every rank receives the global
- * argmin (lowest score, ties to the lower index) through one 8-byte ncclAllReduce(min). comm may be NULL. */
+/* setInputTarget for a map replicated on every rank: `root` passes the cloud (xyz may be NULL elsewhere, n equal
+ * everywhere), the packed points are ncclBroadcast once and every rank builds identical voxel Gaussians. */
+int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* ndt, const float* xyz, int64_t n, int64_t stride_bytes, int32_t root);
+/* Global relocalization.  Hypotheses h_begin..h_begin+h-1 of a global grid are scored on this rank with calculateScore;
+ * the cost that is minimised is -score (the winner is the most likely pose).  Every rank receives the same global
+ * winner through an allreduce-argmin: an 8-byte ncclAllReduce(max) on the order-preserving fp64 score key, then an
+ * 8-byte ncclAllReduce(min) on the index among the rank(s) holding it (exact, ties to the lower index).
+ * comm may be NULL (single GPU).  best = -1 and B200_NO_EFFECTIVE_POINTS when no rank had a hypothesis. */
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t* best,
                           double* best_score, float* gpu_ms);
 

@@ -118,6 +118,7 @@ def lib():
         L.b200_reloc_argmin.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
         L.b200_ndt_align_batch.argtypes = [vp, vp, i64, vp, vp]
         L.b200_ndt_grid.argtypes = [vp, vp, vp]
+        L.b200_ndt_set_target_bcast.argtypes = [vp, vp, vp, i64, i64, i32]
         L.b200_ndt_nbhd_total.restype = i64
         L.b200_ndt_nbhd_total.argtypes = [vp, vp]
         L.b200_ndt_last_ms.restype = C.c_float
@@ -359,6 +360,15 @@ class NormalDistributionsTransform:
         if self.h is not None and not self._dirty:
             _check(lib().b200_ndt_set_target(self.h, _p(self._target), self._target.shape[0], self._target.strides[0]))
 
+    def setInputTargetReplicated(self, comm, cloud, n, root=0):
+        """setInputTarget on every rank of `comm` from the cloud held by `root` (others pass None); n on all ranks."""
+        h = self._handle()
+        if cloud is not None:
+            c = _cloud(cloud)
+            _check(lib().b200_ndt_set_target_bcast(comm.h, h, _p(c), n, c.strides[0], root))
+        else:
+            _check(lib().b200_ndt_set_target_bcast(comm.h, h, None, n, 16, root))
+
     def setInputSource(self, cloud):
         self._source = _cloud(cloud)
         if self.h is not None and not self._dirty:
@@ -475,6 +485,41 @@ def shard_range(h_total: int, nranks: int, rank: int):
     base, rem = divmod(h_total, nranks)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def score_key(s: float) -> int:
+    """Order-preserving map fp64 -> uint64 used by the allreduce-argmin (NaN -> 0, below every real score)."""
+    import struct
+    if s != s:
+        return 0
+    u = struct.unpack("<Q", struct.pack("<d", s))[0]
+    return (~u) & 0xFFFFFFFFFFFFFFFF if (u >> 63) else (u | (1 << 63))
+
+
+def score_from_key(k: int) -> float:
+    import struct
+    u = (k & 0x7FFFFFFFFFFFFFFF) if (k >> 63) else ((~k) & 0xFFFFFFFFFFFFFFFF)
+    return struct.unpack("<d", struct.pack("<Q", u))[0]
+
+
+def argmin_protocol_host(scores, h_begin, all_reduce):
+    """Host mirror of b200_reloc_argmin's collective protocol (used by the CPU gloo test): all_reduce(tensor, op) reduces
+    an int64 tensor in place across ranks.  Step 1: max of the score key; step 2: min of the global index among the holders.
+    Keys are shifted into int64 order (xor 2^63) because gloo has no uint64."""
+    import torch
+    from torch.distributed import ReduceOp
+    keys = [score_key(float(s)) for s in scores]
+    local = max(keys) if keys else 0
+    t = torch.tensor([local - (1 << 63)], dtype=torch.int64)
+    all_reduce(t, ReduceOp.MAX)
+    gkey = int(t[0]) + (1 << 63)
+    cand = min([h_begin + i for i, k in enumerate(keys) if k == gkey and gkey != 0], default=(1 << 62))
+    t = torch.tensor([cand], dtype=torch.int64)
+    all_reduce(t, ReduceOp.MIN)
+    idx = int(t[0])
+    if gkey == 0 or idx == (1 << 62):
+        return -1, 0.0
+    return idx, score_from_key(gkey)
 
 
 def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicator | None = None, h_begin=0):

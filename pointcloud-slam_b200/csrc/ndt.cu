@@ -538,36 +538,48 @@ __global__ void k_ndt_count_done(const Ctl* ctls, int h, int* out) {
 }
 
 // ------------------------------------------------------------------ calculateScore for a batch of poses (:836-880)
-// One block per hypothesis; fp64 throughout like the reference.  Optionally packs (score, index) keys for the argmax.
-__global__ void __launch_bounds__(256) k_ndt_score_batch(View v, const float* __restrict__ poses /*h x 16 col-major*/, double* __restrict__ scores) {
+// grid = (point chunks, hypotheses): a block scores SCORE_CHUNK source points under one pose, fp64 throughout like the
+// reference, and leaves one partial sum; k_ndt_score_finish adds the partials of a hypothesis in chunk order.
+constexpr int SCORE_THREADS = 128;
+constexpr int SCORE_CHUNK = 1024;
+
+template <int NST>
+__global__ void __launch_bounds__(SCORE_THREADS) k_ndt_score_batch(View v, const float* __restrict__ poses /*h x 16 col-major*/,
+                                                                   double* __restrict__ partial /*[h][nchunks]*/) {
     __shared__ float M[12];
-    __shared__ double red[8];
-    const int h = blockIdx.x, tid = threadIdx.x;
+    __shared__ double red[SCORE_THREADS / 32];
+    const int h = blockIdx.y, tid = threadIdx.x;
     if (tid < 12) M[tid] = poses[(size_t)h * 16 + (tid & 3) * 4 + (tid >> 2)];
     __syncthreads();
     double acc = 0.0;
-    for (int i = tid; i < v.n_src; i += blockDim.x) {
+    const int i_end = min(v.n_src, (int)(blockIdx.x + 1) * SCORE_CHUNK);
+    for (int i = blockIdx.x * SCORE_CHUNK + tid; i < i_end; i += SCORE_THREADS) {
         const float4 p = __ldg(v.src + i);
         float tx, ty, tz;
         xform(M, p.x, p.y, p.z, tx, ty, tz);
-        int lf[27];
+        int lf[NST];
         int cnt = 0;
-        for (int s = 0; s < v.nst; ++s) {
-            const int l = nbr_leaf(v, tx, ty, tz, s);
-            if (l >= 0) lf[cnt++] = l;
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            lf[s] = nbr_leaf(v, tx, ty, tz, s);
+            cnt += lf[s] >= 0 ? 1 : 0;
         }
-        for (int c = 0; c < cnt; ++c) {
-            const double2* src = reinterpret_cast<const double2*>(v.leafD + lf[c]);
+        const double dcnt = (double)cnt;
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            if (lf[s] < 0) continue;
+            const double2* src = reinterpret_cast<const double2*>(v.leafD + lf[s]);
             LeafD L;
             double2* dst = reinterpret_cast<double2*>(&L);
 #pragma unroll
             for (int q = 0; q < 6; ++q) dst[q] = __ldg(src + q);
             const double xt[3] = {(double)tx - L.mean[0], (double)ty - L.mean[1], (double)tz - L.mean[2]};
             double cx[3];
+#pragma unroll
             for (int kk = 0; kk < 3; ++kk) cx[kk] = L.icov[kk * 3] * xt[0] + L.icov[kk * 3 + 1] * xt[1] + L.icov[kk * 3 + 2] * xt[2];
             const double e = exp(-v.d2 * (xt[0] * cx[0] + xt[1] * cx[1] + xt[2] * cx[2]) / 2);
             const double inc = -v.d1 * e - v.d3;
-            acc += inc / cnt;
+            acc += inc / dcnt;
         }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -575,9 +587,17 @@ __global__ void __launch_bounds__(256) k_ndt_score_batch(View v, const float* __
     __syncthreads();
     if (tid == 0) {
         double a = red[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += red[w];
-        scores[h] = a / (double)v.n_src;
+#pragma unroll
+        for (int w = 1; w < SCORE_THREADS / 32; ++w) a += red[w];
+        partial[(size_t)h * gridDim.x + blockIdx.x] = a;
     }
+}
+__global__ void k_ndt_score_finish(const double* __restrict__ partial, int nchunks, int64_t h, int n_src, double* __restrict__ scores) {
+    const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (a >= h) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += partial[a * nchunks + c];
+    scores[a] = s / (double)n_src;
 }
 
 // number of (point, voxel) pairs and probes of one evaluation at the poses' transforms (roofline bookkeeping)
@@ -893,9 +913,17 @@ int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
 int32_t Ndt::score_batch_device(const float* d_poses16, int64_t h, double* d_out) {
     if (!have_target) B200_FAIL(B200_ERR_ARG, "no target set");
     if (n_src < 1) B200_FAIL(B200_ERR_ARG, "no source set");
+    if (h > 65535) B200_FAIL(B200_ERR_ARG, "at most 65535 hypotheses per call");
     gauss();
-    k_ndt_score_batch<<<(unsigned)h, 256, 0, stream>>>(view(), d_poses16, d_out);
-    LAUNCH_COUNT(1);
+    const int nch = (n_src + SCORE_CHUNK - 1) / SCORE_CHUNK;
+    CUDA_TRY(d_partials.reserve((size_t)h * nch));
+    const dim3 grid(nch, (unsigned)h);
+    const View v = view();
+    if (prm.search == 1) k_ndt_score_batch<1><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
+    else if (prm.search == 27) k_ndt_score_batch<27><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
+    else k_ndt_score_batch<7><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
+    k_ndt_score_finish<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_partials.p, nch, h, n_src, d_out);
+    LAUNCH_COUNT(2);
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
 }
@@ -951,6 +979,24 @@ int32_t b200_ndt_set_target(b200_ndt* n, const float* xyz, int64_t cnt, int64_t 
     if (!n) B200_FAIL(B200_ERR_ARG, "null handle");
     return n->k.set_target(xyz, cnt, stride);
 }
+/* setInputTarget for a map replicated over the ranks of `comm`: only `root` passes the cloud (xyz may be NULL elsewhere,
+ * cnt must be the same everywhere); the packed points travel once over NVLink (ncclBroadcast, 16 B/point) and every
+ * rank builds its own voxel Gaussians from them - identical on all ranks because the build is deterministic. */
+int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* n, const float* xyz, int64_t cnt, int64_t stride, int32_t root) {
+    if (!n || !comm || cnt < 1 || cnt > (int64_t)0x7fffff00) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    CUDA_TRY(cudaSetDevice(k.device));
+    if (comm->rank == root) {
+        if (!xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "root needs the cloud");
+        int32_t rc = k.upload(xyz, cnt, stride, k.d_tgt);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(k.d_tgt.reserve((size_t)cnt));
+    }
+    NCCL_TRY(comm, comm->Broadcast(k.d_tgt.p, k.d_tgt.p, (size_t)cnt * sizeof(float4), ncclChar, root, comm->comm, k.stream));
+    return k.build_target(cnt);
+}
+
 int32_t b200_ndt_set_source(b200_ndt* n, const float* xyz, int64_t cnt, int64_t stride) {
     if (!n) B200_FAIL(B200_ERR_ARG, "null handle");
     return n->k.set_source(xyz, cnt, stride);
