@@ -4,7 +4,7 @@
  * The reference has no C ABI of its own; each entry point below names the C++
  * interface it replaces (paths relative to the reference's src/).  Thin C++
  * adaptors that re-create those interfaces on top of this ABI live in
- * pointcloud-slam_b200/host/ (see INTEGRATION.md).
+ * pointcloud-slam_b200/host/*.hpp.
  *
  * Conventions
  *   - every function returns int32 status: B200_OK, a positive "soft" status

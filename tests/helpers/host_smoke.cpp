@@ -1,0 +1,75 @@
+// Compiles the header-only host adaptors against the C ABI and runs them end to end (used by tests/test_host_cpp.py).
+// Without a GPU it must fail loudly at construction; with one it registers a small synthetic scene.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "esekf_gpu.hpp"
+#include "ndt_gpu.hpp"
+
+struct PointXYZINormal {  // layout of pcl::PointXYZINormal: 48 bytes
+    float x, y, z, pad0, normal_x, normal_y, normal_z, pad1, intensity, curvature, pad2, pad3;
+};
+struct Cloud { std::vector<PointXYZINormal> points; };
+
+int main() {
+    using namespace b200host;
+    using IVoxType = IVox<3, IVoxNodeType::DEFAULT, PointXYZINormal>;
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> u(-20.f, 20.f), h(0.f, 6.f);
+    std::normal_distribution<float> nz(0.f, 0.01f);
+    // a room: floor z=0, ceiling z=6, walls x=+-20, y=+-20, plus a step so that x/y are observable
+    std::vector<PointXYZINormal> map;
+    auto add = [&](float x, float y, float z) { PointXYZINormal p{}; p.x = x; p.y = y; p.z = z; map.push_back(p); };
+    for (int i = 0; i < 60000; ++i) { add(u(rng), u(rng), nz(rng)); add(u(rng), u(rng), 6.f + nz(rng)); }
+    for (int i = 0; i < 20000; ++i) { add(20.f + nz(rng), u(rng), h(rng)); add(-20.f + nz(rng), u(rng), h(rng)); add(u(rng), 20.f + nz(rng), h(rng)); add(u(rng), -20.f + nz(rng), h(rng)); }
+    try {
+        IVoxType::Options opt;
+        opt.resolution_ = 0.5f;
+        opt.nearby_type_ = IVoxType::NearbyType::NEARBY18;
+        IVoxType ivox(opt);
+        ivox.AddPoints(map);
+        std::vector<PointXYZINormal> near;
+        PointXYZINormal q{}; q.x = 1.f; q.y = 2.f; q.z = 0.02f;
+        const bool ok = ivox.GetClosestPoint(q, near);
+        std::printf("ivox voxels %zu points %zu knn %d first d=%.4f\n", ivox.NumValidGrids(), ivox.NumPoints(), ok ? (int)near.size() : 0,
+                    ok ? std::sqrt((near[0].x - q.x) * (near[0].x - q.x) + (near[0].y - q.y) * (near[0].y - q.y) + (near[0].z - q.z) * (near[0].z - q.z)) : -1.f);
+        if (!ok || near.size() != 5) return 2;
+        // scan = map points near the origin seen from a body frame shifted by (0.03, -0.02, 0.01)
+        std::vector<PointXYZINormal> scan;
+        for (size_t i = 0; i < map.size() && scan.size() < 4000; i += 17) { PointXYZINormal p = map[i]; p.x -= 0.03f; p.y += 0.02f; p.z -= 0.01f; scan.push_back(p); }
+        Esekf<IVoxType> kf(ivox);
+        StateVec x{}; x[6] = 1.0; x[10] = 1.0; x[25] = -9.809;
+        CovMat P{};
+        for (int i = 0; i < 23; ++i) P[i * 23 + i] = 0.01;
+        kf.change_x(x);
+        kf.change_P(P);
+        double ms = 0;
+        const bool valid = kf.update_iterated_dyn_share_modified(scan, ms);
+        const StateVec& xo = kf.get_x();
+        std::printf("iekf valid %d passes %d n_eff %d gpu_ms %.3f pos %.4f %.4f %.4f\n", (int)valid, kf.stats().passes, kf.stats().n_eff[0], ms, xo[0], xo[1], xo[2]);
+        if (!valid || std::fabs(xo[0] - 0.03) > 0.01 || std::fabs(xo[1] + 0.02) > 0.01 || std::fabs(xo[2] - 0.01) > 0.01) return 3;
+        auto target = std::make_shared<Cloud>();
+        target->points = map;
+        auto source = std::make_shared<Cloud>();
+        source->points = scan;
+        NormalDistributionsTransform<Cloud> ndt;
+        ndt.setResolution(2.0f);
+        ndt.setTransformationEpsilon(0.001);
+        ndt.setNeighborhoodSearchMethod(DIRECT7);
+        ndt.setInputTarget(target);
+        ndt.setInputSource(source);
+        Cloud aligned;
+        ndt.align(aligned);
+        const float* T = ndt.getFinalTransformation();
+        std::printf("ndt converged %d iters %d t %.4f %.4f %.4f prob %.4f\n", (int)ndt.hasConverged(), ndt.getFinalNumIteration(), T[12], T[13], T[14],
+                    ndt.getTransformationProbability());
+        if (!ndt.hasConverged() || aligned.points.size() != scan.size()) return 4;
+    } catch (const std::exception& e) {
+        std::printf("FAILED LOUDLY: %s\n", e.what());
+        return 10;
+    }
+    std::printf("host adaptors ok\n");
+    return 0;
+}
