@@ -25,7 +25,9 @@ ndt        configs[1]: pclomp NDT of the 20k-point scan against a 10M-point prio
 reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicated 10M-point map, hypotheses sharded
            over the N ranks (strong scaling: 4096 in total), NCCL allreduce-argmin; hypotheses/s = 4096 / max-over-ranks
            device time, the winner checked against the oracle's argmax at N=1.
-Skip them with --no-ndt (they add ~30 s of synthetic-map generation).
+sequence   configs[2]: sliding-map odometry (update + MapIncremental per scan) over --seq-scans scans (default 120;
+           1000 is the full configuration and takes ~1 min of host-side ray casting).
+Skip them with --no-ndt / --seq-scans 0 (they add ~40 s of synthetic-data generation).
 """
 from __future__ import annotations
 
@@ -296,6 +298,86 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch):
     return out
 
 
+def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
+    """configs[2]: sliding-map odometry over a synthetic scan sequence.  The map starts from the first scan and grows by
+    MapIncremental (downsample-on-insert); the prior of scan k is the posterior of scan k-1 moved by the true relative
+    motion plus a seeded perturbation (stand-in for the IMU propagation, which is out of scope)."""
+    prm = PARAMS["horizon"]
+    world = synth.make_world(synth.SEED)
+    rng = np.random.default_rng(synth.SEED + 31)
+    per_lap = 290
+
+    def true_state(k):
+        a = 2 * np.pi * k / per_lap
+        pos = np.array([30.0 * np.cos(a), 15.0 * np.sin(a), 1.2])
+        yaw = np.arctan2(15.0 * np.cos(a), -30.0 * np.sin(a))
+        return synth.make_state(pos, [0.0, 0.0, yaw])
+
+    def scan_of(k):
+        o, Rl = synth.lidar_pose(true_state(k))
+        return np.ascontiguousarray(synth.raycast(o, Rl, synth.livox_dirs(25_000, seed=synth.SEED + k), world, seed=synth.SEED + 7 * k)[:N_SCAN])
+
+    def move(x_post, k):  # posterior of k-1 -> prior of k by the true relative motion + noise
+        a, b = true_state(k - 1), true_state(k)
+        Ra, Rp = synth.quat_to_R(a[3:7]), synth.quat_to_R(x_post[3:7])
+        x = x_post.copy()
+        x[0:3] = x_post[0:3] + Rp @ (Ra.T @ (b[0:3] - a[0:3])) + rng.uniform(-0.02, 0.02, 3)
+        qa_inv = a[3:7] * np.array([-1, -1, -1, 1.0])
+        dq = synth.quat_mul(qa_inv, b[3:7])
+        q = synth.quat_mul(synth.quat_mul(x_post[3:7], dq), synth.quat_from_rotvec(np.deg2rad(rng.uniform(-0.2, 0.2, 3))))
+        x[3:7] = q / np.linalg.norm(q)
+        return x
+
+    ivox = api.IVox(resolution=prm["resolution"], nearby=prm["nearby"], device=local_rank)
+    kf = api.Esekf(ivox, extrinsic_est_en=False, filter_size_map=0.5)
+    oracle_on = n_parity > 0 and not args.no_cpu
+    if oracle_on:
+        from oracle import binding as ob
+        orc = ob.OracleLio(resolution=prm["resolution"], nearby=prm["nearby"], extrinsic_est_en=False, filter_size_map=0.5)
+    P0 = synth.init_cov() * 0.01
+    x_g = true_state(0)
+    first = scan_of(0)
+    ol, Rl = synth.lidar_pose(x_g)
+    w0 = (first.astype(np.float64) @ Rl.T + ol).astype(np.float32)
+    ivox.AddPoints(w0)                      # first frame: every point goes in (laser_mapping.cc:314-319)
+    if oracle_on:
+        orc.insert(w0)
+    ms_update, ms_incr, ms_wall, voxels, points, par = [], [], [], [], [], []
+    for k in range(1, n_scans):
+        scan = scan_of(k)
+        prior = move(x_g, k)
+        kf.change_x(prior)
+        kf.change_P(P0)
+        t0 = time.perf_counter()
+        rc = kf.update_iterated_dyn_share_modified(scan)
+        t1 = time.perf_counter()
+        na, nd = kf.MapIncremental(kf.get_x(), True)
+        t2 = time.perf_counter()
+        x_g = kf.get_x().copy()
+        ms_update.append(kf.stats.gpu_ms)
+        ms_wall.append((t2 - t0) * 1e3)
+        ms_incr.append((t2 - t1) * 1e3)
+        if k % 50 == 0 or k == n_scans - 1:
+            voxels.append(ivox.NumValidGrids())
+            points.append(ivox.NumPoints())
+        if oracle_on and k <= n_parity:      # the oracle is fed the same prior and grows its own map from its own posterior
+            rco, x_o, P_o, st_o = orc.update(scan, prior, P0)
+            orc.map_incremental(scan, x_o, True)
+            d = ob.boxminus(x_g, x_o)
+            par.append(float(np.abs(d[:6]).max()))
+    xt = true_state(n_scans - 1)
+    drift = float(np.linalg.norm(x_g[0:3] - xt[0:3]))
+    return {"workload": f"configs[2]: {n_scans}-scan closed-loop sequence (0.5 m / 1.2 deg steps), 20k-pt scans, P-horizon map "
+                        "(0.5 m voxels, NEARBY18), update + MapIncremental (filter_size_map 0.5) per scan",
+            "scans": n_scans, "ms_update_device": {"mean": float(np.mean(ms_update)), "p95": float(np.percentile(ms_update, 95))},
+            "ms_per_scan_e2e": {"mean": float(np.mean(ms_wall)), "p95": float(np.percentile(ms_wall, 95)),
+                                "map_incremental_mean": float(np.mean(ms_incr))},
+            "scans_per_s_e2e": 1e3 / float(np.mean(ms_wall)), "points_per_s_e2e": N_SCAN * 1e3 / float(np.mean(ms_wall)),
+            "map_voxels": voxels, "map_points": points, "final_position_error_m": drift,
+            "parity_vs_oracle": {"scans": len(par), "max_state_diff": max(par) if par else None,
+                                 "note": "both filters fed the same priors; posterior and inserted points compared per scan"}}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = its restatement in oracle/
     (the reference cannot be compiled here: no PCL/Eigen/Boost/TBB), all host threads."""
@@ -425,6 +507,9 @@ def run_b200(args, rank, local_rank, world):
     if not args.no_ndt:
         extra = ndt_legs(args, rank, local_rank, world, api, synth, torch)
 
+    if args.seq_scans > 1 and rank == 0:
+        extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans)
+
     ms_step = float(np.mean(dev_ms))
     ms_e2e = float(np.mean(e2e_ms))
     if world > 1:
@@ -503,6 +588,7 @@ def main():
     ap.add_argument("--params", default="livox", choices=list(PARAMS))
     ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] / configs[3] legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--seq-scans", type=int, default=120, help="configs[2] leg: scans in the sliding-map sequence (1000 = full; 0 = skip)")
     ap.add_argument("--small", action="store_true", help="DEV ONLY: shrink the maps 10x (not a valid bench number)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()

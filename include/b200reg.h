@@ -4,7 +4,7 @@
  * The reference has no C ABI of its own; each entry point below names the C++
  * interface it replaces (paths relative to the reference's src/).  Thin C++
  * adaptors that re-create those interfaces on top of this ABI live in
- * pointcloud-slam_b200/host/*.hpp.
+ * the pointcloud-slam_b200/host/ headers.
  *
  * Conventions
  *   - every function returns int32 status: B200_OK, a positive "soft" status
@@ -32,7 +32,7 @@ extern "C" {
 #define B200_ERR_CUDA (-2)
 #define B200_ERR_NOMEM (-3)
 #define B200_ERR_RANGE (-4)    /* coordinate outside the +-2^20-cell key range, or NDT grid too large */
-#define B200_ERR_CAPACITY (-5) /* voxel capacity reached (LRU eviction not implemented yet) */
+#define B200_ERR_CAPACITY (-5) /* voxel capacity too small to hold a single new voxel */
 #define B200_ERR_NCCL (-6)
 
 const char* b200_version(void);

@@ -3,6 +3,11 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+
 namespace b200 {
 
 thread_local std::string g_last_error;
@@ -28,13 +33,16 @@ __global__ void k_point_keys(const float4* __restrict__ pts, int n, float inv_re
 //    run_dst[r]   = pool index where the run's first new point goes
 //    run_reloc[r] = old start if the voxel had to move (its old points are copied by k_relocate), else -1
 __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* __restrict__ cnt, const int32_t* __restrict__ nruns,
+                              const int32_t* __restrict__ run_off, const int32_t* __restrict__ sorted_vals, int base_ord,
                               MapEntry* ent, int2* aux, uint32_t tmask, uint64_t pool_cap, uint32_t capacity_voxels,
-                              uint32_t stamp, MapCounters* ctr, int32_t* __restrict__ run_dst, int32_t* __restrict__ run_reloc,
+                              MapCounters* ctr, int32_t* __restrict__ run_dst, int32_t* __restrict__ run_reloc,
                               int32_t* __restrict__ run_oldcnt) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= *nruns) return;
     const uint64_t key = uniq[r];
     const int c = cnt[r];
+    // LRU recency = ordinal of the last point that touched the voxel (the sort is stable: last element of the run)
+    const int stamp = base_ord + sorted_vals[run_off[r] + c - 1];
     uint32_t slot = hash_key(key) & tmask;
     bool created = false;
     while (true) {
@@ -72,7 +80,7 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     run_oldcnt[r] = v.y;
     atomicAdd(&ctr->live_points, (unsigned long long)c);
     v.y = newcount;
-    v.w = (int)stamp;
+    v.w = stamp;
     ent[slot].start = v.x;
     ent[slot].count = v.y;
     aux[slot] = make_int2(v.z, v.w);
@@ -110,6 +118,62 @@ __global__ void k_scatter_points(const float4* __restrict__ pts, const int32_t* 
     pool[dst0 + (i - run_off[lo])] = p;
 }
 
+// ---- LRU eviction (IVox::AddPoints, ivox3d.h:268-275): a new voxel that brings the map to `capacity_` voxels evicts the
+// least recently touched one.  Only batches that can reach the capacity take this path.
+// run_slot[r] = table slot of the run's voxel or -1 when the voxel does not exist yet; run_first[r] = index (in the batch)
+// of the run's first point = the time the voxel is first touched.
+__global__ void k_lookup_runs(const uint64_t* __restrict__ uniq, const int32_t* __restrict__ run_off, const int32_t* __restrict__ sorted_vals,
+                              const int32_t* __restrict__ nruns, const MapEntry* __restrict__ ent, uint32_t tmask,
+                              int32_t* __restrict__ run_slot, int32_t* __restrict__ run_first) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    const uint64_t key = uniq[r];
+    uint32_t slot = hash_key(key) & tmask;
+    int found = -1;
+    while (true) {
+        const uint64_t k = ent[slot].key;
+        if (k == key) { found = (int)slot; break; }
+        if (k == kEmptyKey) break;
+        slot = (slot + 1) & tmask;
+    }
+    run_slot[r] = found;
+    run_first[r] = sorted_vals[run_off[r]];
+}
+// (stamp << 32 | slot) of every live voxel
+__global__ void k_collect_live(const MapEntry* __restrict__ ent, const int2* __restrict__ aux, uint32_t tsize, uint64_t* __restrict__ out,
+                               unsigned int* __restrict__ n_out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= tsize) return;
+    const uint64_t k = ent[s].key;
+    if (k == kEmptyKey || k == kTombKey) return;
+    const unsigned int i = atomicAdd(n_out, 1u);
+    out[i] = ((uint64_t)(uint32_t)aux[s].y << 32) | (uint64_t)s;
+}
+__global__ void k_evict(const int32_t* __restrict__ victims, int nv, MapEntry* ent, int2* aux, MapCounters* ctr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const int s = victims[i];
+    atomicAdd(&ctr->live_points, (unsigned long long)(-(long long)ent[s].count));
+    atomicSub(&ctr->num_voxels, 1u);
+    ent[s].key = kTombKey;   // probe chains through this slot stay intact; the pool run is reclaimed by the next compaction
+    ent[s].start = 0;
+    ent[s].count = 0;
+    aux[s] = make_int2(0, 0);
+}
+// move every live voxel into a fresh table (drops the tombstones)
+__global__ void k_rehash(const MapEntry* __restrict__ old_ent, const int2* __restrict__ old_aux, uint32_t tsize, MapEntry* ent, int2* aux) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= tsize) return;
+    const MapEntry e = old_ent[s];
+    if (e.key == kEmptyKey || e.key == kTombKey) return;
+    uint32_t slot = hash_key(e.key) & (tsize - 1);
+    while (atomicCAS((unsigned long long*)&ent[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)e.key) != kEmptyKey)
+        slot = (slot + 1) & (tsize - 1);
+    ent[slot].start = e.start;
+    ent[slot].count = e.count;
+    aux[slot] = old_aux[s];
+}
+
 __global__ void k_fill_keys(MapEntry* ent, int2* aux, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -127,7 +191,7 @@ __global__ void k_compact_plan(MapEntry* ent, int2* aux, uint32_t tsize, unsigne
                                const float4* __restrict__ old_pool, float4* new_pool) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= tsize) return;
-    if (ent[s].key == kEmptyKey) return;
+    if (ent[s].key == kEmptyKey || ent[s].key == kTombKey) return;
     int4 v = make_int4(ent[s].start, ent[s].count, aux[s].x, aux[s].y);
     if (v.y == 0) return;
     int slack = v.y < 4 ? v.y : v.y / 2;  // leave growth room so the next insert does not move everything again
@@ -225,7 +289,8 @@ int32_t Map::init(const b200_map_params* p, int dev) {
     k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize);
     LAUNCH_COUNT(1);
     CUDA_TRY(h_ctr_pin.reserve(1));
-    CUDA_TRY(d_nruns.reserve(1));
+    CUDA_TRY(d_nruns.reserve(4));
+    CUDA_TRY(h_small.reserve(4));
     CUDA_TRY(cudaStreamSynchronize(stream));
     memset(&h_ctr, 0, sizeof h_ctr);
     return B200_OK;
@@ -238,6 +303,7 @@ void Map::destroy() {
     in_pts.release(); k_in.release(); k_out.release(); k_uniq.release();
     v_in.release(); v_out.release(); run_cnt.release(); run_off.release(); run_dst.release(); run_reloc.release();
     d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
+    lru_in.release(); lru_out.release(); victims_dev.release(); h_runs.release(); h_lru.release(); h_small.release();
     q_idx.release(); q_cnt.release(); q_d2.release();
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
@@ -259,6 +325,103 @@ int32_t Map::grow_pool(uint64_t min_cap) {
     cudaFree(d_pool);
     d_pool = np;
     pool_cap = ncap;
+    return B200_OK;
+}
+
+constexpr int32_t kSplitBatch = 100;  // internal: evict_for_batch needs the batch replayed in smaller pieces
+
+int32_t Map::rehash() {
+    MapEntry* ne = nullptr;
+    int2* na = nullptr;
+    CUDA_TRY(cudaMalloc(&ne, (size_t)tsize * sizeof(MapEntry)));
+    CUDA_TRY(cudaMalloc(&na, (size_t)tsize * sizeof(int2)));
+    k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(ne, na, tsize);
+    k_rehash<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize, ne, na);
+    LAUNCH_COUNT(2);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d_ent);
+    cudaFree(d_aux);
+    d_ent = ne;
+    d_aux = na;
+    tombstones = 0;
+    return B200_OK;
+}
+
+// Decides, with the reference's sequential semantics, which voxels the batch that has just been sorted into runs evicts.
+// Walks the creation events of the batch in time order on the host (a few hundred per scan) against the LRU order of the
+// live voxels (sorted on the device).  A voxel that is evicted before its first touch in this batch is re-created by that
+// touch with only the new points, exactly like the reference.
+int32_t Map::evict_for_batch(int64_t n) {
+    CUDA_TRY(cudaMemcpyAsync(h_small.p, d_nruns.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const int nruns = h_small.p[0];
+    const int nb = (nruns + 255) / 256;
+    // run_dst / run_reloc are free until the upsert: borrow them for (slot, first)
+    k_lookup_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_off.p, v_out.p, d_nruns.p, d_ent, tsize - 1, run_dst.p, run_reloc.p);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(h_runs.reserve(2 * (size_t)nruns));
+    CUDA_TRY(cudaMemcpyAsync(h_runs.p, run_dst.p, nruns * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_runs.p + nruns, run_reloc.p, nruns * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const int32_t *slot = h_runs.p, *first = h_runs.p + nruns;
+    int64_t n_new = 0;
+    for (int r = 0; r < nruns; ++r) n_new += slot[r] < 0;
+    const int64_t capacity = (int64_t)prm.capacity_voxels;
+    if ((int64_t)h_ctr.num_voxels + n_new < capacity) return B200_OK;
+    // LRU order of the live voxels
+    const size_t live = h_ctr.num_voxels;
+    CUDA_TRY(lru_in.reserve(live + 1)); CUDA_TRY(lru_out.reserve(live + 1));
+    unsigned int* d_cnt = (unsigned int*)(d_nruns.p + 1);
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), stream));
+    k_collect_live<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize, lru_in.p, d_cnt);
+    LAUNCH_COUNT(1);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, lru_in.p, lru_out.p, (int)live, 0, 64, stream);
+    CUDA_TRY(cub_tmp.reserve(tmp));
+    CUDA_TRY(cub::DeviceRadixSort::SortKeys(cub_tmp.p, tmp, lru_in.p, lru_out.p, (int)live, 0, 64, stream));
+    const size_t m = std::min(live, (size_t)2 * nruns + 16);
+    CUDA_TRY(h_lru.reserve(m + 1));
+    CUDA_TRY(cudaMemcpyAsync(h_lru.p, lru_out.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    std::unordered_map<int32_t, std::pair<int, int64_t>> touched;  // old voxel slot -> (run, first touch time)
+    using Ev = std::pair<int64_t, int>;                            // (time, run)
+    std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> heap;
+    for (int r = 0; r < nruns; ++r) {
+        if (slot[r] < 0) heap.push({(int64_t)first[r], r});
+        else touched[slot[r]] = {r, (int64_t)first[r]};
+    }
+    std::vector<int32_t> victims;
+    int64_t size = (int64_t)h_ctr.num_voxels;
+    size_t i = 0;
+    while (!heap.empty()) {
+        const int64_t t = heap.top().first;
+        heap.pop();
+        size += 1;
+        if (size < capacity) continue;
+        while (i < m) {  // voxels touched earlier in this batch have already moved to the front of the LRU list
+            auto it = touched.find((int32_t)(h_lru.p[i] & 0xFFFFFFFFu));
+            if (it != touched.end() && it->second.second < t) { ++i; continue; }
+            break;
+        }
+        if (i >= m) return kSplitBatch;  // every older voxel is gone: the victim is a voxel of this very batch -> smaller batches
+        const int32_t victim = (int32_t)(h_lru.p[i] & 0xFFFFFFFFu);
+        ++i;
+        victims.push_back(victim);
+        size -= 1;
+        auto it = touched.find(victim);
+        if (it != touched.end()) heap.push({it->second.second, it->second.first});  // re-created by its first touch
+    }
+    if (victims.empty()) return B200_OK;
+    CUDA_TRY(h_runs.reserve(victims.size()));
+    memcpy(h_runs.p, victims.data(), victims.size() * sizeof(int32_t));
+    CUDA_TRY(victims_dev.reserve(victims.size()));
+    CUDA_TRY(cudaMemcpyAsync(victims_dev.p, h_runs.p, victims.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    k_evict<<<(unsigned)((victims.size() + 255) / 256), 256, 0, stream>>>(victims_dev.p, (int)victims.size(), d_ent, d_aux, d_ctr);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    tombstones += victims.size();
+    evicted_total += victims.size();
+    if (h_ctr.num_voxels + tombstones + (uint64_t)n > (uint64_t)(0.7 * tsize)) return rehash();
     return B200_OK;
 }
 
@@ -287,10 +450,18 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     CUDA_TRY(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, tmp, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream));
     // exclusive scan over all n slots (entries past nruns are garbage and never read)
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, run_cnt.p, run_off.p, (int)n, stream));
-    ++stamp;
     int32_t* run_oldcnt = run_reloc.p + n;
-    k_upsert_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_cnt.p, d_nruns.p, d_ent, d_aux, tsize - 1, pool_cap,
-                                          (uint32_t)prm.capacity_voxels, stamp, d_ctr, run_dst.p, run_reloc.p, run_oldcnt);
+    if (h_ctr.num_voxels + (uint64_t)n >= prm.capacity_voxels) {  // this batch may reach the voxel capacity: LRU eviction
+        int32_t rc = evict_for_batch(n);
+        if (rc == kSplitBatch) {  // nothing has been modified yet: replay the batch as two halves (exact, down to single points)
+            if (n == 1) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity too small");
+            rc = insert_device(d_pts, n / 2);
+            return rc ? rc : insert_device(d_pts + n / 2, n - n / 2);
+        }
+        if (rc) return rc;
+    }
+    k_upsert_runs<<<nb, 256, 0, stream>>>(k_uniq.p, run_cnt.p, d_nruns.p, run_off.p, v_out.p, (int)next_ord, d_ent, d_aux, tsize - 1, pool_cap,
+                                          (uint32_t)prm.capacity_voxels, d_ctr, run_dst.p, run_reloc.p, run_oldcnt);
     k_relocate<<<nb, 256, 0, stream>>>(d_nruns.p, run_dst.p, run_reloc.p, run_oldcnt, d_pool);
     k_scatter_points<<<nb, 256, 0, stream>>>(d_pts, v_out.p, (int)n, d_nruns.p, run_off.p, run_dst.p, (int)next_ord, d_pool);
     LAUNCH_COUNT(4);  // own kernels (cub's sort/RLE/scan passes are not counted)
@@ -301,7 +472,7 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     h_ctr.num_points = (unsigned long long)next_ord;
     if (h_ctr.err_range) B200_FAIL(B200_ERR_RANGE, "point outside the voxel key range or non-finite");
     if (h_ctr.err_pool) B200_FAIL(B200_ERR_NOMEM, "point pool exhausted");
-    if (h_ctr.err_capacity) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity reached (LRU eviction not implemented)");
+    if (h_ctr.err_capacity) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity exceeded (internal: eviction pre-pass missed a batch)");
     return B200_OK;
 }
 

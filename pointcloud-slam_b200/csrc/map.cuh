@@ -3,7 +3,8 @@
 // Layout in HBM
 //   ent[T]    16 B     open-addressing table (T = pow2 >= 2*capacity): {packed voxel key, start, count};
 //                      one 16-byte load resolves a stencil probe to the voxel's run in the point pool
-//   aux[T]    int2     {cap, stamp}: slot capacity / last-touch stamp, only read by insert
+//   aux[T]    int2     {cap, stamp}: slot capacity / ordinal of the last point that touched the voxel (LRU recency),
+//                      only read by insert
 //   pool[]    float4   points, voxel-contiguous, in-voxel order = insertion order;
 //                      .w carries the global insertion ordinal (int bits)
 // A voxel is one contiguous, 16-byte-aligned run, so a stencil search is <= 27 table probes
@@ -61,6 +62,7 @@ __device__ __forceinline__ MapEntry ld_entry(const MapEntry* e) {
 }
 
 constexpr uint64_t kInfKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;  // evicted voxel: keeps probe chains intact until the next rehash
 constexpr int kRankBits = 26;  // in-voxel index bits inside the tie-break rank
 
 // sorted insert of k into ascending t[0..4]
@@ -215,7 +217,7 @@ struct Map {
     MapCounters* d_ctr = nullptr;
     MapCounters h_ctr{};   // mirror after the last insert
     int64_t next_ord = 0;
-    uint32_t stamp = 0;
+    uint64_t tombstones = 0, evicted_total = 0;
     // scratch
     DevBuf<float4> in_pts;
     DevBuf<uint64_t> k_in, k_out, k_uniq;
@@ -223,6 +225,11 @@ struct Map {
     DevBuf<uint8_t> cub_tmp;
     PinnedBuf<float4> h_stage;
     PinnedBuf<MapCounters> h_ctr_pin;
+    // LRU eviction scratch
+    DevBuf<uint64_t> lru_in, lru_out;
+    DevBuf<int32_t> victims_dev;
+    PinnedBuf<int32_t> h_runs, h_small;
+    PinnedBuf<uint64_t> h_lru;
     // knn scratch
     DevBuf<int32_t> q_idx, q_cnt;
     DevBuf<float> q_d2;
@@ -239,6 +246,8 @@ struct Map {
     int32_t insert_host(const float* xyz, int64_t n, int64_t stride);
     int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt);
     int32_t grow_pool(uint64_t min_cap);
+    int32_t evict_for_batch(int64_t n);
+    int32_t rehash();
 };
 
 }  // namespace b200

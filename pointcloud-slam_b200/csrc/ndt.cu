@@ -206,12 +206,45 @@ __global__ void k_ndt_finalize(const uint32_t* __restrict__ uniq, const int32_t*
 }
 
 // ------------------------------------------------------------------ Newton / More-Thuente state machine (thread 0 of the last block)
-// H x = rhs the way JacobiSVD(H).solve(rhs) answers it for symmetric H: eigen-decomposition, singular values |lambda|,
-// components below max|lambda| * 6 eps dropped (ndt_omp_impl.hpp:112-114)
-__device__ __noinline__ void svd_solve6(const double* H, const double* rhs, double* x) {
+// H x = rhs the way JacobiSVD(H).solve(rhs) answers it for symmetric H (ndt_omp_impl.hpp:112-114): a pseudo-inverse that
+// drops singular values below max(sv) * 6 eps.  When H is comfortably full rank that is simply H^-1 rhs, which a pivoted
+// 6x6 elimination delivers in ~2 us of one thread; only a (nearly) rank-deficient H takes the eigen-decomposition path
+// (cyclic Jacobi, ~60 us) that implements the thresholding literally.
+__device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, double* x) {
+    double a[6][7];
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) a[i][j] = Hs[i * 6 + j];
+        a[i][6] = rhs[i];
+    }
+    double pmax = 0.0, pmin = 1.7976931348623157e308;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        double best = fabs(a[k][k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
+        if (!(best > 0.0)) return false;
+        if (piv != k)
+            for (int j = k; j < 7; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
+        pmax = fmax(pmax, best);
+        pmin = fmin(pmin, best);
+        const double inv = 1.0 / a[k][k];
+        for (int i = k + 1; i < 6; ++i) {
+            const double f = a[i][k] * inv;
+            for (int j = k + 1; j < 7; ++j) a[i][j] -= f * a[k][j];
+        }
+    }
+    if (!(pmin > 1e-9 * pmax)) return false;  // too close to rank deficient for the shortcut (also catches NaN)
+    for (int i = 5; i >= 0; --i) {
+        double sacc = a[i][6];
+        for (int j = i + 1; j < 6; ++j) sacc -= a[i][j] * x[j];
+        x[i] = sacc / a[i][i];
+    }
+    return true;
+}
+
+__device__ __noinline__ void eig_solve6(const double* Hs, const double* rhs, double* x) {
     double A[36], w[6], V[36];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) A[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
+    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
     jacobi_eig<6>(A, w, V);
     double smax = 0.0;
     for (int i = 0; i < 6; ++i) smax = fmax(smax, fabs(w[i]));
@@ -227,6 +260,13 @@ __device__ __noinline__ void svd_solve6(const double* H, const double* rhs, doub
 #pragma unroll
         for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + k] * d;
     }
+}
+
+__device__ inline void svd_solve6(const double* H, const double* rhs, double* x) {
+    double Hs[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
+    if (!lu_solve6(Hs, rhs, x)) eig_solve6(Hs, rhs, x);
 }
 
 // updateIntervalMT (ndt_omp_impl.hpp:594-620)

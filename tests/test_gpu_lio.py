@@ -242,3 +242,33 @@ def test_full_size_properties(api, synth, pname):
     assert kf.stats.n_eff[0] > 0.9 * len(c["scan"])
     err = kf.get_x()[:3] - c["x_true"][:3]
     assert np.linalg.norm(err) < 0.02
+
+
+@pytest.mark.parametrize("capacity,batch", [(3000, 2500), (1500, 4000), (800, 700)])
+def test_lru_eviction_matches_reference_semantics(oracle, api, synth, small_cfg, capacity, batch):
+    """IVox::AddPoints evicts the least recently touched voxel whenever a new voxel brings the map to capacity_
+    (ivox3d.h:268-275), point by point.  The GPU map decides the same victims per batch, including voxels that are
+    evicted and re-created inside one batch."""
+    mp = small_cfg["map"]
+    o = oracle.OracleLio(resolution=0.5, nearby=18, capacity=capacity)
+    g = api.IVox(resolution=0.5, nearby=18, capacity=capacity)
+    q = world_scan(synth, small_cfg)[:1500]
+    rng = np.random.default_rng(5)
+    start = 0
+    for k in range(12):
+        # alternate fresh regions with revisits of old points so that recency matters
+        if k % 3 == 2:
+            sel = rng.integers(0, max(start, 1), batch // 2)
+            pts = np.ascontiguousarray(mp[sel])
+        else:
+            pts = mp[start:start + batch]
+            start += batch
+        o.insert(pts)
+        g.AddPoints(pts)
+        assert g.NumValidGrids() == o.num_voxels, k
+        assert g.NumPoints() == o.num_points, k
+        i0, d0, c0 = o.knn5(q)
+        i1, d1, c1 = g.GetClosestPoint(q)
+        np.testing.assert_array_equal(c1, c0)
+        np.testing.assert_array_equal(i1, i0)
+    assert o.num_voxels == capacity - 1   # the map sits at the capacity: evictions did happen
