@@ -97,7 +97,12 @@ def lib():
     L.b200_iekf_set_graph.argtypes = [vp, i32]
     L.b200_iekf_kernel_times.argtypes = [vp, vp, i32]
     L.b200_iekf_io_bytes.argtypes = [vp, i64, vp, vp]
+    L.b200_iekf_launch_modes.argtypes = [vp, vp, vp, vp]
     L.b200_map_stencil_points.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.b200_map_last_knn_ms.restype = C.c_float
+    L.b200_map_last_knn_ms.argtypes = [vp]
+    L.b200_map_evicted.restype = i64
+    L.b200_map_evicted.argtypes = [vp]
     L.b200_flush_l2.argtypes = [i32]
     if hasattr(L, "b200_ndt_create"):
         L.b200_ndt_create.argtypes = [C.POINTER(NdtParams), i32, C.POINTER(vp)]
@@ -190,6 +195,12 @@ class IVox:
         _check(lib().b200_map_stencil_points(self.h, _p(q), q.shape[0], q.strides[0], C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_knn_ms(self) -> float:
+        return float(lib().b200_map_last_knn_ms(self.h))
+
+    def evicted(self) -> int:
+        return int(lib().b200_map_evicted(self.h))
+
     def NumValidGrids(self) -> int:
         return int(lib().b200_map_num_voxels(self.h))
 
@@ -254,6 +265,12 @@ class Esekf:
         ms = (C.c_float * 17)()
         k = lib().b200_iekf_kernel_times(self.h, ms, 17)
         return [ms[i] for i in range(k)]
+
+    def launch_modes(self):
+        """(graph captures, graph replays, plain launch sequences) so far."""
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(lib().b200_iekf_launch_modes(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def io_bytes(self, n):
         a, b = C.c_int64(0), C.c_int64(0)

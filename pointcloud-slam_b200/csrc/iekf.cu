@@ -127,7 +127,8 @@ struct ObsSmem {
 // Stencil search of a pass (dyn_share.converge == true): 8 lanes per scan point, one wave over the
 // whole scan at high occupancy.  Results go to a scratch array that k_obs consumes; the kernel is a
 // no-op when the pass reuses the previous neighbours (decided on the device).
-__global__ void __launch_bounds__(256, 5) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 0 ? 5 : 4) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
                                                 float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
     if (ctl->done || !ctl->converge) return;
     __shared__ PassConsts pc;
@@ -140,9 +141,9 @@ __global__ void __launch_bounds__(256, 5) k_search(MapView map, const float4* __
     const unsigned gmask = ((1u << KNN_G) - 1u) << ((tid & 31) / KNN_G * KNN_G);
     const float4 pbody = __ldg(scan + q);
     const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
-    uint64_t win[5];
+    uint64_t wkey;
     float4 mine;
-    const int c = knn5_group<KNN_G>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), win, mine);
+    const int c = knn5_group<KNN_G, MODE>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), wkey, mine);
     if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
     if (lg == 0) nbc_out[q] = (unsigned char)c;
 }
@@ -333,14 +334,15 @@ struct Iekf {
     struct GraphKey {
         const void *pts, *hdr, *ent, *pool, *plane, *nb;
         unsigned search_grid;
-        int single, force;
+        int single, force, knn_mode;
         bool operator==(const GraphKey& o) const {
             return pts == o.pts && hdr == o.hdr && ent == o.ent && pool == o.pool && plane == o.plane && nb == o.nb &&
-                   search_grid == o.search_grid && single == o.single && force == o.force;
+                   search_grid == o.search_grid && single == o.single && force == o.force && knn_mode == o.knn_mode;
         }
     };
-    GraphKey gkey{};
+    GraphKey gkey{}, pending_key{};
     cudaGraphExec_t gexec = nullptr;
+    int graph_captures = 0, graph_replays = 0, direct_runs = 0;
     int use_graph = 1;
     int profiling = 0;  // record an event after every kernel (disables the graph path)
     cudaEvent_t evk[2 * B200_MAX_PASSES + 2] = {};
@@ -445,7 +447,8 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
     const MapView mv = map->view();
     const int npass = single_pass ? 1 : prm.max_iter + 1;
     for (int it = 0; it < npass; ++it) {
-        k_search<<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
+        if (map->knn_mode() == 1) k_search<1><<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
+        else k_search<0><<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
         k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(d_pts, d_nb.p, d_nbc.p, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials,
                                                    prm.max_iter, prm.R, d_limit, single_pass);
@@ -483,8 +486,11 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
         if (rc) return rc;
     } else {
         const MapView mv0 = map->view();
-        GraphKey key{d_pts, d_hdr, mv0.ent, mv0.pool, ps.plane, d_nb.p, search_grid, single_pass, force_converge};
-        if (!gexec || !(key == gkey)) {
+        GraphKey key{d_pts, d_hdr, mv0.ent, mv0.pool, ps.plane, d_nb.p, search_grid, single_pass, force_converge, map->knn_mode()};
+        if (gexec && key == gkey) {
+            CUDA_TRY(cudaGraphLaunch(gexec, stream));
+            ++graph_replays;
+        } else if (key == pending_key) {  // the same buffers twice in a row: worth a graph from now on
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t graph = nullptr;
             CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -495,8 +501,14 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
             CUDA_TRY(cudaGraphInstantiate(&gexec, graph, 0));
             cudaGraphDestroy(graph);
             gkey = key;
+            ++graph_captures;
+            CUDA_TRY(cudaGraphLaunch(gexec, stream));
+        } else {  // a buffer moved (map grew, scan size class changed): plain launches, no instantiation cost
+            pending_key = key;
+            rc = enqueue(d_pts, d_hdr, search_grid, single_pass, force_converge, false);
+            if (rc) return rc;
+            ++direct_runs;
         }
-        CUDA_TRY(cudaGraphLaunch(gexec, stream));
     }
     LAUNCH_COUNT(1 + 2 * npass);
     CUDA_TRY(cudaEventRecord(ev1, stream));
@@ -528,7 +540,7 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
 
 // ------------------------------------------------------------------ C ABI (B2)
 using namespace b200;
-struct b200_iekf { Iekf k; };
+struct b200_iekf { Iekf k; b200_map* owner = nullptr; };
 
 extern "C" {
 
@@ -537,13 +549,20 @@ int32_t b200_iekf_create(const b200_iekf_params* params, b200_map* map, b200_iek
     b200_iekf* h = new b200_iekf();
     int32_t rc = h->k.init(params, &map->m);
     if (rc != B200_OK) { h->k.destroy(); delete h; return rc; }
+    h->owner = map;
+    ++map->refs;  // the filter shares the map's stream and tables: the map outlives it even if destroyed first
     *out = h;
     return B200_OK;
 }
 int32_t b200_iekf_destroy(b200_iekf* ekf) {
     if (!ekf) return B200_OK;
     ekf->k.destroy();
+    b200_map* map = ekf->owner;
     delete ekf;
+    if (map && --map->refs == 0 && map->zombie) {
+        map->m.destroy();
+        delete map;
+    }
     return B200_OK;
 }
 
@@ -614,6 +633,15 @@ int32_t b200_iekf_io_bytes(b200_iekf* ekf, int64_t n, int64_t* h2d, int64_t* d2h
     const size_t hdr_pad = (offsetof(Ctl, x_prop) + 255) / 256 * 256;
     if (h2d) *h2d = (int64_t)(hdr_pad + (size_t)n * sizeof(float4));
     if (d2h) *d2h = (int64_t)sizeof(Ctl);
+    return B200_OK;
+}
+
+/* how the updates were launched so far: graph captures / graph replays / plain launch sequences */
+int32_t b200_iekf_launch_modes(b200_iekf* ekf, int32_t* captures, int32_t* replays, int32_t* direct) {
+    if (!ekf) B200_FAIL(B200_ERR_ARG, "bad argument");
+    if (captures) *captures = ekf->k.graph_captures;
+    if (replays) *replays = ekf->k.graph_replays;
+    if (direct) *direct = ekf->k.direct_runs;
     return B200_OK;
 }
 

@@ -202,7 +202,7 @@ __global__ void k_compact_plan(MapEntry* ent, int2* aux, uint32_t tsize, unsigne
 }
 
 // ------------------------------------------------------------------ standalone k=5 search
-template <int G>
+template <int G, int MODE>
 __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
                                                float* __restrict__ d2, int32_t* __restrict__ cnt) {
     const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -210,14 +210,10 @@ __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restric
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     if (gid >= n) return;  // whole groups leave together
     float4 p = __ldg(q + gid);
-    uint64_t win[5];
+    uint64_t w;
     float4 mine;
-    int c = knn5_group<G>(m, p.x, p.y, p.z, lg, gmask, lane_stencil<G>(lg, m.nstencil), win, mine);
+    int c = knn5_group<G, MODE>(m, p.x, p.y, p.z, lg, gmask, lane_stencil<G>(lg, m.nstencil), w, mine);
     if (lg < 5) {
-        uint64_t w = win[0];
-#pragma unroll
-        for (int r = 1; r < 5; ++r)
-            if (lg == r) w = win[r];
         idx[gid * 5 + lg] = __float_as_int(mine.w);
         d2[gid * 5 + lg] = (w == kInfKey) ? 0.0f : __uint_as_float((uint32_t)(w >> 32));
     }
@@ -305,6 +301,8 @@ void Map::destroy() {
     d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
     lru_in.release(); lru_out.release(); victims_dev.release(); h_runs.release(); h_lru.release(); h_small.release();
     q_idx.release(); q_cnt.release(); q_d2.release();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
 }
@@ -498,13 +496,21 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     CUDA_TRY(cudaMemcpyAsync(in_pts.p, h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, stream));
     constexpr int G = 8;
     const int64_t threads = n * G;
-    k_knn5<G><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+    if (!ev0) { CUDA_TRY(cudaEventCreate(&ev0)); CUDA_TRY(cudaEventCreate(&ev1)); }
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    {
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        if (knn_mode() == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        else k_knn5<G, 0><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+    }
+    CUDA_TRY(cudaEventRecord(ev1, stream));
     LAUNCH_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(idx, q_idx.p, n * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(d2, q_d2.p, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(cnt, q_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaEventElapsedTime(&last_knn_ms, ev0, ev1);
     return B200_OK;
 }
 
@@ -531,6 +537,10 @@ int32_t b200_map_create(const b200_map_params* params, int32_t device, b200_map*
 }
 int32_t b200_map_destroy(b200_map* map) {
     if (!map) return B200_OK;
+    if (map->refs > 0) {  // filters still attached: the last b200_iekf_destroy frees the map
+        map->zombie = true;
+        return B200_OK;
+    }
     map->m.destroy();
     delete map;
     return B200_OK;
@@ -580,6 +590,9 @@ int32_t b200_flush_l2(int32_t device) {
     return B200_OK;
 }
 
+/* device time (CUDA events) of the search kernel of the last b200_map_knn5 call */
+float b200_map_last_knn_ms(b200_map* map) { return map ? map->m.last_knn_ms : 0.f; }
+int64_t b200_map_evicted(b200_map* map) { return map ? (int64_t)map->m.evicted_total : 0; }
 int64_t b200_map_num_voxels(b200_map* map) { return map ? (int64_t)map->m.h_ctr.num_voxels : 0; }
 int64_t b200_map_num_points(b200_map* map) { return map ? (int64_t)map->m.h_ctr.live_points : 0; }
 

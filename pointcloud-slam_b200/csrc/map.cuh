@@ -83,12 +83,15 @@ __device__ __forceinline__ void top5_insert(uint64_t (&t)[5], uint64_t k) {
 // One query handled by a group of G lanes (G = 8): IVox::GetClosestPoint(pt, out, 5, max_range)
 // (ivox3d.h:132-204) + IVoxNode::KNNPointByCondition (ivox3d_node.hpp:140-205).
 // Candidate total order = (float d2 bits, stencil index, in-voxel index) — the "stable selection"
-// contract of SURVEY.md §7.  Returns the number found (0..5); win[] holds the composite keys in
-// ascending order on every lane of the group; lanes r < count also return winner r's pool entry.
+// contract of SURVEY.md §7.  Returns the number found (0..5); lane r < count holds the r-th winner: its
+// composite key in wkey and its pool entry (x, y, z, ordinal) in mine.
 //
-// Memory-level parallelism is the whole game here (a probe and a gather are both dependent L2/HBM
-// round trips): a lane first issues the table loads of all its stencil cells, then walks its runs as
-// one flat candidate sequence, four 16-byte gathers in flight at a time.
+// Memory-level parallelism and coalescing are the whole game here (a probe and a gather are both dependent
+// L2/HBM round trips): a lane first issues the table loads of all its stencil cells, then the group walks
+// the occupied runs together, G consecutive points per step (one or two 128-byte lines per query instead
+// of G scattered 16-byte gathers), four steps in flight; short runs stay with the probing lane.  Every lane keeps a
+// sorted top-5 of 64-bit keys and the G lists are merged by five group-min rounds.  (A group-shared running top-5
+// with a ballot per step was measured slower on B200: the ballots serialise the four groups of a warp.)
 // packed stencil offsets of lane lg: byte t of the result = (dx+1) | (dy+1)<<2 | (dz+1)<<4 for cell lg + G*t,
 // 0xFF when that cell is beyond the stencil.  Computed once per thread.
 template <int G>
@@ -104,67 +107,131 @@ __device__ __forceinline__ uint32_t lane_stencil(int lg, int nstencil) {
     return r;
 }
 
-template <int G>
+#ifndef B200_KNN_MODE
+#define B200_KNN_MODE 0
+#endif
+template <int G, int MODE = B200_KNN_MODE>
 __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, float qz, int lg, unsigned gmask, uint32_t lst,
-                                          uint64_t (&win)[5], float4& mine) {
+                                          uint64_t& wkey, float4& mine) {
     constexpr int SLOTS = (27 + G - 1) / G;
     static_assert(SLOTS <= 4, "lane_stencil packs four cells per lane");
+    static_assert(G >= 8, "lanes 0..4 of the group hold the running top-5");
+    constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     int cstart[SLOTS], ccount[SLOTS];
-    uint64_t ckey[SLOTS];
-    uint32_t cslot[SLOTS];
-    MapEntry ce[SLOTS];
-    const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
+    {
+        uint64_t ckey[SLOTS];
+        uint32_t cslot[SLOTS];
+        MapEntry ce[SLOTS];
+        const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
 #pragma unroll
-    for (int t = 0; t < SLOTS; ++t) {  // all first probes in flight together
-        const uint32_t b = (lst >> (8 * t)) & 0xFFu;
-        ckey[t] = kEmptyKey;
-        ce[t].key = kEmptyKey;
-        ce[t].start = 0;
-        ce[t].count = 0;
-        cslot[t] = 0;
-        if (b != 0xFFu) {
-            const int cx = kx + (int)(b & 3u) - 1, cy = ky + (int)((b >> 2) & 3u) - 1, cz = kz + (int)((b >> 4) & 3u) - 1;
-            if (cell_in_range(cx, cy, cz)) {
-                ckey[t] = pack_key(cx, cy, cz);
-                cslot[t] = hash_key(ckey[t]) & m.tmask;
+        for (int t = 0; t < SLOTS; ++t) {  // all first probes in flight together
+            const uint32_t b = (lst >> (8 * t)) & 0xFFu;
+            ckey[t] = kEmptyKey;
+            ce[t].key = kEmptyKey;
+            ce[t].start = 0;
+            ce[t].count = 0;
+            cslot[t] = 0;
+            if (b != 0xFFu) {
+                const int cx = kx + (int)(b & 3u) - 1, cy = ky + (int)((b >> 2) & 3u) - 1, cz = kz + (int)((b >> 4) & 3u) - 1;
+                if (cell_in_range(cx, cy, cz)) {
+                    ckey[t] = pack_key(cx, cy, cz);
+                    cslot[t] = hash_key(ckey[t]) & m.tmask;
+                    ce[t] = ld_entry(m.ent + cslot[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {  // collisions: keep probing linearly (rare at load factor <= 0.5)
+            while (ce[t].key != ckey[t] && ce[t].key != kEmptyKey) {
+                cslot[t] = (cslot[t] + 1) & m.tmask;
                 ce[t] = ld_entry(m.ent + cslot[t]);
+            }
+            const bool hit = ckey[t] != kEmptyKey && ce[t].key == ckey[t];
+            cstart[t] = ce[t].start;
+            ccount[t] = hit ? ce[t].count : 0;
+        }
+    }
+    const int lane0 = ((threadIdx.x & 31) / G) * G;  // first lane of this group inside the warp
+    uint64_t top[5] = {kInfKey, kInfKey, kInfKey, kInfKey, kInfKey};  // this lane's sorted best keys
+    auto consider = [&](const float4& p, uint32_t rank) {
+        // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
+        const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d2 < m.max_range2) top5_insert(top, ((uint64_t)__float_as_uint(d2) << 32) | rank);
+    };
+    // MODE 0: every lane walks its own cells one after the other, four gathers in flight (scattered 16-byte loads)
+    // MODE 1: the group walks every occupied cell together, G consecutive points per step
+    // MODE 2/3: runs of <= SHORT points stay with the probing lane (2: two points of every cell of the lane in flight
+    //           together, 3: cell by cell, four points in flight), longer runs are walked by the group
+    // MODE 4: like 3 when the query's stencil holds more than DENSE candidates in total, like 0 otherwise (decided per query)
+    int SHORT = MODE == 0 ? (1 << 30) : MODE == 1 ? 0 : MODE == 2 ? 2 : 4;
+    if (MODE == 4) {
+        constexpr int DENSE = 80;
+        int tot = 0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) tot += ccount[t];
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
+        if (tot <= DENSE) SHORT = 1 << 30;
+    }
+    if (MODE == 0 || MODE == 3 || MODE == 4) {
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            const int cnt = ccount[t] <= SHORT ? ccount[t] : 0;
+            const float4* run = m.pool + cstart[t];
+            const uint32_t rbase = (uint32_t)(lg + G * t) << kRankBits;
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u < cnt) p[u] = __ldg(run + j0 + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u < cnt) consider(p[u], rbase | (uint32_t)(j0 + u));
             }
         }
     }
+    if (MODE == 2) {
+        float4 p[SLOTS][2];
 #pragma unroll
-    for (int t = 0; t < SLOTS; ++t) {  // collisions: keep probing linearly (rare at load factor <= 0.5)
-        while (ce[t].key != ckey[t] && ce[t].key != kEmptyKey) {
-            cslot[t] = (cslot[t] + 1) & m.tmask;
-            ce[t] = ld_entry(m.ent + cslot[t]);
-        }
-        const bool hit = ckey[t] != kEmptyKey && ce[t].key == ckey[t];
-        cstart[t] = ce[t].start;
-        ccount[t] = hit ? ce[t].count : 0;
+        for (int t = 0; t < SLOTS; ++t)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ccount[t] <= SHORT && u < ccount[t]) p[t][u] = __ldg(m.pool + cstart[t] + u);
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ccount[t] <= SHORT && u < ccount[t]) consider(p[t][u], ((uint32_t)(lg + G * t) << kRankBits) | (uint32_t)u);
     }
-    uint64_t top[5] = {kInfKey, kInfKey, kInfKey, kInfKey, kInfKey};
+    if (MODE != 0) {
+        // longer runs are walked by the whole group: G consecutive points per step (one or two 128-byte lines per query
+        // instead of G scattered gathers), four steps in flight.  Which lane sees a candidate does not matter: the key
+        // carries the full enumeration rank.
 #pragma unroll
-    for (int t = 0; t < SLOTS; ++t) {
-        const float4* run = m.pool + cstart[t];
-        const int cnt = ccount[t];
-        const uint32_t rbase = (uint32_t)(lg + G * t) << kRankBits;
-        for (int j0 = 0; j0 < cnt; j0 += 4) {  // four gathers in flight
-            float4 p[4];
+        for (int t = 0; t < SLOTS; ++t) {
+            unsigned occ = (__ballot_sync(gmask, ccount[t] > SHORT) >> lane0) & GM;
+            while (occ) {  // uniform inside the group
+                const int o = __ffs(occ) - 1;
+                occ &= occ - 1;
+                const int cnt = __shfl_sync(gmask, ccount[t], lane0 + o);
+                const float4* run = m.pool + __shfl_sync(gmask, cstart[t], lane0 + o);
+                const uint32_t rbase = (uint32_t)(o + G * t) << kRankBits;
+                for (int j0 = lg; j0 < cnt; j0 += 4 * G) {
+                    float4 p[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (j0 + u < cnt) p[u] = __ldg(run + j0 + u);
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u * G < cnt) p[u] = __ldg(run + j0 + u * G);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j0 + u < cnt) {
-                    // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
-                    const float dx = __fsub_rn(p[u].x, qx), dy = __fsub_rn(p[u].y, qy), dz = __fsub_rn(p[u].z, qz);
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (d2 < m.max_range2) top5_insert(top, ((uint64_t)__float_as_uint(d2) << 32) | (rbase | (uint32_t)(j0 + u)));
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u * G < cnt) consider(p[u], rbase | (uint32_t)(j0 + u * G));
                 }
             }
         }
     }
-    // merge the G sorted lists: 5 rounds of group-min + pop
+    // merge the G sorted lists: 5 rounds of group-min + pop; lane r keeps winner r
     int count = 0;
+    uint64_t best = kInfKey;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         uint64_t mn = top[0];
@@ -173,7 +240,7 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
             const uint64_t other = __shfl_xor_sync(gmask, mn, o);
             mn = other < mn ? other : mn;
         }
-        win[r] = mn;
+        if (lg == r) best = mn;
         if (mn != kInfKey) {
             ++count;
             if (top[0] == mn) {
@@ -181,23 +248,20 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
             }
         }
     }
+    wkey = best;
     // fetch the winners: lane r loads winner r
     mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     {
-        uint64_t w = win[0];
-#pragma unroll
-        for (int r = 1; r < 5; ++r)
-            if (lg == r) w = win[r];
-        const uint32_t lo = (uint32_t)w;
+        const uint32_t lo = (uint32_t)best;
         const int s = (int)(lo >> kRankBits), j = (int)(lo & ((1u << kRankBits) - 1));
         const int owner = s % G, slot = s / G;
         int st = 0;
 #pragma unroll
         for (int t = 0; t < SLOTS; ++t) {  // every lane takes part in the shuffles
-            const int v = __shfl_sync(gmask, cstart[t], (owner & (G - 1)) + ((threadIdx.x & 31) / G) * G);
+            const int v = __shfl_sync(gmask, cstart[t], lane0 + (owner & (G - 1)));
             if (slot == t) st = v;
         }
-        if (lg < 5 && w != kInfKey) mine = __ldg(m.pool + st + j);
+        if (best != kInfKey) mine = __ldg(m.pool + st + j);
     }
     return count;
 }
@@ -218,6 +282,8 @@ struct Map {
     MapCounters h_ctr{};   // mirror after the last insert
     int64_t next_ord = 0;
     uint64_t tombstones = 0, evicted_total = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_knn_ms = 0.f;
     // scratch
     DevBuf<float4> in_pts;
     DevBuf<uint64_t> k_in, k_out, k_uniq;
@@ -234,6 +300,14 @@ struct Map {
     DevBuf<int32_t> q_idx, q_cnt;
     DevBuf<float> q_d2;
 
+    // Candidate-walk variant of the search kernels, picked per launch from the map's density: lane-owned cells (0) win while
+    // voxels hold a few points each (0.2 m voxels), the cooperative walk (1) once a long-lived map has dense voxels
+    // (measured on B200: 27 vs 47 us at 3 points/voxel, 100 vs 52 us at 25 points/voxel, 20k queries).
+    int knn_mode() const {
+        static const char* env = getenv("B200_KNN_MODE");
+        if (env) return atoi(env) ? 1 : 0;
+        return h_ctr.num_voxels > 0 && h_ctr.live_points > 6ull * h_ctr.num_voxels ? 1 : 0;
+    }
     MapView view() const {
         MapView v;
         v.ent = d_ent; v.pool = d_pool; v.tmask = tsize - 1; v.inv_res = inv_res;
@@ -252,4 +326,8 @@ struct Map {
 
 }  // namespace b200
 
-struct b200_map { b200::Map m; };
+struct b200_map {
+    b200::Map m;
+    int refs = 0;         // b200_iekf handles built on this map
+    bool zombie = false;  // b200_map_destroy was called while filters were still attached
+};
