@@ -186,6 +186,36 @@ int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* ndt, const float* x
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t* best,
                           double* best_score, float* gpu_ms);
 
+/* ------------------------------------------------------------------------- *
+ * Voxel-grid reductions.
+ *   b200_voxel_downsample replaces pcl::VoxelGrid<PointType>::filter as jueying_lio runs it on every scan
+ *   (jueying_lio/src/laser_mapping.cc:323-328; arithmetic as vendored in jueying_slam/include/voxel_grid_large.cpp:25-258).
+ *   b200_mapbuild_* replaces dynamic_map/construct_full_map <poses.txt> <frames_dir> <out.pcd> <leaf>
+ *   (scripts/construct_full_map.sh:6; sources absent from the reference - keyframes moved by their poses, merged,
+ *   VoxelGrid(leaf)); with a communicator the keyframes are split over GPUs and partial voxel sums are exchanged.
+ * ------------------------------------------------------------------------- */
+typedef struct b200_downsampler b200_downsampler;
+int32_t b200_downsampler_create(int32_t device, b200_downsampler** out);
+int32_t b200_downsampler_destroy(b200_downsampler* d);
+/* records x, y, z[, intensity] at stride_bytes; out_xyzi 4 floats per voxel in ascending leaf-index order, out_count
+ * points per voxel (either may be NULL), *n_out = number of voxels */
+int32_t b200_voxel_downsample(b200_downsampler* d, const float* xyzi, int64_t n, int64_t stride_bytes, float leaf, int32_t min_points,
+                              float* out_xyzi, int32_t* out_count, int64_t max_out, int64_t* n_out);
+/* the last result as it sits on the device (float4 per voxel): pass it to b200_iekf_update_device */
+const void* b200_downsampler_device_points(b200_downsampler* d, int64_t* n);
+
+typedef struct b200_mapbuild b200_mapbuild;
+int32_t b200_mapbuild_create(float leaf, uint64_t capacity_voxels, int32_t device, b200_mapbuild** out);
+int32_t b200_mapbuild_destroy(b200_mapbuild* h);
+/* one keyframe (frames/<i>.pcd, x y z intensity) with its pose (a line of poses.txt: x y z qw qx qy qz); asynchronous */
+int32_t b200_mapbuild_add_keyframe(b200_mapbuild* h, const float* xyzi, int64_t n, int64_t stride_bytes, const double* pose7);
+int32_t b200_mapbuild_add_keyframe_device(b200_mapbuild* h, const void* d_xyzi_float4, int64_t n, const double* pose7);
+int64_t b200_mapbuild_num_voxels(b200_mapbuild* h);
+/* collective: afterwards every voxel lives on exactly one rank with the sums of all ranks */
+int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h);
+/* centroids held by this rank, ascending (z, y, x) voxel order; returns the voxel count */
+int64_t b200_mapbuild_extract(b200_mapbuild* h, float* out_xyzi, int32_t* out_count, int64_t max_out);
+
 #ifdef __cplusplus
 }
 #endif

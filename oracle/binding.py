@@ -46,7 +46,7 @@ class NdtResult(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "smallmat.h", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "smallmat.h", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -102,6 +102,10 @@ def lib():
         L.orc_ndt_score_batch.argtypes = [vp, vp, i64, vp]
         L.orc_ndt_nbhd_total.restype = i64
         L.orc_ndt_nbhd_total.argtypes = [vp, vp]
+        L.orc_voxel_grid.restype = i64
+        L.orc_voxel_grid.argtypes = [vp, i64, i64, C.c_float, i32, vp, vp, i64]
+        L.orc_full_map.restype = i64
+        L.orc_full_map.argtypes = [vp, vp, i64, vp, C.c_float, vp, vp, i64]
         L.orc_euler_from_matrix.argtypes = [vp, vp]
         L.orc_matrix_from_pose.argtypes = [vp, vp]
         _LIB = L
@@ -322,3 +326,25 @@ def matrix_from_pose(p6):
     m = np.zeros((4, 4), np.float32)
     lib().orc_matrix_from_pose(_p(p6), _p(m))
     return m.T.copy()
+
+
+def voxel_grid(xyzi, leaf, min_points=0):
+    """pcl::VoxelGrid::filter on [n,3] or [n,4] (x,y,z,intensity) float32: returns (centroids [m,4], counts [m])."""
+    a = np.ascontiguousarray(xyzi, dtype=np.float32)
+    n = a.shape[0]
+    out = np.empty((max(n, 1), 4), np.float32)
+    cnt = np.empty(max(n, 1), np.int32)
+    m = lib().orc_voxel_grid(_p(a), n, a.strides[0], leaf, min_points, _p(out), _p(cnt), n)
+    return out[:m].copy(), cnt[:m].copy()
+
+
+def full_map(frames, poses7, leaf):
+    """construct_full_map oracle: frames = list of [n_k,4] float32 clouds, poses7 [k,7] (x y z qw qx qy qz)."""
+    offs = np.zeros(len(frames) + 1, np.int64)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    allp = np.ascontiguousarray(np.concatenate(frames, 0), dtype=np.float32)
+    poses = np.ascontiguousarray(poses7, dtype=np.float64)
+    out = np.empty((len(allp), 4), np.float32)
+    cnt = np.empty(len(allp), np.int32)
+    m = lib().orc_full_map(_p(allp), _p(offs), len(frames), _p(poses), leaf, _p(out), _p(cnt), len(allp))
+    return out[:m].copy(), cnt[:m].copy()

@@ -131,6 +131,14 @@ int64_t orc_ndt_nbhd_total(orc_ndt* h, const double* p6); /* sum of neighbourhoo
 void orc_euler_from_matrix(const float* m16_colmajor, float* rpy);
 void orc_matrix_from_pose(const double* p6, float* m16_colmajor);
 
+/* ---- pcl::VoxelGrid (scan downsample) and the keyframe-merge map builder (construct_full_map) ---- */
+/* records are (x, y, z, intensity) floats at `stride` bytes (stride 12: no intensity); out: 4 floats per voxel in
+ * ascending leaf-index order, out_count the points per voxel; returns the number of voxels */
+int64_t orc_voxel_grid(const float* xyzi, int64_t n, int64_t stride, float leaf, int32_t min_points, float* out_xyzi, int32_t* out_count,
+                       int64_t max);
+int64_t orc_full_map(const float* xyzi, const int64_t* offsets, int64_t n_frames, const double* poses7, float leaf, float* out_xyzi,
+                     int32_t* out_count, int64_t max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,24 @@ def lib():
         L.b200_ndt_last_ms.restype = C.c_float
         L.b200_ndt_last_ms.argtypes = [vp]
         L.b200_ndt_last_launches.argtypes = [vp]
+    L.b200_downsampler_create.argtypes = [i32, C.POINTER(vp)]
+    L.b200_downsampler_destroy.argtypes = [vp]
+    L.b200_voxel_downsample.argtypes = [vp, vp, i64, i64, C.c_float, i32, vp, vp, i64, vp]
+    L.b200_downsampler_device_points.restype = vp
+    L.b200_downsampler_device_points.argtypes = [vp, vp]
+    L.b200_downsampler_last_ms.restype = C.c_float
+    L.b200_downsampler_last_ms.argtypes = [vp]
+    L.b200_mapbuild_create.argtypes = [C.c_float, C.c_uint64, i32, C.POINTER(vp)]
+    L.b200_mapbuild_destroy.argtypes = [vp]
+    L.b200_mapbuild_add_keyframe.argtypes = [vp, vp, i64, i64, vp]
+    L.b200_mapbuild_add_keyframe_device.argtypes = [vp, vp, i64, vp]
+    L.b200_mapbuild_num_voxels.restype = i64
+    L.b200_mapbuild_num_voxels.argtypes = [vp]
+    L.b200_mapbuild_merge.argtypes = [vp, vp]
+    L.b200_mapbuild_extract.restype = i64
+    L.b200_mapbuild_extract.argtypes = [vp, vp, vp, i64]
+    L.b200_mapbuild_last_exchange_ms.restype = C.c_float
+    L.b200_mapbuild_last_exchange_ms.argtypes = [vp]
     _LIB = L
     return L
 
@@ -548,3 +566,93 @@ def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicat
                                  poses.shape[0], h_begin, C.byref(best), C.byref(score), C.byref(ms))
     _check(rc)
     return best.value, score.value, ms.value
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid's surface (setLeafSize / setInputCloud / filter) on the GPU (laser_mapping.cc:323-328)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().b200_downsampler_create(device, C.byref(self.h)))
+        self.leaf, self.min_points = 0.5, 0
+        self._cloud = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_downsampler_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def setLeafSize(self, lx, ly=None, lz=None):
+        self.leaf = float(lx)
+
+    def setMinimumPointsNumberPerVoxel(self, n):
+        self.min_points = int(n)
+
+    def setInputCloud(self, cloud):
+        a = np.asarray(cloud)
+        self._cloud = np.ascontiguousarray(a, dtype=np.float32)
+
+    def filter(self):
+        """Returns (centroids [m,4] x y z intensity, counts [m])."""
+        a = self._cloud
+        n = a.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        cnt = np.empty(max(n, 1), np.int32)
+        m = C.c_int64(0)
+        _check(lib().b200_voxel_downsample(self.h, _p(a), n, a.strides[0], self.leaf, self.min_points, _p(out), _p(cnt), n, C.byref(m)))
+        return out[:m.value].copy(), cnt[:m.value].copy()
+
+    def device_points(self):
+        n = C.c_int64(0)
+        p = lib().b200_downsampler_device_points(self.h, C.byref(n))
+        return p, n.value
+
+    def last_ms(self):
+        return float(lib().b200_downsampler_last_ms(self.h))
+
+
+class FullMapBuilder:
+    """construct_full_map <poses.txt> <frames_dir> <out.pcd> <leaf>: keyframes + poses -> voxel-grid merged map."""
+
+    def __init__(self, leaf=0.1, capacity_voxels=8_000_000, device=0):
+        self.h = C.c_void_p()
+        _check(lib().b200_mapbuild_create(leaf, capacity_voxels, device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_mapbuild_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def add_keyframe(self, xyzi, pose7):
+        a = np.ascontiguousarray(xyzi, dtype=np.float32)
+        p = np.ascontiguousarray(pose7, dtype=np.float64)
+        _check(lib().b200_mapbuild_add_keyframe(self.h, _p(a), a.shape[0], a.strides[0], _p(p)))
+
+    def add_keyframe_device(self, d_ptr, n, pose7):
+        p = np.ascontiguousarray(pose7, dtype=np.float64)
+        _check(lib().b200_mapbuild_add_keyframe_device(self.h, C.c_void_p(d_ptr), n, _p(p)))
+
+    def num_voxels(self):
+        n = lib().b200_mapbuild_num_voxels(self.h)
+        if n < 0:
+            raise B200Error(lib().b200_last_error().decode())
+        return int(n)
+
+    def merge(self, comm):
+        _check(lib().b200_mapbuild_merge(comm.h if comm is not None else None, self.h))
+
+    def exchange_ms(self):
+        return float(lib().b200_mapbuild_last_exchange_ms(self.h))
+
+    def extract(self):
+        m = lib().b200_mapbuild_extract(self.h, None, None, 0)
+        if m < 0:
+            raise B200Error(lib().b200_last_error().decode())
+        out = np.empty((max(m, 1), 4), np.float32)
+        cnt = np.empty(max(m, 1), np.int32)
+        lib().b200_mapbuild_extract(self.h, _p(out), _p(cnt), m)
+        return out[:m].copy(), cnt[:m].copy()

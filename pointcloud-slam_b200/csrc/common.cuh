@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -28,6 +29,18 @@ inline int32_t fail(int32_t code, const char* what, const char* file, int line) 
         if (_e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 #define LAUNCH_COUNT(n) (::b200::g_kernel_launches += (n))
+// Entry of a public call: select the handle's device and drop a stale "last error" left behind by an earlier, unrelated
+// runtime call in this process (ours or anybody else's), so that it is not mistaken for a failure of this call.
+inline void drop_stale_error(const char* file, int line) {
+    const cudaError_t e = cudaGetLastError();
+    static const bool dbg = getenv("B200_DEBUG") != nullptr;
+    if (e != cudaSuccess && dbg) fprintf(stderr, "[b200reg] stale CUDA error dropped at %s:%d: %s\n", file, line, cudaGetErrorString(e));
+}
+#define CUDA_SET_DEVICE(dev)                              \
+    do {                                                  \
+        ::b200::drop_stale_error(__FILE__, __LINE__);     \
+        CUDA_TRY(cudaSetDevice(dev));                     \
+    } while (0)
 
 template <class T>
 struct DevBuf {  // grow-only device buffer

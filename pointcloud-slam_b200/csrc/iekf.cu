@@ -377,7 +377,7 @@ int32_t Iekf::init(const b200_iekf_params* p, Map* m) {
     prm = *p;
     map = m;
     if (prm.max_iter < 1 || prm.max_iter + 1 > B200_MAX_PASSES) B200_FAIL(B200_ERR_ARG, "max_iter must be in [1, 7]");
-    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_SET_DEVICE(m->device);
     stream = m->stream;  // one stream per map/filter pair: inserts and updates are naturally ordered
     init_pair_tables();
     CUDA_TRY(cudaMalloc(&d_ctl, sizeof(Ctl)));
@@ -461,7 +461,7 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
 
 int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, double* P, b200_iekf_stats* st, int single_pass,
                   int force_converge) {
-    CUDA_TRY(cudaSetDevice(map->device));
+    CUDA_SET_DEVICE(map->device);
     int32_t rc = ensure_points((size_t)n);
     if (rc) return rc;
     CUDA_TRY(d_nb.reserve((size_t)n * 5));
@@ -586,7 +586,7 @@ static int32_t stage_scan(Iekf& k, const float* xyz, int64_t n, int64_t stride, 
 int32_t b200_iekf_update(b200_iekf* ekf, const float* scan, int64_t n, int64_t stride, double* x26, double* P, b200_iekf_stats* stats) {
     if (!ekf || !scan || !x26 || !P || n < 1 || stride < 12 || n > (1 << 26)) B200_FAIL(B200_ERR_ARG, "bad argument");
     Iekf& k = ekf->k;
-    CUDA_TRY(cudaSetDevice(k.map->device));
+    CUDA_SET_DEVICE(k.map->device);
     int32_t rc = stage_scan(k, scan, n, stride, x26, P);
     if (rc) return rc;
     const size_t hdr_pad = (offsetof(Ctl, x_prop) + 255) / 256 * 256;
@@ -655,7 +655,7 @@ int32_t b200_iekf_obs_model(b200_iekf* ekf, const float* scan, int64_t n, int64_
                             double* HtH, double* Hth, int32_t* n_eff) {
     if (!ekf || !scan || !x26 || n < 1 || stride < 12) B200_FAIL(B200_ERR_ARG, "bad argument");
     Iekf& k = ekf->k;
-    CUDA_TRY(cudaSetDevice(k.map->device));
+    CUDA_SET_DEVICE(k.map->device);
     int32_t rc = stage_scan(k, scan, n, stride, x26, nullptr);
     if (rc) return rc;
     const size_t hdr_pad = (offsetof(Ctl, x_prop) + 255) / 256 * 256;
@@ -675,7 +675,7 @@ int32_t b200_iekf_point_state(b200_iekf* ekf, int64_t n, float* plane4, float* r
                               int32_t* nn_count) {
     if (!ekf || n < 0 || (size_t)n > ekf->k.ps_cap) B200_FAIL(B200_ERR_ARG, "bad argument");
     Iekf& k = ekf->k;
-    CUDA_TRY(cudaSetDevice(k.map->device));
+    CUDA_SET_DEVICE(k.map->device);
     CUDA_TRY(cudaStreamSynchronize(k.stream));
     if (plane4) CUDA_TRY(cudaMemcpy(plane4, k.ps.plane, n * sizeof(float4), cudaMemcpyDeviceToHost));
     if (residual) CUDA_TRY(cudaMemcpy(residual, k.ps.resid, n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -705,7 +705,7 @@ int32_t b200_iekf_map_incremental(b200_iekf* ekf, const double* x26, int32_t ekf
     Iekf& k = ekf->k;
     const int n = k.last_n;
     if (n < 1 || !k.last_scan) B200_FAIL(B200_ERR_ARG, "no scan has been processed");
-    CUDA_TRY(cudaSetDevice(k.map->device));
+    CUDA_SET_DEVICE(k.map->device);
     CUDA_TRY(k.d_world.reserve(n)); CUDA_TRY(k.d_sel_pts.reserve(2 * (size_t)n));
     CUDA_TRY(k.d_flag.reserve(n)); CUDA_TRY(k.d_flag2.reserve(n));
     memcpy(k.h_x.p, x26, sizeof(double) * 26);

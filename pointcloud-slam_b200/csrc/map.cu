@@ -271,7 +271,7 @@ int32_t Map::init(const b200_map_params* p, int dev) {
     if (prm.capacity_voxels == 0) prm.capacity_voxels = 1000000;
     if (prm.max_points == 0) prm.max_points = 8u << 20;
     device = dev;
-    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_SET_DEVICE(dev);
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     inv_res = (float)(1.0 / (double)prm.resolution);  // ivox3d.h:65
     nstencil = prm.nearby == 0 ? 1 : prm.nearby == 6 ? 7 : prm.nearby == 26 ? 27 : 19;
@@ -426,7 +426,7 @@ int32_t Map::evict_for_batch(int64_t n) {
 int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     if (n == 0) return B200_OK;
     if (n > (int64_t)0x3fffffff) B200_FAIL(B200_ERR_ARG, "batch too large");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     // worst case for this batch: every touched voxel relocates and doubles -> <= 2*(live + n) new slots
     if (h_ctr.pool_top + 2 * (h_ctr.live_points + (uint64_t)n) > pool_cap) {
         int32_t rc = grow_pool((uint64_t)n);
@@ -477,7 +477,7 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
 int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
     if (n == 0) return B200_OK;
     if (n < 0 || !xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "bad point buffer");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     CUDA_TRY(h_stage.reserve(n));
     CUDA_TRY(in_pts.reserve(n));
     pack_xyz_float4(xyz, n, stride, h_stage.p);
@@ -488,7 +488,7 @@ int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
 int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt) {
     if (n == 0) return B200_OK;
     if (n < 0 || !xyz || !idx || !d2 || !cnt || stride < 12) B200_FAIL(B200_ERR_ARG, "bad query buffer");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     CUDA_TRY(h_stage.reserve(n));
     CUDA_TRY(in_pts.reserve(n));
     CUDA_TRY(q_idx.reserve(n * 5)); CUDA_TRY(q_d2.reserve(n * 5)); CUDA_TRY(q_cnt.reserve(n));
@@ -557,7 +557,7 @@ int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t 
 int32_t b200_map_stencil_points(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int64_t* points, int64_t* cells) {
     if (!map || !xyz_world || n < 1 || stride_bytes < 12) B200_FAIL(B200_ERR_ARG, "bad argument");
     b200::Map& m = map->m;
-    CUDA_TRY(cudaSetDevice(m.device));
+    CUDA_SET_DEVICE(m.device);
     CUDA_TRY(m.h_stage.reserve(n));
     CUDA_TRY(m.in_pts.reserve(n));
     b200::pack_xyz_float4(xyz_world, n, stride_bytes, m.h_stage.p);
@@ -580,7 +580,7 @@ int32_t b200_flush_l2(int32_t device) {
     static float4* buf[16] = {};
     const size_t n = (256u << 20) / sizeof(float4);
     if (device < 0 || device >= 16) B200_FAIL(B200_ERR_ARG, "bad device");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     if (!buf[device]) CUDA_TRY(cudaMalloc(&buf[device], n * sizeof(float4)));
     static float v = 0.f;
     v += 1.f;

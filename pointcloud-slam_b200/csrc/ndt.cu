@@ -742,7 +742,7 @@ int32_t Ndt::init(const b200_ndt_params* p, int dev) {
     if (prm.min_pts <= 0) prm.min_pts = 6;
     if (!(prm.eig_ratio > 0)) prm.eig_ratio = 0.01;
     device = dev;
-    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_SET_DEVICE(dev);
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
@@ -813,7 +813,7 @@ int32_t Ndt::upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>&
 int32_t Ndt::set_target(const float* xyz, int64_t n, int64_t stride) {
     if (n < 1 || !xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "bad target cloud");
     if (n > (int64_t)0x7fffff00) B200_FAIL(B200_ERR_ARG, "target cloud too large");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     int32_t rc = upload(xyz, n, stride, d_tgt);
     if (rc) return rc;
     return build_target(n);
@@ -840,7 +840,7 @@ int32_t Ndt::build_target(int64_t n) {
     const float inv_leaf = 1.0f / prm.resolution;
     const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv_leaf) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv_leaf) + 1,
                   dz = (int64_t)((mx[2] - mn[2]) * inv_leaf) + 1;
-    if (dx * dy * dz > (int64_t)INT32_MAX) B200_FAIL(B200_ERR_RANGE, "leaf size too small for the target: integer leaf indices would overflow");
+    if ((double)dx * (double)dy * (double)dz > (double)INT32_MAX) B200_FAIL(B200_ERR_RANGE, "leaf size too small for the target: integer leaf indices would overflow");
     gd.inv_leaf = inv_leaf;
     for (int k = 0; k < 3; ++k) {
         gd.min_b[k] = (int)std::floor(mn[k] * inv_leaf);
@@ -895,7 +895,7 @@ int32_t Ndt::build_target(int64_t n) {
 
 int32_t Ndt::set_source(const float* xyz, int64_t n, int64_t stride) {
     if (n < 1 || !xyz || stride < 12 || n > (1 << 28)) B200_FAIL(B200_ERR_ARG, "bad source cloud");
-    CUDA_TRY(cudaSetDevice(device));
+    CUDA_SET_DEVICE(device);
     int32_t rc = upload(xyz, n, stride, d_src);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1025,7 +1025,7 @@ int32_t b200_ndt_set_target(b200_ndt* n, const float* xyz, int64_t cnt, int64_t 
 int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* n, const float* xyz, int64_t cnt, int64_t stride, int32_t root) {
     if (!n || !comm || cnt < 1 || cnt > (int64_t)0x7fffff00) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     if (comm->rank == root) {
         if (!xyz || stride < 12) B200_FAIL(B200_ERR_ARG, "root needs the cloud");
         int32_t rc = k.upload(xyz, cnt, stride, k.d_tgt);
@@ -1088,7 +1088,7 @@ int32_t b200_ndt_grid(b200_ndt* n, int32_t* min_b3, int32_t* div_b3) {
 int32_t b200_ndt_align(b200_ndt* n, const float* guess16, float* final16, b200_ndt_result* result) {
     if (!n || !guess16 || !final16) B200_FAIL(B200_ERR_ARG, "null argument");
     Ndt& k = n->k;
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     CUDA_TRY(k.d_poses.reserve(16));
     CUDA_TRY(k.h_poses.reserve(16));
     memcpy(k.h_poses.p, guess16, 16 * sizeof(float));
@@ -1105,7 +1105,7 @@ int32_t b200_ndt_align(b200_ndt* n, const float* guess16, float* final16, b200_n
 int32_t b200_ndt_align_batch(b200_ndt* n, const float* guesses16, int64_t h, float* finals16, b200_ndt_result* results) {
     if (!n || !guesses16 || h < 1 || h > 65535) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     CUDA_TRY(k.d_poses.reserve((size_t)h * 16));
     CUDA_TRY(k.h_poses.reserve((size_t)h * 16));
     memcpy(k.h_poses.p, guesses16, (size_t)h * 16 * sizeof(float));
@@ -1117,7 +1117,7 @@ int32_t b200_ndt_align_batch(b200_ndt* n, const float* guesses16, int64_t h, flo
 }
 
 static int32_t single_eval(Ndt& k, const double* p6, int phase) {
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     CUDA_TRY(k.d_p_in.reserve(6));
     CUDA_TRY(k.h_scores.reserve(8));
     memcpy(k.h_scores.p, p6, 6 * sizeof(double));
@@ -1147,7 +1147,7 @@ int32_t b200_ndt_hessian(b200_ndt* n, const double* p6, double* H36) {
 int32_t b200_ndt_score_batch(b200_ndt* n, const float* poses16, int64_t h, double* scores) {
     if (!n || !poses16 || !scores || h < 1) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     CUDA_TRY(k.d_poses.reserve((size_t)h * 16)); CUDA_TRY(k.h_poses.reserve((size_t)h * 16));
     CUDA_TRY(k.d_scores.reserve(h)); CUDA_TRY(k.h_scores.reserve(h));
     memcpy(k.h_poses.p, poses16, (size_t)h * 16 * sizeof(float));
@@ -1204,7 +1204,7 @@ int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, in
                           float* gpu_ms) {
     if (!n || (h > 0 && !poses16) || h < 0 || h_begin < 0) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
-    CUDA_TRY(cudaSetDevice(k.device));
+    CUDA_SET_DEVICE(k.device);
     const int64_t hh = std::max<int64_t>(h, 1);
     CUDA_TRY(k.d_poses.reserve((size_t)hh * 16)); CUDA_TRY(k.h_poses.reserve((size_t)hh * 16));
     CUDA_TRY(k.d_scores.reserve(hh));

@@ -1,0 +1,652 @@
+// b200reg — voxel-grid reductions: scan downsample (pcl::VoxelGrid) and the keyframe-merge map builder.
+//
+// Replaces
+//   pcl::VoxelGrid<PointType>::filter as jueying_lio calls it on every scan (jueying_lio/src/laser_mapping.cc:323-328,
+//   leaf = filter_size_surf); PCL is third-party, its applyFilter is vendored nearly verbatim in
+//   jueying_slam/include/voxel_grid_large.cpp:25-258 (min/max -> leaf index -> sort -> per-leaf centroid);
+//   dynamic_map/construct_full_map <poses.txt> <frames_dir> <out.pcd> <leaf> (scripts/construct_full_map.sh:6) — sources
+//   absent from the reference; built here as "move every keyframe by its pose, merge, VoxelGrid(leaf)".
+//
+// downsample   min/max -> 64-bit leaf index per point -> stable radix sort -> run-length segments -> one thread per
+//              leaf sums x, y, z, intensity in fp32 in input order and divides by the count (the arithmetic of
+//              pcl::CentroidPoint) -> centroids in ascending leaf-index order.  The result can stay on the device and feed
+//              b200_iekf_update_device directly.
+// map builder  a voxel hash table in HBM {key, sum x/y/z/intensity in fp64, count}; every keyframe is transformed (fp32,
+//              pcl::transformPointCloud order) and accumulated with atomics, so keyframes stream through in any order
+//              and any number per launch.  Across GPUs (one process each, keyframes split in contiguous blocks) the
+//              partial sums are exchanged by voxel ownership (hash of the key) with grouped ncclSend/ncclRecv and merged;
+//              afterwards every rank owns a disjoint part of the map.
+#include "common.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "comm.cuh"
+
+namespace b200 {
+namespace vox {
+
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+__global__ void k_minmax_init(int* mm) {
+    if (threadIdx.x < 3) mm[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) mm[threadIdx.x] = (int)0x80000000;
+}
+__global__ void k_minmax(const float4* __restrict__ pts, int64_t n, int* __restrict__ mm) {
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(pts + i);
+        if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(mm + k, f2ord(mn[k]));
+            atomicMax(mm + 3 + k, f2ord(mx[k]));
+        }
+    }
+}
+
+struct Grid {
+    long long min_b[3], div_b[3];
+    float inv_leaf;
+};
+
+// leaf index of every point (voxel_grid_large.cpp:163-168), 64-bit; non-finite points get the sentinel and sort last
+__global__ void k_keys(const float4* __restrict__ pts, int n, Grid g, unsigned long long sentinel, unsigned long long* __restrict__ keys,
+                       int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    unsigned long long key = sentinel;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const long long i0 = (long long)(floorf(p.x * g.inv_leaf) - (float)g.min_b[0]);
+        const long long i1 = (long long)(floorf(p.y * g.inv_leaf) - (float)g.min_b[1]);
+        const long long i2 = (long long)(floorf(p.z * g.inv_leaf) - (float)g.min_b[2]);
+        key = (unsigned long long)(i0 + i1 * g.div_b[0] + i2 * g.div_b[0] * g.div_b[1]);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// one thread per leaf: fp32 sums in input order, divided by the count (pcl::CentroidPoint); compacts on min_points
+__global__ void k_centroids(const float4* __restrict__ pts, const int32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ uniq,
+                            const int32_t* __restrict__ run_off, const int32_t* __restrict__ run_cnt, const int32_t* __restrict__ nruns,
+                            unsigned long long sentinel, int min_points, float4* __restrict__ out, int32_t* __restrict__ out_cnt,
+                            uint8_t* __restrict__ keep) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    const int c = run_cnt[r];
+    const bool ok = uniq[r] != sentinel && c >= min_points;
+    keep[r] = ok ? 1 : 0;
+    out_cnt[r] = c;
+    if (!ok) return;
+    const int off = run_off[r];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int k = 0; k < c; ++k) {
+        const float4 p = __ldg(pts + __ldg(sorted_idx + off + k));
+        sx += p.x; sy += p.y; sz += p.z; si += p.w;
+    }
+    const float n = (float)c;
+    out[r] = make_float4(sx / n, sy / n, sz / n, si / n);
+}
+
+// ------------------------------------------------------------------ map builder
+struct __align__(16) Acc {
+    double sx, sy, sz, si;
+};
+struct __align__(16) Xfer {  // what travels between ranks
+    unsigned long long key;
+    unsigned int n, pad;
+    double sx, sy, sz, si;
+};
+static_assert(sizeof(Xfer) == 48, "exchange record");
+
+__device__ __forceinline__ uint32_t mix64(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+struct Table {
+    unsigned long long* keys;
+    Acc* acc;
+    unsigned int* cnt;
+    uint32_t mask;
+};
+
+__device__ __forceinline__ int table_slot(const Table& t, unsigned long long key, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
+    uint32_t slot = mix64(key) & t.mask;
+    for (uint32_t probes = 0; probes <= t.mask; ++probes) {
+        const unsigned long long k = t.keys[slot];
+        if (k == key) return (int)slot;
+        if (k == kEmptyKey) {
+            const unsigned long long old = atomicCAS(t.keys + slot, kEmptyKey, key);
+            if (old == kEmptyKey) {
+                if (atomicAdd(n_voxels, 1u) + 1u > capacity) atomicAdd(err, 1u);
+                return (int)slot;
+            }
+            if (old == key) return (int)slot;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+    atomicAdd(err, 1u);
+    return -1;
+}
+
+// One keyframe (or several: `frame_of` maps a point to its pose) through pcl::transformPointCloud and into the table.
+// Voxel cell = floor(p * inverse_leaf) per axis, exactly VoxelGrid's partition; the key orders voxels like VoxelGrid's
+// leaf index does (z slowest, then y, then x).
+__global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, const float* __restrict__ M12, float inv_leaf, Table t,
+                             unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
+    __shared__ float M[12];
+    if (threadIdx.x < 12) M[threadIdx.x] = M12[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(pts + i);
+        const float x = ((M[0] * p.x + M[1] * p.y) + M[2] * p.z) + M[3];
+        const float y = ((M[4] * p.x + M[5] * p.y) + M[6] * p.z) + M[7];
+        const float z = ((M[8] * p.x + M[9] * p.y) + M[10] * p.z) + M[11];
+        if (!(isfinite(x) && isfinite(y) && isfinite(z))) continue;
+        const int cx = (int)floorf(x * inv_leaf), cy = (int)floorf(y * inv_leaf), cz = (int)floorf(z * inv_leaf);
+        if (!cell_in_range(cx, cy, cz)) { atomicAdd(err + 1, 1u); continue; }
+        const unsigned long long key = pack_key(cz, cy, cx);
+        const int s = table_slot(t, key, n_voxels, capacity, err);
+        if (s < 0) continue;
+        atomicAdd(&t.acc[s].sx, (double)x);
+        atomicAdd(&t.acc[s].sy, (double)y);
+        atomicAdd(&t.acc[s].sz, (double)z);
+        atomicAdd(&t.acc[s].si, (double)p.w);
+        atomicAdd(t.cnt + s, 1u);
+    }
+}
+
+__global__ void k_table_clear(Table t) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > t.mask) return;
+    t.keys[s] = kEmptyKey;
+    t.acc[s] = Acc{0.0, 0.0, 0.0, 0.0};
+    t.cnt[s] = 0;
+}
+
+// occupied slots -> (key, slot) pairs
+__global__ void k_table_list(Table t, unsigned long long* __restrict__ keys, uint32_t* __restrict__ slots, unsigned int* n_out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > t.mask) return;
+    const unsigned long long k = t.keys[s];
+    if (k == kEmptyKey) return;
+    const unsigned int i = atomicAdd(n_out, 1u);
+    keys[i] = k;
+    slots[i] = s;
+}
+
+__global__ void k_extract(Table t, const uint32_t* __restrict__ slots, int64_t m, float4* __restrict__ out, int32_t* __restrict__ out_cnt) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t s = slots[i];
+    const Acc a = t.acc[s];
+    const double n = (double)t.cnt[s];
+    out[i] = make_float4((float)(a.sx / n), (float)(a.sy / n), (float)(a.sz / n), (float)(a.si / n));
+    if (out_cnt) out_cnt[i] = (int32_t)t.cnt[s];
+}
+
+// exchange: owner rank of a voxel, records grouped by owner
+__device__ __forceinline__ int owner_of(unsigned long long key, int nranks) { return (int)((mix64(key ^ 0x9E3779B97F4A7C15ULL) >> 8) % (uint32_t)nranks); }
+
+__global__ void k_owner_count(Table t, int nranks, unsigned long long* __restrict__ counts) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > t.mask) return;
+    const unsigned long long k = t.keys[s];
+    if (k == kEmptyKey) return;
+    atomicAdd(counts + owner_of(k, nranks), 1ull);
+}
+__global__ void k_owner_scatter(Table t, int nranks, unsigned long long* __restrict__ cursor /*starts at the owner offsets*/, Xfer* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > t.mask) return;
+    const unsigned long long k = t.keys[s];
+    if (k == kEmptyKey) return;
+    const unsigned long long i = atomicAdd(cursor + owner_of(k, nranks), 1ull);
+    const Acc a = t.acc[s];
+    out[i] = Xfer{k, t.cnt[s], 0u, a.sx, a.sy, a.sz, a.si};
+}
+__global__ void k_merge_records(const Xfer* __restrict__ rec, int64_t m, Table t, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Xfer r = rec[i];
+    const int s = table_slot(t, r.key, n_voxels, capacity, err);
+    if (s < 0) return;
+    atomicAdd(&t.acc[s].sx, r.sx);
+    atomicAdd(&t.acc[s].sy, r.sy);
+    atomicAdd(&t.acc[s].sz, r.sz);
+    atomicAdd(&t.acc[s].si, r.si);
+    atomicAdd(t.cnt + s, r.n);
+}
+
+static uint32_t next_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v && p < (1u << 31)) p <<= 1;
+    return p;
+}
+
+struct Builder {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float leaf = 0.1f, inv_leaf = 10.f;
+    uint64_t capacity = 0;
+    Table tab{}, tab2{};
+    bool have_tab2 = false;
+    unsigned int* d_ctr = nullptr;  // [0] voxels, [1] table errors, [2] range errors, [3] list count
+    PinnedBuf<unsigned int> h_ctr;
+    DevBuf<float4> d_pts, d_out;
+    DevBuf<float> d_M;
+    PinnedBuf<float> h_M;
+    PinnedBuf<float4> h_stage;
+    DevBuf<unsigned long long> d_keys, d_keys2, d_counts;
+    DevBuf<uint32_t> d_slots, d_slots2;
+    DevBuf<int32_t> d_cnt;
+    DevBuf<uint8_t> cub_tmp;
+    DevBuf<Xfer> d_send, d_recv;
+    PinnedBuf<unsigned long long> h_counts;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t frames = 0, points = 0;
+    float ms_accumulate = 0.f, last_ms = 0.f;
+    int64_t n_sorted = -1;  // entries of d_slots valid for extraction, -1 = stale
+
+    int32_t alloc_table(Table& t) {
+        const uint32_t T = next_pow2(2 * capacity);
+        t.mask = T - 1;
+        CUDA_TRY(cudaMalloc(&t.keys, (size_t)T * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&t.acc, (size_t)T * sizeof(Acc)));
+        CUDA_TRY(cudaMalloc(&t.cnt, (size_t)T * sizeof(unsigned int)));
+        k_table_clear<<<(T + 255) / 256, 256, 0, stream>>>(t);
+        LAUNCH_COUNT(1);
+        return B200_OK;
+    }
+    void free_table(Table& t) {
+        cudaFree(t.keys); cudaFree(t.acc); cudaFree(t.cnt);
+        t = Table{};
+    }
+    int32_t init(float leaf_, uint64_t cap, int dev) {
+        if (!(leaf_ > 0.f) || cap < 1 || cap > (1ull << 30)) B200_FAIL(B200_ERR_ARG, "bad map-builder parameters");
+        device = dev; leaf = leaf_; inv_leaf = 1.0f / leaf_; capacity = cap;
+        CUDA_SET_DEVICE(dev);
+        CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaMalloc(&d_ctr, 8 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemsetAsync(d_ctr, 0, 8 * sizeof(unsigned int), stream));
+        CUDA_TRY(h_ctr.reserve(8));
+        CUDA_TRY(d_M.reserve(12));
+        CUDA_TRY(h_M.reserve(12));
+        int32_t rc = alloc_table(tab);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return B200_OK;
+    }
+    void destroy() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        free_table(tab);
+        if (have_tab2) free_table(tab2);
+        cudaFree(d_ctr);
+        h_ctr.release(); d_pts.release(); d_out.release(); d_M.release(); h_M.release(); h_stage.release(); d_keys.release(); d_keys2.release();
+        d_counts.release(); d_slots.release(); d_slots2.release(); d_cnt.release(); cub_tmp.release(); d_send.release(); d_recv.release();
+        h_counts.release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    // T = Translation * Quaterniond in double, narrowed to float (poses.txt: x y z qw qx qy qz)
+    static void pose_matrix(const double* p7, float* M) {
+        const double w = p7[3], x = p7[4], y = p7[5], z = p7[6];
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                             2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                             2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) M[r * 4 + c] = (float)R[r * 3 + c];
+            M[r * 4 + 3] = (float)p7[r];
+        }
+    }
+    int32_t add_device(const float4* d_frame, int64_t n, const double* pose7) {
+        CUDA_SET_DEVICE(device);
+        // the 48-byte matrix rides in a small pinned ring so that keyframes can be queued back to back
+        const int slot = (int)(frames % 64);
+        CUDA_TRY(h_M.reserve(12 * 64));
+        CUDA_TRY(d_M.reserve(12 * 64));
+        if (slot == 0 && frames > 0) CUDA_TRY(cudaStreamSynchronize(stream));  // the ring is about to be reused
+        pose_matrix(pose7, h_M.p + 12 * slot);
+        CUDA_TRY(cudaMemcpyAsync(d_M.p + 12 * slot, h_M.p + 12 * slot, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        k_accumulate<<<blocks, 256, 0, stream>>>(d_frame, n, d_M.p + 12 * slot, inv_leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
+        LAUNCH_COUNT(1);
+        ++frames;
+        points += n;
+        n_sorted = -1;
+        return B200_OK;
+    }
+    int32_t check() {
+        CUDA_TRY(cudaMemcpyAsync(h_ctr.p, d_ctr, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaGetLastError());
+        if (h_ctr.p[1]) B200_FAIL(B200_ERR_CAPACITY, "map builder: voxel capacity exceeded");
+        if (h_ctr.p[2]) B200_FAIL(B200_ERR_RANGE, "map builder: point outside the voxel key range");
+        return B200_OK;
+    }
+    // sorted list of the occupied slots (ascending key = VoxelGrid's leaf order)
+    int32_t sort_slots() {
+        int32_t rc = check();
+        if (rc) return rc;
+        const int64_t m = h_ctr.p[0];
+        const uint32_t T = tab.mask + 1;
+        CUDA_TRY(d_keys.reserve(m + 1)); CUDA_TRY(d_keys2.reserve(m + 1)); CUDA_TRY(d_slots.reserve(m + 1)); CUDA_TRY(d_slots2.reserve(m + 1));
+        CUDA_TRY(cudaMemsetAsync(d_ctr + 3, 0, sizeof(unsigned int), stream));
+        k_table_list<<<(T + 255) / 256, 256, 0, stream>>>(tab, d_keys.p, d_slots.p, d_ctr + 3);
+        LAUNCH_COUNT(1);
+        if (m > 0) {
+            size_t tmp = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys.p, d_keys2.p, d_slots.p, d_slots2.p, (int)m, 0, 63, stream);
+            CUDA_TRY(cub_tmp.reserve(tmp));
+            CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, d_keys.p, d_keys2.p, d_slots.p, d_slots2.p, (int)m, 0, 63, stream));
+        }
+        n_sorted = m;
+        return B200_OK;
+    }
+};
+
+}  // namespace vox
+}  // namespace b200
+
+using namespace b200;
+struct b200_mapbuild { vox::Builder b; };
+struct b200_downsampler {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf<float4> d_in, d_out, d_cmp;
+    DevBuf<unsigned long long> k_in, k_out, k_uniq;
+    DevBuf<int32_t> v_in, v_out, run_cnt, run_off, d_small, d_cnt, d_cnt_cmp;
+    DevBuf<uint8_t> keep, cub_tmp;
+    PinnedBuf<float4> h_stage;
+    PinnedBuf<int32_t> h_small;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int64_t n_out = 0;
+};
+
+static int32_t downsample_run(b200_downsampler* d, int64_t n, float leaf, int32_t min_points) {
+    using namespace vox;
+    cudaStream_t s = d->stream;
+    CUDA_TRY(cudaEventRecord(d->ev0, s));
+    int* mm = d->d_small.p;
+    k_minmax_init<<<1, 32, 0, s>>>(mm);
+    k_minmax<<<148 * 4, 256, 0, s>>>(d->d_in.p, n, mm);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(d->h_small.p, mm, 6 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+        int a = d->h_small.p[k], b = d->h_small.p[3 + k];
+        a = a >= 0 ? a : a ^ 0x7fffffff;
+        b = b >= 0 ? b : b ^ 0x7fffffff;
+        memcpy(&mn[k], &a, 4);
+        memcpy(&mx[k], &b, 4);
+    }
+    d->n_out = 0;
+    if (!(mn[0] <= mx[0])) return B200_OK;  // no finite point: empty output
+    Grid g;
+    g.inv_leaf = 1.0f / leaf;
+    for (int k = 0; k < 3; ++k) {
+        g.min_b[k] = (long long)std::floor(mn[k] * g.inv_leaf);
+        g.div_b[k] = (long long)std::floor(mx[k] * g.inv_leaf) - g.min_b[k] + 1;
+    }
+    const double cells = (double)g.div_b[0] * (double)g.div_b[1] * (double)g.div_b[2];
+    if (cells > 9.0e18) B200_FAIL(B200_ERR_RANGE, "leaf size too small for the cloud extent");
+    const unsigned long long sentinel = (unsigned long long)cells;
+    int end_bit = 1;
+    while (end_bit < 64 && (double)(1ull << end_bit) <= cells) ++end_bit;
+    CUDA_TRY(d->k_in.reserve(n)); CUDA_TRY(d->k_out.reserve(n)); CUDA_TRY(d->k_uniq.reserve(n));
+    CUDA_TRY(d->v_in.reserve(n)); CUDA_TRY(d->v_out.reserve(n)); CUDA_TRY(d->run_cnt.reserve(n)); CUDA_TRY(d->run_off.reserve(n));
+    CUDA_TRY(d->d_out.reserve(n)); CUDA_TRY(d->d_cmp.reserve(n)); CUDA_TRY(d->d_cnt.reserve(n)); CUDA_TRY(d->d_cnt_cmp.reserve(n));
+    CUDA_TRY(d->keep.reserve(n));
+    const int nb = (int)((n + 255) / 256);
+    k_keys<<<nb, 256, 0, s>>>(d->d_in.p, (int)n, g, sentinel, d->k_in.p, d->v_in.p);
+    CUDA_TRY(cudaGetLastError());
+    int32_t* d_nruns = d->d_small.p + 8;
+    int32_t* d_nsel = d->d_small.p + 9;
+    size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, d->k_in.p, d->k_out.p, d->v_in.p, d->v_out.p, (int)n, 0, end_bit, s));
+    CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, t2, d->k_out.p, d->k_uniq.p, d->run_cnt.p, d_nruns, (int)n, s));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t3, d->run_cnt.p, d->run_off.p, (int)n, s));
+    CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, t4, d->d_out.p, d->keep.p, d->d_cmp.p, d_nsel, (int)n, s));
+    const size_t tmp = std::max(std::max(t1, t2), std::max(t3, t4));
+    CUDA_TRY(d->cub_tmp.reserve(tmp));
+    size_t tt = tmp;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->cub_tmp.p, tt, d->k_in.p, d->k_out.p, d->v_in.p, d->v_out.p, (int)n, 0, end_bit, s));
+    tt = tmp;
+    CUDA_TRY(cub::DeviceRunLengthEncode::Encode(d->cub_tmp.p, tt, d->k_out.p, d->k_uniq.p, d->run_cnt.p, d_nruns, (int)n, s));
+    tt = tmp;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(d->cub_tmp.p, tt, d->run_cnt.p, d->run_off.p, (int)n, s));
+    k_centroids<<<nb, 256, 0, s>>>(d->d_in.p, d->v_out.p, d->k_uniq.p, d->run_off.p, d->run_cnt.p, d_nruns, sentinel, min_points, d->d_out.p,
+                                   d->d_cnt.p, d->keep.p);
+    // runs beyond nruns carry stale keep flags: compact only the first nruns entries
+    CUDA_TRY(cudaMemcpyAsync(d->h_small.p, d_nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const int nruns = d->h_small.p[0];
+    tt = tmp;
+    CUDA_TRY(cub::DeviceSelect::Flagged(d->cub_tmp.p, tt, d->d_out.p, d->keep.p, d->d_cmp.p, d_nsel, nruns, s));
+    tt = tmp;
+    CUDA_TRY(cub::DeviceSelect::Flagged(d->cub_tmp.p, tt, d->d_cnt.p, d->keep.p, d->d_cnt_cmp.p, d_nsel, nruns, s));
+    LAUNCH_COUNT(4);
+    CUDA_TRY(cudaEventRecord(d->ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(d->h_small.p, d_nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    d->n_out = d->h_small.p[0];
+    cudaEventElapsedTime(&d->last_ms, d->ev0, d->ev1);
+    return B200_OK;
+}
+
+extern "C" {
+
+/* ---- scan downsample ---- */
+int32_t b200_downsampler_create(int32_t device, b200_downsampler** out) {
+    if (!out) B200_FAIL(B200_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B200_FAIL(B200_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) B200_FAIL(B200_ERR_ARG, "bad device ordinal");
+    b200_downsampler* d = new b200_downsampler();
+    d->device = device;
+    CUDA_SET_DEVICE(device);
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&d->ev0));
+    CUDA_TRY(cudaEventCreate(&d->ev1));
+    CUDA_TRY(d->d_small.reserve(16));
+    CUDA_TRY(d->h_small.reserve(16));
+    *out = d;
+    return B200_OK;
+}
+int32_t b200_downsampler_destroy(b200_downsampler* d) {
+    if (!d) return B200_OK;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    d->d_in.release(); d->d_out.release(); d->d_cmp.release(); d->k_in.release(); d->k_out.release(); d->k_uniq.release();
+    d->v_in.release(); d->v_out.release(); d->run_cnt.release(); d->run_off.release(); d->d_small.release(); d->d_cnt.release();
+    d->d_cnt_cmp.release(); d->keep.release(); d->cub_tmp.release(); d->h_stage.release(); d->h_small.release();
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    return B200_OK;
+}
+/* pcl::VoxelGrid::filter (setLeafSize(leaf, leaf, leaf), setMinimumPointsNumberPerVoxel(min_points)).  Records are
+ * x, y, z[, intensity] floats at stride_bytes (>= 16: the 4th float is averaged too).  out_xyzi: 4 floats per voxel in
+ * ascending leaf-index order, out_count: points per voxel (either may be NULL); *n_out = number of voxels. */
+int32_t b200_voxel_downsample(b200_downsampler* d, const float* xyzi, int64_t n, int64_t stride, float leaf, int32_t min_points, float* out_xyzi,
+                              int32_t* out_count, int64_t max_out, int64_t* n_out) {
+    if (!d || !xyzi || n < 1 || stride < 12 || !(leaf > 0.f) || n > (int64_t)0x7fffff00) B200_FAIL(B200_ERR_ARG, "bad argument");
+    CUDA_SET_DEVICE(d->device);
+    CUDA_TRY(d->h_stage.reserve(n));
+    CUDA_TRY(d->d_in.reserve(n));
+    const char* src = (const char*)xyzi;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = (const float*)(src + i * stride);
+        d->h_stage.p[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 0.0f);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d->d_in.p, d->h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, d->stream));
+    int32_t rc = downsample_run(d, n, leaf, min_points);
+    if (rc) return rc;
+    if (n_out) *n_out = d->n_out;
+    const int64_t m = std::min<int64_t>(d->n_out, max_out);
+    if (m > 0 && out_xyzi) CUDA_TRY(cudaMemcpyAsync(out_xyzi, d->d_cmp.p, m * sizeof(float4), cudaMemcpyDeviceToHost, d->stream));
+    if (m > 0 && out_count) CUDA_TRY(cudaMemcpyAsync(out_count, d->d_cnt_cmp.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return B200_OK;
+}
+/* device view of the last result: float4 (x, y, z, intensity) per voxel - feeds b200_iekf_update_device without a host trip */
+const void* b200_downsampler_device_points(b200_downsampler* d, int64_t* n) {
+    if (!d) return nullptr;
+    if (n) *n = d->n_out;
+    return d->d_cmp.p;
+}
+float b200_downsampler_last_ms(b200_downsampler* d) { return d ? d->last_ms : 0.f; }
+
+/* ---- map builder ---- */
+int32_t b200_mapbuild_create(float leaf, uint64_t capacity_voxels, int32_t device, b200_mapbuild** out) {
+    if (!out) B200_FAIL(B200_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) B200_FAIL(B200_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) B200_FAIL(B200_ERR_ARG, "bad device ordinal");
+    b200_mapbuild* h = new b200_mapbuild();
+    int32_t rc = h->b.init(leaf, capacity_voxels, device);
+    if (rc) { h->b.destroy(); delete h; return rc; }
+    *out = h;
+    return B200_OK;
+}
+int32_t b200_mapbuild_destroy(b200_mapbuild* h) {
+    if (!h) return B200_OK;
+    h->b.destroy();
+    delete h;
+    return B200_OK;
+}
+/* one keyframe: records x, y, z, intensity at stride_bytes (frames/<i>.pcd, pcl::PointXYZI), pose7 = x y z qw qx qy qz
+ * (one line of poses.txt).  Asynchronous: returns once the copy and the kernel are queued. */
+int32_t b200_mapbuild_add_keyframe(b200_mapbuild* h, const float* xyzi, int64_t n, int64_t stride, const double* pose7) {
+    if (!h || !xyzi || !pose7 || n < 1 || stride < 12) B200_FAIL(B200_ERR_ARG, "bad argument");
+    vox::Builder& b = h->b;
+    CUDA_SET_DEVICE(b.device);
+    CUDA_TRY(cudaStreamSynchronize(b.stream));  // the staging buffer is reused
+    CUDA_TRY(b.h_stage.reserve(n));
+    CUDA_TRY(b.d_pts.reserve(n));
+    const char* src = (const char*)xyzi;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = (const float*)(src + i * stride);
+        b.h_stage.p[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 0.0f);
+    }
+    CUDA_TRY(cudaMemcpyAsync(b.d_pts.p, b.h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, b.stream));
+    return b.add_device(b.d_pts.p, n, pose7);
+}
+/* same with the keyframe already on the device as float4 (x, y, z, intensity) */
+int32_t b200_mapbuild_add_keyframe_device(b200_mapbuild* h, const void* d_xyzi_float4, int64_t n, const double* pose7) {
+    if (!h || !d_xyzi_float4 || !pose7 || n < 1) B200_FAIL(B200_ERR_ARG, "bad argument");
+    return h->b.add_device((const float4*)d_xyzi_float4, n, pose7);
+}
+/* waits for the queued keyframes; number of voxels held by this rank */
+int64_t b200_mapbuild_num_voxels(b200_mapbuild* h) {
+    if (!h) return 0;
+    if (h->b.check() < 0) return -1;
+    return (int64_t)h->b.h_ctr.p[0];
+}
+/* Exchange of partial voxel sums between the ranks of `comm`: afterwards each voxel lives on exactly one rank
+ * (owner = hash(key) mod nranks) with the sums of all ranks.  Collective; no-op for a single rank. */
+int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h) {
+    if (!h) B200_FAIL(B200_ERR_ARG, "null handle");
+    if (!comm || comm->nranks < 2) return B200_OK;
+    using namespace vox;
+    Builder& b = h->b;
+    CUDA_SET_DEVICE(b.device);
+    int32_t rc = b.check();
+    if (rc) return rc;
+    const int R = comm->nranks;
+    const uint32_t T = b.tab.mask + 1;
+    const int64_t m = b.h_ctr.p[0];
+    CUDA_TRY(b.d_counts.reserve(2 * (size_t)R + (size_t)R * R));
+    CUDA_TRY(b.h_counts.reserve((size_t)R * R + 2 * R));
+    unsigned long long* d_cnt = b.d_counts.p;           // [R] my records per owner
+    unsigned long long* d_cursor = b.d_counts.p + R;    // [R]
+    unsigned long long* d_all = b.d_counts.p + 2 * R;   // [R][R] counts of every rank
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, R * sizeof(unsigned long long), b.stream));
+    k_owner_count<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab, R, d_cnt);
+    NCCL_TRY(comm, comm->AllGather(d_cnt, d_all, R, ncclUint64, comm->comm, b.stream));
+    CUDA_TRY(cudaMemcpyAsync(b.h_counts.p, d_all, (size_t)R * R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b.stream));
+    CUDA_TRY(cudaStreamSynchronize(b.stream));
+    const unsigned long long* all = b.h_counts.p;  // all[src * R + dst]
+    std::vector<unsigned long long> send_off(R + 1, 0), recv_off(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        send_off[r + 1] = send_off[r] + all[(size_t)comm->rank * R + r];
+        recv_off[r + 1] = recv_off[r] + all[(size_t)r * R + comm->rank];
+    }
+    CUDA_TRY(b.d_send.reserve(std::max<size_t>(send_off[R], 1)));
+    CUDA_TRY(b.d_recv.reserve(std::max<size_t>(recv_off[R], 1)));
+    unsigned long long* h_cur = b.h_counts.p + (size_t)R * R;
+    for (int r = 0; r < R; ++r) h_cur[r] = send_off[r];
+    CUDA_TRY(cudaMemcpyAsync(d_cursor, h_cur, R * sizeof(unsigned long long), cudaMemcpyHostToDevice, b.stream));
+    k_owner_scatter<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab, R, d_cursor, b.d_send.p);
+    CUDA_TRY(cudaEventRecord(b.ev0, b.stream));
+    NCCL_TRY(comm, comm->GroupStart());
+    for (int r = 0; r < R; ++r) {
+        const size_t ns = (size_t)(send_off[r + 1] - send_off[r]) * sizeof(Xfer), nr = (size_t)(recv_off[r + 1] - recv_off[r]) * sizeof(Xfer);
+        if (ns) NCCL_TRY(comm, comm->Send(b.d_send.p + send_off[r], ns, ncclChar, r, comm->comm, b.stream));
+        if (nr) NCCL_TRY(comm, comm->Recv(b.d_recv.p + recv_off[r], nr, ncclChar, r, comm->comm, b.stream));
+    }
+    NCCL_TRY(comm, comm->GroupEnd());
+    CUDA_TRY(cudaEventRecord(b.ev1, b.stream));
+    // rebuild the table from what this rank owns
+    k_table_clear<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab);
+    CUDA_TRY(cudaMemsetAsync(b.d_ctr, 0, 8 * sizeof(unsigned int), b.stream));
+    const int64_t mr = (int64_t)recv_off[R];
+    if (mr) k_merge_records<<<(unsigned)((mr + 255) / 256), 256, 0, b.stream>>>(b.d_recv.p, mr, b.tab, b.d_ctr, (unsigned int)b.capacity, b.d_ctr + 1);
+    LAUNCH_COUNT(4);
+    b.n_sorted = -1;
+    rc = b.check();
+    cudaEventElapsedTime(&b.last_ms, b.ev0, b.ev1);
+    (void)m;
+    return rc;
+}
+float b200_mapbuild_last_exchange_ms(b200_mapbuild* h) { return h ? h->b.last_ms : 0.f; }
+/* Centroids of the voxels this rank holds, ascending voxel order (z, then y, then x cell = VoxelGrid's leaf order):
+ * out_xyzi 4 floats per voxel, out_count points per voxel (may be NULL); returns the number of voxels (<= max written). */
+int64_t b200_mapbuild_extract(b200_mapbuild* h, float* out_xyzi, int32_t* out_count, int64_t max_out) {
+    if (!h) return -1;
+    vox::Builder& b = h->b;
+    if (cudaSetDevice(b.device) != cudaSuccess) return -1;
+    if (b.n_sorted < 0 && b.sort_slots() != B200_OK) return -1;
+    const int64_t m = b.n_sorted;
+    const int64_t w = std::min<int64_t>(m, max_out);
+    if (w > 0 && out_xyzi) {
+        if (b.d_out.reserve(m) != cudaSuccess || b.d_cnt.reserve(m) != cudaSuccess) return -1;
+        vox::k_extract<<<(unsigned)((m + 255) / 256), 256, 0, b.stream>>>(b.tab, b.d_slots2.p, m, b.d_out.p, b.d_cnt.p);
+        LAUNCH_COUNT(1);
+        cudaMemcpyAsync(out_xyzi, b.d_out.p, w * sizeof(float4), cudaMemcpyDeviceToHost, b.stream);
+        if (out_count) cudaMemcpyAsync(out_count, b.d_cnt.p, w * sizeof(int32_t), cudaMemcpyDeviceToHost, b.stream);
+        if (cudaStreamSynchronize(b.stream) != cudaSuccess) return -1;
+    }
+    return m;
+}
+
+}  // extern "C"

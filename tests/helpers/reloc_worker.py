@@ -59,6 +59,36 @@ def main():
         res = dict(best=int(best), score=float(score), expect=int(np.argmax(full)), expect_score=float(full.max()), world=world,
                    same_on_all_ranks=bool((tmin == tmax).all().item()), voxels=int(nvox), ms=float(ms), slice=[b, e])
         comm.close()
+    if mode == "nccl":
+        # construct_full_map over the ranks: contiguous keyframe blocks, exchange of partial sums, disjoint ownership
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_gpu_voxel import make_frames
+        frames, poses = make_frames(synth, k=9, n=4000)
+        fb, fe = api.shard_range(len(frames), world, rank)
+        ident2 = [api.Communicator.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident2, src=0)
+        comm2 = api.Communicator(world, rank, ident2[0], device=local)
+        b = api.FullMapBuilder(leaf=0.1, capacity_voxels=400_000, device=local)
+        for f, p in zip(frames[fb:fe], poses[fb:fe]):
+            b.add_keyframe(f, p)
+        b.merge(comm2)
+        c, n = b.extract()
+        single = api.FullMapBuilder(leaf=0.1, capacity_voxels=400_000, device=local)
+        for f, p in zip(frames, poses):
+            single.add_keyframe(f, p)
+        cs, ns = single.extract()
+        tot = torch.tensor([len(c), int(n.sum())], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot)
+        # every voxel this rank owns must equal the single-GPU voxel with the same centroid
+        key = lambda a: np.floor(a[:, :3] / np.float32(0.1)).astype(np.int64)
+        lut = {tuple(k): i for i, k in enumerate(key(cs))}
+        idx = np.array([lut.get(tuple(k), -1) for k in key(c)])
+        ok = bool((idx >= 0).all() and np.array_equal(ns[idx], n) and np.abs(cs[idx] - c).max() < 1e-6)
+        okt = torch.tensor([int(ok)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        res.update(fullmap_voxels=int(tot[0]), fullmap_points=int(tot[1]), single_voxels=len(cs), single_points=int(ns.sum()),
+                   fullmap_match=bool(okt.item()), exchange_ms=b.exchange_ms())
+        comm2.close()
     if rank == 0:
         json.dump(res, open(out_path, "w"))
     dist.barrier()

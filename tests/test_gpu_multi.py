@@ -34,3 +34,6 @@ def test_sharded_reloc_matches_single_gpu(tmp_path, world):
     r = json.load(open(out))
     assert r["same_on_all_ranks"]
     assert r["best"] == r["expect"] and r["score"] == r["expect_score"]
+    # sharded construct_full_map: same voxels, counts and centroids as one GPU, each voxel on exactly one rank
+    assert r["fullmap_voxels"] == r["single_voxels"] and r["fullmap_points"] == r["single_points"]
+    assert r["fullmap_match"]
