@@ -25,6 +25,8 @@ ndt        configs[1]: pclomp NDT of the 20k-point scan against a 10M-point prio
 reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicated 10M-point map, hypotheses sharded
            over the N ranks (strong scaling: 4096 in total), NCCL allreduce-argmin; hypotheses/s = 4096 / max-over-ranks
            device time, the winner checked against the oracle's argmax at N=1.
+fullmap    configs[4]: construct_full_map - keyframes x 100k points merged into a 0.1 m voxel map, keyframes split over the
+           ranks, partial voxel sums exchanged over NCCL; keyframes/s (--fullmap-frames, default 320; 10000 = full).
 sequence   configs[2]: sliding-map odometry (update + MapIncremental per scan) over --seq-scans scans (default 120;
            1000 is the full configuration and takes ~1 min of host-side ray casting).
 Skip them with --no-ndt / --seq-scans 0 (they add ~40 s of synthetic-data generation).
@@ -167,16 +169,12 @@ def ndt_cpu(cfg, poses, budget_s=20.0, want_build=True):
                 score_s=t_sc, score_n=len(sel), score_sel=sel, scores=sc, deriv=(s, g, H))
 
 
-def ndt_legs(args, rank, local_rank, world, api, synth, torch):
+def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
     """configs[1] (single-GPU NDT) on rank 0 and configs[3] (sharded relocalization) on all ranks."""
     import ctypes
     dist = torch.distributed if world > 1 else None
     cfg = synth.config2(N_PRIOR, N_SCAN) if rank == 0 else None
-    comm = None
     if world > 1:
-        ident = [api.Communicator.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        comm = api.Communicator(world, rank, ident[0], device=local_rank)
         small = [dict(scan=cfg["scan"], p_true=cfg["p_true"], p_guess=cfg["p_guess"], guess=cfg["guess"]) if rank == 0 else None]
         dist.broadcast_object_list(small, src=0)
         if rank != 0:
@@ -293,8 +291,6 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch):
             out["reloc"]["parity"] = {"scores_rel": float(np.abs(s1 - c["scores"]).max() / np.abs(c["scores"]).max()),
                                       "argmax_equal_on_sample": bool(int(np.argmax(s1)) == int(np.argmax(c["scores"])))}
     g.close()
-    if comm is not None:
-        comm.close()
     return out
 
 
@@ -382,6 +378,89 @@ def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
             "map_voxels": voxels, "map_points": points, "final_position_error_m": drift,
             "parity_vs_oracle": {"scans": len(par), "max_state_diff": max(par) if par else None,
                                  "note": "both filters fed the same priors; posterior and inserted points compared per scan"}}
+
+
+def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
+    """configs[4]: construct_full_map - keyframes (Avia-shaped, 100k points) moved by their poses and merged into a 0.1 m
+    voxel-grid map.  A pool of ray-cast keyframes along a loop in the synthetic hall is replayed on a grid of tiles
+    (copies of the hall side by side), so the map keeps growing; the keyframe list is cut into contiguous blocks, one per
+    rank (weak scaling would need N x frames: here the total is fixed = strong scaling)."""
+    n_frames, n_pool, n_pts = args.fullmap_frames, args.fullmap_pool, 100_000
+    world_geo = synth.make_world(synth.SEED, beams=True)
+    pool, pool_pose = [], []
+    for k in range(n_pool):
+        a = 2 * np.pi * k / n_pool
+        pos = np.array([30.0 * np.cos(a), 15.0 * np.sin(a), 1.2])
+        q = synth.quat_from_rotvec([0.0, 0.0, a + np.pi / 2])
+        pts = synth.raycast(pos, synth.quat_to_R(q), synth.avia_dirs(int(n_pts * 1.15), seed=900 + k), world_geo, seed=950 + k)[:n_pts]
+        inten = np.full((len(pts), 1), float(k), np.float32)
+        pool.append(np.ascontiguousarray(np.concatenate([pts, inten], 1)))
+        pool_pose.append(np.array([pos[0], pos[1], pos[2], q[3], q[0], q[1], q[2]]))
+
+    def pose_of(i):
+        t = i // n_pool
+        p = pool_pose[i % n_pool].copy()
+        p[0] += (t % 16) * 125.0
+        p[1] += (t // 16) * 85.0
+        return p
+
+    fb, fe = api.shard_range(n_frames, world, rank)
+    d_pool = [torch.from_numpy(f).cuda() for f in pool]
+    cap = int(min(1 << 29, max(4_000_000, 1.6e6 * (n_frames / n_pool + 1))))
+    times, times_e2e, vox_total, exch = [], [], 0, []
+    for rep in range(3):
+        for mode in ("device", "host"):
+            if mode == "host" and rep > 0:
+                continue
+            b = api.FullMapBuilder(leaf=0.1, capacity_voxels=cap, device=local_rank)
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            t0 = time.perf_counter()
+            for i in range(fb, fe):
+                if mode == "device":
+                    b.add_keyframe_device(d_pool[i % n_pool].data_ptr(), len(pool[i % n_pool]), pose_of(i))
+                else:
+                    b.add_keyframe(pool[i % n_pool], pose_of(i))
+            b.merge(comm)
+            nv = b.num_voxels()
+            dt = time.perf_counter() - t0
+            (times if mode == "device" else times_e2e).append(dt)
+            if mode == "device":
+                exch.append(b.exchange_ms())
+                vox_local = nv
+            b.close()
+    t = torch.tensor([min(times), min(times_e2e), float(vox_local)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tm = t.clone()
+        torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+        ts = t.clone()
+        torch.distributed.all_reduce(ts, op=torch.distributed.ReduceOp.SUM)
+        t_dev, t_e2e, vox_total = float(tm[0]), float(tm[1]), int(ts[2])
+    else:
+        t_dev, t_e2e, vox_total = float(t[0]), float(t[1]), int(t[2])
+    out = {"workload": f"configs[4] scaled: {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes replayed on tiles), leaf 0.1 m; "
+                       "10000 keyframes = full size (--fullmap-frames)",
+           "metric": "keyframes/s", "value": n_frames / t_dev, "unit": "keyframes/s", "points_per_s": n_frames * n_pts / t_dev, "n_gpus": world,
+           "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.mean(exch)) if exch else 0.0,
+           "timing": "wall clock around add_keyframe_device x frames + merge (NCCL exchange) + final sync, keyframes resident in HBM; max over ranks, best of 3",
+           "e2e": {"value": n_frames / t_e2e, "unit": "keyframes/s", "seconds": t_e2e, "h2d_bytes_per_keyframe": n_pts * 16,
+                   "note": "b200_mapbuild_add_keyframe with host buffers: pack + H2D per keyframe"}}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import binding as ob
+        ns = min(8, n_frames)
+        t0 = time.perf_counter()
+        c0, n0 = ob.full_map([pool[i % n_pool] for i in range(ns)], np.array([pose_of(i) for i in range(ns)]), 0.1)
+        dt = time.perf_counter() - t0
+        b = api.FullMapBuilder(leaf=0.1, capacity_voxels=4_000_000, device=local_rank)
+        for i in range(ns):
+            b.add_keyframe(pool[i % n_pool], pose_of(i))
+        c1, n1 = b.extract()
+        out["cpu_baseline"] = {"value": ns / dt, "unit": "keyframes/s", "cores": 1, "kind": "port", "sample": f"first {ns} keyframes (single thread, as pcl::VoxelGrid)"}
+        out["parity"] = {"voxels_equal": bool(len(c0) == len(c1) and np.array_equal(n0, n1)),
+                         "max_centroid_diff_m": float(np.abs(c0 - c1).max()) if len(c0) == len(c1) else None}
+        b.close()
+    return out
 
 
 def run_reference(args, rank, world):
@@ -510,8 +589,17 @@ def run_b200(args, rank, local_rank, world):
     kf.set_profiling(False)
 
     extra = {}
+    comm = None
+    if world > 1 and not (args.no_ndt and args.fullmap_frames <= 0):
+        ident = [api.Communicator.unique_id() if rank == 0 else None]
+        torch.distributed.broadcast_object_list(ident, src=0)
+        comm = api.Communicator(world, rank, ident[0], device=local_rank)
     if not args.no_ndt:
-        extra = ndt_legs(args, rank, local_rank, world, api, synth, torch)
+        extra = ndt_legs(args, rank, local_rank, world, api, synth, torch, comm)
+    if args.fullmap_frames > 0:
+        extra["fullmap"] = fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm)
+    if comm is not None:
+        comm.close()
 
     if args.seq_scans > 1 and rank == 0:
         extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans)
@@ -611,6 +699,8 @@ def main():
     ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] / configs[3] legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--seq-scans", type=int, default=120, help="configs[2] leg: scans in the sliding-map sequence (1000 = full; 0 = skip)")
+    ap.add_argument("--fullmap-frames", type=int, default=320, help="configs[4] leg: keyframes to merge (10000 = full; 0 = skip)")
+    ap.add_argument("--fullmap-pool", type=int, default=32, help="distinct ray-cast keyframes in the replay pool")
     ap.add_argument("--small", action="store_true", help="DEV ONLY: shrink the maps 10x (not a valid bench number)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
