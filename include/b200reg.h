@@ -159,6 +159,10 @@ int32_t b200_ndt_align(b200_ndt* ndt, const float* guess16, float* final16, b200
 int32_t b200_ndt_derivatives(b200_ndt* ndt, const double* p6, double* score, double* g6, double* H36);
 /* computeHessian (double path, ndt_omp_impl.hpp:499-560) */
 int32_t b200_ndt_hessian(b200_ndt* ndt, const double* p6, double* H36);
+/* pcl::Registration::getFitnessScore(max_range) (PCL; loop-closure gate at jueying_slam/src/mapOptmization.cpp:693,719): mean
+ * squared distance from the source, moved by T16 (column-major; NULL = final transformation of the last align), to its exact
+ * nearest target points; points farther than max_range (squared distance) are skipped; DBL_MAX when none is in range */
+int32_t b200_ndt_fitness_score(b200_ndt* ndt, const float* T16, double max_range, double* score, int64_t* n_in_range);
 /* calculateScore for h <= 65535 candidate poses (ndt_omp_impl.hpp:836-880) — global relocalization primitive */
 int32_t b200_ndt_score_batch(b200_ndt* ndt, const float* poses16, int64_t h, double* scores);
 /* align() from h independent initial guesses in one batch (relocalization with refinement): finals16 h x 16, results[h] */

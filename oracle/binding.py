@@ -100,6 +100,8 @@ def lib():
         L.orc_ndt_align.restype = i32
         L.orc_ndt_align.argtypes = [vp, vp, vp, C.POINTER(NdtResult)]
         L.orc_ndt_score_batch.argtypes = [vp, vp, i64, vp]
+        L.orc_ndt_fitness.restype = C.c_double
+        L.orc_ndt_fitness.argtypes = [vp, vp, C.c_double, vp]
         L.orc_ndt_nbhd_total.restype = i64
         L.orc_ndt_nbhd_total.argtypes = [vp, vp]
         L.orc_voxel_grid.restype = i64
@@ -312,6 +314,12 @@ class OracleNdt:
     def nbhd_total(self, p6):
         p6 = np.ascontiguousarray(p6, dtype=np.float64)
         return lib().orc_ndt_nbhd_total(self.h, _p(p6))
+
+    def fitness(self, T, max_range=1.7976931348623157e308):
+        t = np.ascontiguousarray(np.asarray(T, dtype=np.float32).T)
+        nr = C.c_int64(0)
+        s = lib().orc_ndt_fitness(self.h, _p(t), max_range, C.byref(nr))
+        return s, nr.value
 
 
 def euler_from_matrix(M):

@@ -39,7 +39,7 @@ struct Ndt {
     float leaf = 1.0f, inv_leaf = 1.0f;
     int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0}, divb_mul[3] = {0, 0, 0};
     std::map<size_t, Leaf> leaves;
-    std::vector<F3> source;
+    std::vector<F3> source, target;
     // gaussian constants
     double d1 = 0, d2 = 0, d3 = 0;
     // angle tables
@@ -59,6 +59,11 @@ struct Ndt {
 
     int64_t set_target(const float* xyz, int64_t n, int64_t stride) {  // applyFilter
         leaves.clear();
+        target.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const float* p = (const float*)((const char*)xyz + i * stride);
+            target[i] = F3{p[0], p[1], p[2]};
+        }
         leaf = prm.resolution;
         inv_leaf = 1.0f / leaf;  // setLeafSize: inverse_leaf_size_ = Array4f::Ones()/leaf_size_
         float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
@@ -641,6 +646,35 @@ void orc_ndt_score_batch(orc_ndt* h, const float* poses, int64_t np, double* sco
         Ndt::transform_cloud(h->N.source, M, trans);
         scores[k] = h->N.calculate_score(trans);
     }
+}
+/* pcl::Registration::getFitnessScore(max_range) (PCL, third party): transformPointCloud(source, final_transformation),
+ * kd-tree nearestKSearch(1) per point = exact nearest neighbour (brute force here), float squared distances (FLANN
+ * L2_Simple: sequential float accumulation) summed in double over the points with dist <= max_range, divided by their
+ * number; DBL_MAX when there is none. */
+double orc_ndt_fitness(orc_ndt* h, const float* T16_colmajor, double max_range, int64_t* n_in_range) {
+    float M[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) M[i * 4 + j] = T16_colmajor[j * 4 + i];
+    std::vector<F3> trans;
+    Ndt::transform_cloud(h->N.source, M, trans);
+    const size_t n = trans.size();
+    std::vector<float> best(n);
+#pragma omp parallel for num_threads(h->N.nthreads) schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        float b = std::numeric_limits<float>::max();
+        for (const F3& t : h->N.target) {
+            float dx = trans[i].x - t.x, dy = trans[i].y - t.y, dz = trans[i].z - t.z;
+            float d = (dx * dx + dy * dy) + dz * dz;
+            if (d < b) b = d;
+        }
+        best[i] = b;
+    }
+    double sum = 0;
+    int64_t nr = 0;
+    for (size_t i = 0; i < n; ++i)
+        if ((double)best[i] <= max_range && best[i] < std::numeric_limits<float>::max()) { sum += (double)best[i]; ++nr; }
+    if (n_in_range) *n_in_range = nr;
+    return nr > 0 ? sum / (double)nr : std::numeric_limits<double>::max();
 }
 int64_t orc_ndt_nbhd_total(orc_ndt* h, const double* p6) {
     float M[16];

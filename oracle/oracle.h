@@ -127,7 +127,9 @@ void orc_ndt_hessian(orc_ndt* h, const double* p6, double* H36);
 int32_t orc_ndt_align(orc_ndt* h, const float* guess16_colmajor, float* final16_colmajor, orc_ndt_result* r);
 /* calculateScore for h poses (col-major float 4x4 each) */
 void orc_ndt_score_batch(orc_ndt* h, const float* poses16, int64_t nposes, double* scores);
-int64_t orc_ndt_nbhd_total(orc_ndt* h, const double* p6); /* sum of neighbourhood sizes (roofline bytes) */
+int64_t orc_ndt_nbhd_total(orc_ndt* h, const double* p6);
+/* pcl::Registration::getFitnessScore(max_range) with the source moved by T (col-major 4x4) */
+double orc_ndt_fitness(orc_ndt* h, const float* T16_colmajor, double max_range, int64_t* n_in_range); /* sum of neighbourhood sizes (roofline bytes) */
 void orc_euler_from_matrix(const float* m16_colmajor, float* rpy);
 void orc_matrix_from_pose(const double* p6, float* m16_colmajor);
 

@@ -129,6 +129,7 @@ def lib():
         L.b200_ndt_last_ms.restype = C.c_float
         L.b200_ndt_last_ms.argtypes = [vp]
         L.b200_ndt_last_launches.argtypes = [vp]
+        L.b200_ndt_fitness_score.argtypes = [vp, vp, C.c_double, vp, vp]
     L.b200_downsampler_create.argtypes = [i32, C.POINTER(vp)]
     L.b200_downsampler_destroy.argtypes = [vp]
     L.b200_voxel_downsample.argtypes = [vp, vp, i64, i64, C.c_float, i32, vp, vp, i64, vp]
@@ -423,6 +424,14 @@ class NormalDistributionsTransform:
 
     def getFinalTransformation(self):
         return self._final
+
+    def getFitnessScore(self, max_range=1.7976931348623157e308, T=None):
+        """pcl::Registration::getFitnessScore: mean squared exact-NN distance of the aligned source to the target."""
+        s, nr = C.c_double(0), C.c_int64(0)
+        t = None if T is None else np.ascontiguousarray(np.asarray(T, dtype=np.float32).T)
+        _check(lib().b200_ndt_fitness_score(self._handle(), None if t is None else _p(t), max_range, C.byref(s), C.byref(nr)))
+        self.fitness_in_range = nr.value
+        return s.value
 
     def getFinalNumIteration(self):
         return self.result.iters

@@ -718,6 +718,106 @@ __global__ void k_best_index(const double* __restrict__ scores, int64_t h, int64
     if ((threadIdx.x & 31) == 0 && b != ~0ull) atomicMin(idx, b);
 }
 
+// ------------------------------------------------------------------ getFitnessScore: exact nearest neighbour in the target
+// pcl::Registration::getFitnessScore(max_range) (PCL, third party; used by the loop-closure gate mapOptmization.cpp:693,719):
+// mean over the transformed source points of the squared distance to their nearest target point (kd-tree nearestKSearch(1)
+// = exact), points farther than max_range skipped.  The target is already sorted by voxel for the NDT build; a second
+// dense table maps every non-empty cell to its run of points, and a warp searches cube shells of growing radius around
+// the query until no unexplored cell can hold a closer point.
+__global__ void k_ndt_cell_runs(const uint32_t* __restrict__ uniq, const int32_t* __restrict__ nruns, uint32_t sentinel, int32_t* __restrict__ cell2run) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    if (uniq[r] != sentinel) cell2run[uniq[r]] = r;
+}
+
+struct FitView {
+    const float4* pts;       // target points sorted by cell
+    const int32_t* cell2run;
+    const int32_t* run_off;
+    const int32_t* run_cnt;
+    int min_b[3], div_b[3];
+    float leaf, inv_leaf;
+};
+
+__global__ void __launch_bounds__(256) k_ndt_fitness(FitView f, const float4* __restrict__ src, int n, const float* __restrict__ M12g, double* __restrict__ d2_out) {
+    __shared__ float M[12];
+    if (threadIdx.x < 12) M[threadIdx.x] = M12g[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= n) return;
+    const float4 p = __ldg(src + q);
+    float x, y, z;
+    xform(M, p.x, p.y, p.z, x, y, z);
+    float best = 3.402823466e+38f;
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        // start cell, clamped into the grid
+        int c[3] = {(int)floorf(x * f.inv_leaf) - f.min_b[0], (int)floorf(y * f.inv_leaf) - f.min_b[1], (int)floorf(z * f.inv_leaf) - f.min_b[2]};
+        const float qv[3] = {x, y, z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c[a] = min(max(c[a], 0), f.div_b[a] - 1);
+        const int rmax = max(max(f.div_b[0], f.div_b[1]), f.div_b[2]);
+        for (int r = 0; r <= rmax; ++r) {
+            // explored box [lo, hi] in cells; shell = box(r) minus box(r-1)
+            int lo[3], hi[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = max(c[a] - r, 0); hi[a] = min(c[a] + r, f.div_b[a] - 1); }
+            const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+            const int ncell = nx * ny * nz;
+            for (int i = 0; i < ncell; ++i) {  // warp-uniform walk over the box, shell cells only
+                const int ix = lo[0] + i % nx, iy = lo[1] + (i / nx) % ny, iz = lo[2] + i / (nx * ny);
+                if (r > 0 && abs(ix - c[0]) < r && abs(iy - c[1]) < r && abs(iz - c[2]) < r) continue;  // inner cells were done
+                const int run = __ldg(f.cell2run + ((size_t)iz * f.div_b[1] + iy) * f.div_b[0] + ix);
+                if (run < 0) continue;
+                const int off = __ldg(f.run_off + run), cnt = __ldg(f.run_cnt + run);
+                for (int j = lane; j < cnt; j += 32) {
+                    const float4 t = __ldg(f.pts + off + j);
+                    const float dx = x - t.x, dy = y - t.y, dz = z - t.z;
+                    const float d2 = (dx * dx + dy * dy) + dz * dz;  // FLANN L2_Simple: sequential float accumulation
+                    best = fminf(best, d2);
+                }
+            }
+            float wb = best;
+            for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+            best = wb;
+            // lower bound on the distance to anything outside the explored box: nearest face that is not a grid face
+            float lb = 3.402823466e+38f;
+            bool all_grid = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (lo[a] > 0) { all_grid = false; lb = fminf(lb, qv[a] - (float)(lo[a] + f.min_b[a]) * f.leaf); }
+                if (hi[a] < f.div_b[a] - 1) { all_grid = false; lb = fminf(lb, (float)(hi[a] + 1 + f.min_b[a]) * f.leaf - qv[a]); }
+            }
+            if (all_grid) break;
+            // a small safety margin absorbs the rounding of the face coordinates
+            if (lb > 0.f && best <= (lb - 1e-4f * f.leaf) * (lb - 1e-4f * f.leaf)) break;
+        }
+    }
+    if (lane == 0) d2_out[q] = (double)best;
+}
+
+__global__ void k_ndt_fitness_reduce(const double* __restrict__ d2, int n, double max_range, double* __restrict__ out /*sum, count*/) {
+    // single block, fixed order: deterministic
+    __shared__ double ssum[256];
+    __shared__ double scnt[256];
+    double s = 0.0, c = 0.0;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    for (int i = b; i < e; ++i) {
+        const double v = d2[i];
+        if (v <= max_range && v < 3.0e38) { s += v; c += 1.0; }
+    }
+    ssum[threadIdx.x] = s;
+    scnt[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double S = 0.0, C = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { S += ssum[i]; C += scnt[i]; }
+        out[0] = S;
+        out[1] = C;
+    }
+}
+
 // ------------------------------------------------------------------ host object
 struct Ndt {
     b200_ndt_params prm;
@@ -729,7 +829,13 @@ struct Ndt {
     GridDims gd{};
     int64_t ncells = 0;
     int nruns = 0, n_valid = 0;
-    DevBuf<float4> d_tgt, d_src, d_src_raw;
+    DevBuf<float4> d_tgt, d_src, d_src_raw, d_tgt_sorted;
+    DevBuf<uint32_t> s_keys_in, s_keys_out;
+    DevBuf<int32_t> s_vals_in, s_vals_out, d_cell2run;
+    DevBuf<uint8_t> s_tmp;
+    DevBuf<double> d_fit;
+    bool have_fitness_index = false;
+    int64_t n_tgt = 0;
     DevBuf<int32_t> d_cell2leaf;
     DevBuf<LeafF> d_leafF;
     DevBuf<LeafD> d_leafD;
@@ -765,6 +871,7 @@ struct Ndt {
     int32_t set_source(const float* xyz, int64_t n, int64_t stride);
     int32_t run(int h, const float* d_guesses, const double* d_p, int phase);
     int32_t score_batch_device(const float* d_poses16, int64_t h, double* d_out);
+    int32_t fitness(const float* T16_colmajor, double max_range, double* score, int64_t* nr);
 };
 
 int32_t Ndt::init(const b200_ndt_params* p, int dev) {
@@ -792,7 +899,8 @@ int32_t Ndt::init(const b200_ndt_params* p, int dev) {
 void Ndt::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    d_tgt.release(); d_src.release(); d_src_raw.release(); d_cell2leaf.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
+    d_tgt.release(); d_src.release(); d_src_raw.release(); d_tgt_sorted.release(); s_keys_in.release(); s_keys_out.release();
+    s_vals_in.release(); s_vals_out.release(); d_cell2run.release(); s_tmp.release(); d_fit.release(); d_cell2leaf.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
     d_npts.release(); d_vals_in.release(); d_vals_out.release(); d_run_cnt.release(); d_run_off.release(); d_small.release();
     d_keys_in.release(); d_keys_out.release(); d_uniq.release(); d_valid.release(); cub_tmp.release();
     h_stage.release(); h_small.release(); d_ctl.release(); d_partials.release(); d_p_in.release(); d_scores.release(); d_poses.release();
@@ -853,6 +961,8 @@ int32_t Ndt::set_target(const float* xyz, int64_t n, int64_t stride) {
 
 int32_t Ndt::build_target(int64_t n) {
     have_target = false;
+    have_fitness_index = false;
+    n_tgt = n;
     CUDA_TRY(cudaEventRecord(ev0, stream));
     int* mm = d_small.p;
     k_ndt_minmax_init<<<1, 32, 0, stream>>>(mm);
@@ -931,14 +1041,14 @@ int32_t Ndt::set_source(const float* xyz, int64_t n, int64_t stride) {
     int32_t rc = upload(xyz, n, stride, d_src_raw);
     if (rc) return rc;
     CUDA_TRY(d_src.reserve((size_t)n));
-    CUDA_TRY(d_keys_in.reserve(n)); CUDA_TRY(d_keys_out.reserve(n)); CUDA_TRY(d_vals_in.reserve(n)); CUDA_TRY(d_vals_out.reserve(n));
+    CUDA_TRY(s_keys_in.reserve(n)); CUDA_TRY(s_keys_out.reserve(n)); CUDA_TRY(s_vals_in.reserve(n)); CUDA_TRY(s_vals_out.reserve(n));
     const int nb = (int)((n + 255) / 256);
-    k_ndt_source_keys<<<nb, 256, 0, stream>>>(d_src_raw.p, (int)n, 1.0f / prm.resolution, d_keys_in.p, d_vals_in.p);
+    k_ndt_source_keys<<<nb, 256, 0, stream>>>(d_src_raw.p, (int)n, 1.0f / prm.resolution, s_keys_in.p, s_vals_in.p);
     size_t tmp = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys_in.p, d_keys_out.p, d_vals_in.p, d_vals_out.p, (int)n, 0, 32, stream));
-    CUDA_TRY(cub_tmp.reserve(tmp));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, d_keys_in.p, d_keys_out.p, d_vals_in.p, d_vals_out.p, (int)n, 0, 32, stream));
-    k_ndt_gather<<<nb, 256, 0, stream>>>(d_src_raw.p, d_vals_out.p, (int)n, d_src.p);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, s_keys_in.p, s_keys_out.p, s_vals_in.p, s_vals_out.p, (int)n, 0, 32, stream));
+    CUDA_TRY(s_tmp.reserve(tmp));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(s_tmp.p, tmp, s_keys_in.p, s_keys_out.p, s_vals_in.p, s_vals_out.p, (int)n, 0, 32, stream));
+    k_ndt_gather<<<nb, 256, 0, stream>>>(d_src_raw.p, s_vals_out.p, (int)n, d_src.p);
     LAUNCH_COUNT(2);
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaGetLastError());
@@ -1008,6 +1118,43 @@ int32_t Ndt::score_batch_device(const float* d_poses16, int64_t h, double* d_out
     k_ndt_score_finish<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_partials.p, nch, h, n_src, d_out);
     LAUNCH_COUNT(2);
     CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+}
+
+int32_t Ndt::fitness(const float* T16, double max_range, double* score, int64_t* nr) {
+    if (!have_target) B200_FAIL(B200_ERR_ARG, "no target set");
+    if (n_src < 1) B200_FAIL(B200_ERR_ARG, "no source set");
+    if (!have_fitness_index) {  // built on first use: target points in cell order + cell -> run table
+        CUDA_TRY(d_tgt_sorted.reserve((size_t)n_tgt));
+        CUDA_TRY(d_cell2run.reserve((size_t)ncells));
+        CUDA_TRY(cudaMemsetAsync(d_cell2run.p, 0xFF, (size_t)ncells * sizeof(int32_t), stream));
+        k_ndt_gather<<<(unsigned)((n_tgt + 255) / 256), 256, 0, stream>>>(d_tgt.p, d_vals_out.p, (int)n_tgt, d_tgt_sorted.p);
+        k_ndt_cell_runs<<<(nruns + 255) / 256, 256, 0, stream>>>(d_uniq.p, d_small.p + 8, (uint32_t)ncells, d_cell2run.p);
+        LAUNCH_COUNT(2);
+        have_fitness_index = true;
+    }
+    CUDA_TRY(d_fit.reserve((size_t)n_src + 2));
+    CUDA_TRY(d_poses.reserve(16)); CUDA_TRY(h_poses.reserve(16)); CUDA_TRY(h_scores.reserve(8));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) h_poses.p[i * 4 + j] = T16[j * 4 + i];
+    CUDA_TRY(cudaMemcpyAsync(d_poses.p, h_poses.p, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    FitView f;
+    f.pts = d_tgt_sorted.p; f.cell2run = d_cell2run.p; f.run_off = d_run_off.p; f.run_cnt = d_run_cnt.p;
+    for (int k = 0; k < 3; ++k) { f.min_b[k] = gd.min_b[k]; f.div_b[k] = gd.div_b[k]; }
+    f.leaf = prm.resolution; f.inv_leaf = gd.inv_leaf;
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    // the fitness is defined on the source in its original order; any order gives the same set of distances
+    k_ndt_fitness<<<(unsigned)(((size_t)n_src * 32 + 255) / 256), 256, 0, stream>>>(f, d_src.p, n_src, d_poses.p, d_fit.p);
+    k_ndt_fitness_reduce<<<1, 256, 0, stream>>>(d_fit.p, n_src, max_range, d_fit.p + n_src);
+    LAUNCH_COUNT(2);
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaMemcpyAsync(h_scores.p, d_fit.p + n_src, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&last_ms, ev0, ev1);
+    const double S = h_scores.p[0], Cn = h_scores.p[1];
+    if (nr) *nr = (int64_t)Cn;
+    if (score) *score = Cn > 0 ? S / Cn : 1.7976931348623157e308;  // PCL returns DBL_MAX when nothing is in range
     return B200_OK;
 }
 
@@ -1204,6 +1351,23 @@ int32_t b200_ndt_score_batch(b200_ndt* n, const float* poses16, int64_t h, doubl
     cudaEventElapsedTime(&k.last_ms, k.ev0, k.ev1);
     memcpy(scores, k.h_scores.p, (size_t)h * sizeof(double));
     return B200_OK;
+}
+
+/* pcl::Registration::getFitnessScore(max_range): mean squared distance from the source, moved by T16 (column-major 4x4;
+ * NULL = the final transformation of the last align), to its exact nearest neighbours in the target */
+int32_t b200_ndt_fitness_score(b200_ndt* n, const float* T16, double max_range, double* score, int64_t* n_in_range) {
+    if (!n || !score) B200_FAIL(B200_ERR_ARG, "null argument");
+    Ndt& k = n->k;
+    CUDA_SET_DEVICE(k.device);
+    float T[16];
+    if (T16) memcpy(T, T16, sizeof T);
+    else {
+        if (!k.h_ctl.p) B200_FAIL(B200_ERR_ARG, "no alignment has been run");
+        const ndt::Ctl& c = k.h_ctl.p[0];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) T[j * 4 + i] = c.final_T[i * 4 + j];
+    }
+    return k.fitness(T, max_range, score, n_in_range);
 }
 
 /* roofline bookkeeping: number of (point, voxel) pairs one evaluation at pose p6 touches */

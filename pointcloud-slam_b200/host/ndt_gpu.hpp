@@ -60,6 +60,13 @@ class NormalDistributionsTransform {
     double getTransformationProbability() const { return result_.trans_probability; }   // ndt_omp.h:200-204
     int getFinalNumIteration() const { return result_.iters; }                            // :226-230
     const double* getHessian() const { return result_.hessian; }
+    /// pcl::Registration::getFitnessScore(max_range): mean squared nearest-neighbour distance after the last align
+    double getFitnessScore(double max_range = 1.7976931348623157e308) {
+        double s = 0;
+        int64_t nr = 0;
+        check(b200_ndt_fitness_score(ndt_, final_, max_range, &s, &nr), "b200_ndt_fitness_score");
+        return s;
+    }
 
     /// calculateScore (ndt_omp_impl.hpp:836-880) for h candidate poses (h x 16 floats, column-major)
     void calculateScore(const float* poses16, int64_t h, double* scores) {

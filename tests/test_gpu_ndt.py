@@ -162,3 +162,22 @@ def test_ndt_errors(api, ndt_small):
     g2.setInputTarget(big)
     with pytest.raises(api.B200Error):
         g2.numVoxels()                          # leaf indices would overflow (applyFilter's guard)
+
+
+def test_fitness_score_exact_nn(oracle, api, synth, ndt_small):
+    """getFitnessScore = mean squared exact nearest-neighbour distance (PCL kd-tree semantics), also for points that fall
+    outside the map and for a max_range cut."""
+    cfg = dict(map=ndt_small["map"][:80_000], scan=ndt_small["scan"][:1500])
+    o, g = pair(oracle, api, cfg)
+    for d in ([0, 0, 0, 0, 0, 0], [0.4, -0.3, 0.1, 0.01, 0.02, 0.05], [30.0, 5.0, 2.0, 0, 0, 1.0], [150.0, 100.0, 20.0, 0, 0, 0]):
+        T = synth.pose_vec_to_matrix(ndt_small["p_true"] + np.array(d)).astype(np.float32)
+        s0, n0 = o.fitness(T)
+        s1 = g.getFitnessScore(T=T)
+        assert g.fitness_in_range == n0
+        assert abs(s1 - s0) <= 1e-12 * abs(s0)
+        s0, n0 = o.fitness(T, max_range=0.01)
+        s1 = g.getFitnessScore(max_range=0.01, T=T)
+        assert g.fitness_in_range == n0 and (abs(s1 - s0) <= 1e-12 * abs(s0) or (n0 == 0 and s1 == s0))
+    rc0, T0, r0 = o.align(synth.pose_vec_to_matrix(ndt_small["p_true"]).astype(np.float32))
+    g.align(synth.pose_vec_to_matrix(ndt_small["p_true"]).astype(np.float32))
+    assert abs(g.getFitnessScore() - o.fitness(T0)[0]) <= 1e-6 * o.fitness(T0)[0]
