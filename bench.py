@@ -26,7 +26,7 @@ reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicate
            over the N ranks (strong scaling: 4096 in total), NCCL allreduce-argmin; hypotheses/s = 4096 / max-over-ranks
            device time, the winner checked against the oracle's argmax at N=1.
 fullmap    configs[4]: construct_full_map - keyframes x 100k points merged into a 0.1 m voxel map, keyframes split over the
-           ranks, partial voxel sums exchanged over NCCL; keyframes/s (--fullmap-frames, default 320; 10000 = full).
+           ranks, partial voxel sums exchanged over NCCL; keyframes/s (--fullmap-frames, default 1600; 10000 = full).
 sequence   configs[2]: sliding-map odometry (update + MapIncremental per scan) over --seq-scans scans (default 120;
            1000 is the full configuration and takes ~1 min of host-side ray casting).
 Skip them with --no-ndt / --seq-scans 0 (they add ~40 s of synthetic-data generation).
@@ -227,7 +227,7 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
         "e2e": {"value": len(poses) / (reloc_wall_ms * 1e-3), "unit": "hypotheses/s", "ms_per_batch": reloc_wall_ms,
                 "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": 32},
         "best": int(best), "best_score": float(score), "true_index": (16 * 32 + 16) * 4, "gpu_launches_per_batch": int(reloc_launches),
-        "collective": "2 x 8-byte ncclAllReduce (max of score key, min of index)" if world > 1 else "none (single GPU)",
+        "collective": "one ncclAllGather of 16 B per rank ((score key, index) winners), reduced identically on every rank" if world > 1 else "none (single GPU)",
         "workload": "configs[3]: 32x32x4 pose grid (1 m, 90 deg) vs 10M-pt prior map, calculateScore per hypothesis, map replicated per GPU",
         "l2": "flushed between timed batches"}
 
@@ -397,8 +397,10 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
         pool.append(np.ascontiguousarray(np.concatenate([pts, inten], 1)))
         pool_pose.append(np.array([pos[0], pos[1], pos[2], q[3], q[0], q[1], q[2]]))
 
+    reuse = args.fullmap_reuse   # keyframes per tile = pool x reuse: ~20 points per voxel, the density BASELINE.json quotes (1e9 pts -> 50M)
+
     def pose_of(i):
-        t = i // n_pool
+        t = i // (n_pool * reuse)
         p = pool_pose[i % n_pool].copy()
         p[0] += (t % 16) * 125.0
         p[1] += (t // 16) * 85.0
@@ -406,7 +408,7 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
 
     fb, fe = api.shard_range(n_frames, world, rank)
     d_pool = [torch.from_numpy(f).cuda() for f in pool]
-    cap = int(min(1 << 29, max(4_000_000, 1.6e6 * (n_frames / n_pool + 1))))
+    cap = int(min(1 << 29, max(4_000_000, 1.6e6 * (-(-n_frames // (n_pool * reuse)) // world + 2))))
     times, times_e2e, vox_total, exch = [], [], 0, []
     for rep in range(3):
         for mode in ("device", "host"):
@@ -439,7 +441,7 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
         t_dev, t_e2e, vox_total = float(tm[0]), float(tm[1]), int(ts[2])
     else:
         t_dev, t_e2e, vox_total = float(t[0]), float(t[1]), int(t[2])
-    out = {"workload": f"configs[4] scaled: {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes replayed on tiles), leaf 0.1 m; "
+    out = {"workload": f"configs[4] scaled: {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes, {reuse} passes per tile, tiles side by side), leaf 0.1 m; "
                        "10000 keyframes = full size (--fullmap-frames)",
            "metric": "keyframes/s", "value": n_frames / t_dev, "unit": "keyframes/s", "points_per_s": n_frames * n_pts / t_dev, "n_gpus": world,
            "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.mean(exch)) if exch else 0.0,
@@ -699,8 +701,9 @@ def main():
     ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] / configs[3] legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--seq-scans", type=int, default=120, help="configs[2] leg: scans in the sliding-map sequence (1000 = full; 0 = skip)")
-    ap.add_argument("--fullmap-frames", type=int, default=320, help="configs[4] leg: keyframes to merge (10000 = full; 0 = skip)")
+    ap.add_argument("--fullmap-frames", type=int, default=1600, help="configs[4] leg: keyframes to merge (10000 = full; 0 = skip)")
     ap.add_argument("--fullmap-pool", type=int, default=32, help="distinct ray-cast keyframes in the replay pool")
+    ap.add_argument("--fullmap-reuse", type=int, default=5, help="times the pool is replayed on one tile before moving to the next")
     ap.add_argument("--small", action="store_true", help="DEV ONLY: shrink the maps 10x (not a valid bench number)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()

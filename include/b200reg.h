@@ -184,8 +184,8 @@ int32_t b200_comm_destroy(b200_comm* comm);
 int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* ndt, const float* xyz, int64_t n, int64_t stride_bytes, int32_t root);
 /* Global relocalization.  Hypotheses h_begin..h_begin+h-1 of a global grid are scored on this rank with calculateScore;
  * the cost that is minimised is -score (the winner is the most likely pose).  Every rank receives the same global
- * winner through an allreduce-argmin: an 8-byte ncclAllReduce(max) on the order-preserving fp64 score key, then an
- * 8-byte ncclAllReduce(min) on the index among the rank(s) holding it (exact, ties to the lower index).
+ * winner through one collective: each rank's local winner travels as a 16-byte (order-preserving fp64 score key, index)
+ * pair in an ncclAllGather and every rank reduces the gathered pairs (exact, ties to the lower index).
  * comm may be NULL (single GPU).  best = -1 and B200_NO_EFFECTIVE_POINTS when no rank had a hypothesis. */
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t* best,
                           double* best_score, float* gpu_ms);

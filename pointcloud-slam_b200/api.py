@@ -546,24 +546,26 @@ def score_from_key(k: int) -> float:
     return struct.unpack("<d", struct.pack("<Q", u))[0]
 
 
-def argmin_protocol_host(scores, h_begin, all_reduce):
-    """Host mirror of b200_reloc_argmin's collective protocol (used by the CPU gloo test): all_reduce(tensor, op) reduces
-    an int64 tensor in place across ranks.  Step 1: max of the score key; step 2: min of the global index among the holders.
-    Keys are shifted into int64 order (xor 2^63) because gloo has no uint64."""
+def argmin_protocol_host(scores, h_begin, all_gather):
+    """Host mirror of b200_reloc_argmin's collective protocol (used by the CPU gloo test): every rank contributes its local
+    winner as an (order-preserving score key, global index) pair; all_gather(tensor[2]) returns the pairs of all ranks
+    ([R, 2] int64, keys shifted into int64 order by xor 2^63 because gloo has no uint64); the global winner is the pair
+    with the highest key, ties to the lowest index."""
     import torch
-    from torch.distributed import ReduceOp
     keys = [score_key(float(s)) for s in scores]
-    local = max(keys) if keys else 0
-    t = torch.tensor([local - (1 << 63)], dtype=torch.int64)
-    all_reduce(t, ReduceOp.MAX)
-    gkey = int(t[0]) + (1 << 63)
-    cand = min([h_begin + i for i, k in enumerate(keys) if k == gkey and gkey != 0], default=(1 << 62))
-    t = torch.tensor([cand], dtype=torch.int64)
-    all_reduce(t, ReduceOp.MIN)
-    idx = int(t[0])
-    if gkey == 0 or idx == (1 << 62):
+    lk, li = 0, (1 << 62)
+    for i, k in enumerate(keys):
+        if k > lk:
+            lk, li = k, h_begin + i
+    pairs = all_gather(torch.tensor([lk - (1 << 63), li], dtype=torch.int64))
+    best_k, best_i = 0, (1 << 62)
+    for kr, ir in pairs.tolist():
+        kr += (1 << 63)
+        if kr > best_k or (kr == best_k and kr != 0 and ir < best_i):
+            best_k, best_i = kr, ir
+    if best_k == 0 or best_i == (1 << 62):
         return -1, 0.0
-    return idx, score_from_key(gkey)
+    return best_i, score_from_key(best_k)
 
 
 def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicator | None = None, h_begin=0):

@@ -691,31 +691,25 @@ __device__ __forceinline__ unsigned long long dbl_key(double s) {
     unsigned long long u = (unsigned long long)__double_as_longlong(s);
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
-// best[0] = max over this rank's slice of the score key
-__global__ void k_best_score(const double* __restrict__ scores, int64_t h, unsigned long long* best) {
-    unsigned long long b = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h; i += (int64_t)gridDim.x * blockDim.x) {
+// This rank's winner: pair[0] = highest score key of the slice, pair[1] = lowest global index holding it (one block)
+__global__ void __launch_bounds__(256) k_local_best(const double* __restrict__ scores, int64_t h, int64_t h_begin, unsigned long long* __restrict__ pair) {
+    __shared__ unsigned long long sk[256], si[256];
+    unsigned long long bk = 0, bi = ~0ull;
+    for (int64_t i = threadIdx.x; i < h; i += blockDim.x) {
         const unsigned long long key = dbl_key(scores[i]);
-        b = key > b ? key : b;
+        if (key > bk) { bk = key; bi = (unsigned long long)(h_begin + i); }  // ascending i per thread: ties keep the lower index
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, b, o);
-        b = o2 > b ? o2 : b;
+    sk[threadIdx.x] = bk;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const unsigned long long k2 = sk[threadIdx.x + o], i2 = si[threadIdx.x + o];
+            if (k2 > sk[threadIdx.x] || (k2 == sk[threadIdx.x] && i2 < si[threadIdx.x])) { sk[threadIdx.x] = k2; si[threadIdx.x] = i2; }
+        }
+        __syncthreads();
     }
-    if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
-}
-// idx[0] = lowest global hypothesis index on this rank whose key equals the global best (else ~0)
-__global__ void k_best_index(const double* __restrict__ scores, int64_t h, int64_t h_begin, const unsigned long long* __restrict__ gbest,
-                             unsigned long long* idx) {
-    const unsigned long long g = *gbest;
-    unsigned long long b = ~0ull;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h; i += (int64_t)gridDim.x * blockDim.x)
-        if (g != 0 && dbl_key(scores[i]) == g) { const unsigned long long v = (unsigned long long)(h_begin + i); b = v < b ? v : b; }
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, b, o);
-        b = o2 < b ? o2 : b;
-    }
-    if ((threadIdx.x & 31) == 0 && b != ~0ull) atomicMin(idx, b);
+    if (threadIdx.x == 0) { pair[0] = sk[0]; pair[1] = sk[0] ? si[0] : ~0ull; }
 }
 
 // ------------------------------------------------------------------ getFitnessScore: exact nearest neighbour in the target
@@ -1404,53 +1398,44 @@ int64_t b200_ndt_nbhd_total(b200_ndt* n, const double* p6) {
 }
 
 /* Global relocalization: score hypotheses h_begin .. h_begin+h-1 on this rank (calculateScore; the cost that is
- * minimised is -score, i.e. the winner is the most likely pose), then an allreduce-argmin across ranks: one 8-byte
- * ncclAllReduce(max) on the order-preserving score key, one 8-byte ncclAllReduce(min) on the index of the rank(s)
- * holding that key - exact in fp64, ties to the lowest hypothesis index, identical result on every rank. */
+ * minimised is -score, i.e. the winner is the most likely pose), then the argmin across ranks: every rank contributes its
+ * local winner as a 16-byte (order-preserving fp64 score key, global index) pair to one ncclAllGather and all ranks take
+ * the same maximum of the gathered pairs - exact in fp64, ties to the lowest hypothesis index. */
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t* best, double* best_score,
                           float* gpu_ms) {
     if (!n || (h > 0 && !poses16) || h < 0 || h_begin < 0) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
     CUDA_SET_DEVICE(k.device);
+    const int R = comm && comm->nranks > 1 ? comm->nranks : 1;
     const int64_t hh = std::max<int64_t>(h, 1);
     CUDA_TRY(k.d_poses.reserve((size_t)hh * 16)); CUDA_TRY(k.h_poses.reserve((size_t)hh * 16));
     CUDA_TRY(k.d_scores.reserve(hh));
-    CUDA_TRY(k.d_best.reserve(4)); CUDA_TRY(k.h_best.reserve(4));
+    CUDA_TRY(k.d_best.reserve(2 + 2 * (size_t)R)); CUDA_TRY(k.h_best.reserve(2 + 2 * (size_t)R));
     if (h) {
         memcpy(k.h_poses.p, poses16, (size_t)h * 16 * sizeof(float));
         CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, (size_t)h * 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
     }
-    unsigned long long* d = k.d_best.p;  // [0] local best key, [1] global best key, [2] local index, [3] global index
+    unsigned long long* d = k.d_best.p;  // [0..1] local (key, index), [2..2+2R) the pairs of all ranks
     CUDA_TRY(cudaEventRecord(k.ev0, k.stream));
-    CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), k.stream));
-    CUDA_TRY(cudaMemsetAsync(d + 2, 0xFF, 2 * sizeof(unsigned long long), k.stream));
-    const unsigned nb = (unsigned)std::min<int64_t>((hh + 255) / 256, 64);
     if (h) {
         int32_t rc = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
         if (rc) return rc;
-        ndt::k_best_score<<<nb, 256, 0, k.stream>>>(k.d_scores.p, h, d);
     }
-    if (comm && comm->nranks > 1) {
-        int32_t rc = b200::comm_allreduce_u64(comm, d, d + 1, ncclMax, k.stream);
-        if (rc) return rc;
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(d + 1, d, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
-    }
-    if (h) ndt::k_best_index<<<nb, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, d + 1, d + 2);
-    if (comm && comm->nranks > 1) {
-        int32_t rc = b200::comm_allreduce_u64(comm, d + 2, d + 3, ncclMin, k.stream);
-        if (rc) return rc;
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(d + 3, d + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
-    }
-    LAUNCH_COUNT(h ? 2 : 0);
+    ndt::k_local_best<<<1, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, d);
+    LAUNCH_COUNT(1);
+    if (R > 1) NCCL_TRY(comm, comm->AllGather(d, d + 2, 2, ncclUint64, comm->comm, k.stream));
+    else CUDA_TRY(cudaMemcpyAsync(d + 2, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
     CUDA_TRY(cudaEventRecord(k.ev1, k.stream));
-    CUDA_TRY(cudaMemcpyAsync(k.h_best.p, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaMemcpyAsync(k.h_best.p, d + 2, 2 * (size_t)R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k.stream));
     CUDA_TRY(cudaStreamSynchronize(k.stream));
     CUDA_TRY(cudaGetLastError());
     cudaEventElapsedTime(&k.last_ms, k.ev0, k.ev1);
     if (gpu_ms) *gpu_ms = k.last_ms;
-    const unsigned long long key = k.h_best.p[1], idx = k.h_best.p[3];
+    unsigned long long key = 0, idx = ~0ull;
+    for (int r = 0; r < R; ++r) {
+        const unsigned long long kr = k.h_best.p[2 * r], ir = k.h_best.p[2 * r + 1];
+        if (kr > key || (kr == key && kr != 0 && ir < idx)) { key = kr; idx = ir; }
+    }
     if (key == 0 || idx == ~0ull) { if (best) *best = -1; if (best_score) *best_score = 0; return B200_NO_EFFECTIVE_POINTS; }
     const unsigned long long u = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
     double sc;

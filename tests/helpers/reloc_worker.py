@@ -1,7 +1,7 @@
 """Worker for the multi-rank relocalization tests (launched with torch.distributed.run).
 
 mode "gloo": CPU only - the hypothesis slices are scored by the oracle and the allreduce-argmin protocol of
-             b200_reloc_argmin (max of the order-preserving score key, then min of the index among its holders) runs over gloo.
+             b200_reloc_argmin (all-gather of the ranks' (score key, index) winners, same reduction everywhere) runs over gloo.
 mode "nccl": the product path - map replicated with b200_ndt_set_target_bcast, slices scored on each GPU, NCCL collectives.
 Rank 0 writes a JSON result to argv[2].
 """
@@ -35,7 +35,11 @@ def main():
         o.set_target(mp)
         o.set_source(scan)
         scores = o.score_batch(poses[b:e]) if e > b else np.zeros(0)
-        best, score = api.argmin_protocol_host(scores, b, lambda t, op: dist.all_reduce(t, op=op))
+        def gather(t):
+            out = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return torch.stack(out)
+        best, score = api.argmin_protocol_host(scores, b, gather)
         full = o.score_batch(poses)
         res = dict(best=int(best), score=float(score), expect=int(np.argmax(full)), expect_score=float(full.max()), world=world,
                    slice=[b, e])

@@ -33,10 +33,13 @@ def test_score_key_is_order_preserving(api):
 
 def test_argmin_protocol_single_rank(api):
     s = np.array([0.1, 0.7, 0.7, -0.2])
-    best, score = api.argmin_protocol_host(s, 10, lambda t, op: None)
+    best, score = api.argmin_protocol_host(s, 10, lambda t: t[None])
     assert (best, score) == (11, 0.7)       # ties go to the lower index
-    best, score = api.argmin_protocol_host(np.zeros(0), 0, lambda t, op: None)
+    best, score = api.argmin_protocol_host(np.zeros(0), 0, lambda t: t[None])
     assert best == -1
+    import torch
+    two = lambda t: torch.stack([t, torch.tensor([api.score_key(0.7) - (1 << 63), 3], dtype=torch.int64)])
+    assert api.argmin_protocol_host(s, 10, two) == (3, 0.7)   # equal scores on two ranks: the lower global index wins
 
 
 @pytest.mark.timeout(300)
