@@ -269,7 +269,9 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
                          "points_per_s": N_SCAN / (float(np.mean(al_dev)) * 1e-3)},
             "roofline": {"bound": "hbm", "kernel": "k_ndt_eval (one init + one evaluation launch, CUDA events around both)",
                          "achieved": der_bytes / (der_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": der_bytes / (der_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(der_bytes), "traffic": None,
+                         "frac": der_bytes / (der_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(der_bytes),
+                         # ncu dram bytes of one k_ndt_eval launch (profiles/r01_ndt_ncu_full_summary.md): leaves and cell table are L2-resident
+                         "traffic": 1546240 + 1024,
                          "note": "20k points x <=7 voxels is ~9 MB per evaluation: the kernel is latency/launch bound, not bandwidth bound"},
         }
         if world == 1 and not args.no_cpu:
@@ -628,10 +630,14 @@ def run_b200(args, rank, local_rank, world):
     k_ms = float(np.mean(search_ms)) if search_ms else float("nan")
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_search (stencil k-NN, 8 lanes/query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None, "algorithmic_bytes": int(algo_bytes),
+                "frac": achieved / peak, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch at this workload (P-livox, cold L2),
+                # ncu --set full capture summarised in profiles/r01_iekf_ncu_full_summary.md (prof_iekf_r1c, launch id 0)
+                "traffic": 29512704 + 2816000 if args.params == "livox" else None, "algorithmic_bytes": int(algo_bytes),
                 "kernel_ms": k_ms, "candidates_per_query": sum_c / n, "occupied_cells_per_query": cells / n,
-                "note": "kernel_ms is event-to-event inside the update's stream (includes ~4 us of launch/event gap); "
-                        "traffic: see profiles/ (ncu dram bytes, cold L2)"}
+                "note": "kernel_ms is event-to-event inside the update's stream (includes ~4 us of launch/event gap); traffic = ncu dram bytes "
+                        "per launch with a cold L2 (2.3x the algorithmic bytes: 32-byte sectors around 16-byte table entries and short runs); "
+                        "the kernel is bound by L1 wavefronts of scattered 16-byte gathers, not by DRAM (profiles/README.md)"}
     # the same search kernel with enough parallelism to leave the launch-latency regime: 50 scans' worth of queries in one call
     rng = np.random.default_rng(1)
     qbig = np.ascontiguousarray(np.concatenate([qw + rng.normal(0, 0.05, qw.shape).astype(np.float32) for _ in range(50)], 0))
