@@ -205,6 +205,17 @@ int32_t b200_downsampler_destroy(b200_downsampler* d);
  * points per voxel (either may be NULL), *n_out = number of voxels */
 int32_t b200_voxel_downsample(b200_downsampler* d, const float* xyzi, int64_t n, int64_t stride_bytes, float leaf, int32_t min_points,
                               float* out_xyzi, int32_t* out_count, int64_t max_out, int64_t* n_out);
+/* ImuProcess::UndistortPcl, backward half (jueying_lio/include/imu_processing.hpp:175-177,247-284): time-sorts the raw
+ * scan and moves every point to the end-of-scan frame.  Float records at stride_bytes (x y z first, time offset in ms at
+ * float index time_index - pcl curvature, 9 in PointXYZINormal - intensity at intensity_index or < 0); poses22 = K x 22
+ * doubles {offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]} (IMUpose_ of the forward propagation, which stays on the
+ * host); x_end26 = state after the last predict.  The result is staged on the device; out_xyzi / out_order optional. */
+int32_t b200_scan_undistort(b200_downsampler* d, const float* points, int64_t n, int64_t stride_bytes, int32_t time_index,
+                            int32_t intensity_index, const double* poses22, int32_t K, const double* x_end26, float* out_xyzi,
+                            int32_t* out_order);
+/* pcl::VoxelGrid::filter on the staged (undistorted) scan - raw scan -> undistort -> downsample -> IEKF update without
+ * a host round trip */
+int32_t b200_voxel_downsample_staged(b200_downsampler* d, float leaf, int32_t min_points, int64_t* n_out);
 /* the last result as it sits on the device (float4 per voxel): pass it to b200_iekf_update_device */
 const void* b200_downsampler_device_points(b200_downsampler* d, int64_t* n);
 

@@ -46,7 +46,7 @@ class NdtResult(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "smallmat.h", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "undistort_oracle.cpp", "smallmat.h", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -108,6 +108,7 @@ def lib():
         L.orc_voxel_grid.argtypes = [vp, i64, i64, C.c_float, i32, vp, vp, i64]
         L.orc_full_map.restype = i64
         L.orc_full_map.argtypes = [vp, vp, i64, vp, C.c_float, vp, vp, i64]
+        L.orc_undistort.argtypes = [vp, i64, i64, i32, i32, vp, i32, vp, vp, vp]
         L.orc_euler_from_matrix.argtypes = [vp, vp]
         L.orc_matrix_from_pose.argtypes = [vp, vp]
         _LIB = L
@@ -356,3 +357,14 @@ def full_map(frames, poses7, leaf):
     cnt = np.empty(len(allp), np.int32)
     m = lib().orc_full_map(_p(allp), _p(offs), len(frames), _p(poses), leaf, _p(out), _p(cnt), len(allp))
     return out[:m].copy(), cnt[:m].copy()
+
+
+def undistort(points, time_index, intensity_index, poses22, x_end26):
+    """ImuProcess::UndistortPcl, backward half: returns (xyzi [n,4] in time order, order [n])."""
+    a = np.ascontiguousarray(points, dtype=np.float32)
+    poses = np.ascontiguousarray(poses22, dtype=np.float64).reshape(-1, 22)
+    x = np.ascontiguousarray(x_end26, dtype=np.float64)
+    out = np.zeros((a.shape[0], 4), np.float32)
+    order = np.zeros(a.shape[0], np.int32)
+    lib().orc_undistort(_p(a), a.shape[0], a.strides[0], time_index, intensity_index, _p(poses), poses.shape[0], _p(x), _p(out), _p(order))
+    return out, order

@@ -141,6 +141,10 @@ int64_t orc_voxel_grid(const float* xyzi, int64_t n, int64_t stride, float leaf,
 int64_t orc_full_map(const float* xyzi, const int64_t* offsets, int64_t n_frames, const double* poses7, float leaf, float* out_xyzi,
                      int32_t* out_count, int64_t max);
 
+/* ---- per-point motion compensation (ImuProcess::UndistortPcl, backward half) ---- */
+void orc_undistort(const float* pts, int64_t n, int64_t stride, int32_t time_index, int32_t intensity_index, const double* poses22, int32_t K,
+                   const double* x_end26, float* out_xyzi, int32_t* out_order);
+
 #ifdef __cplusplus
 }
 #endif

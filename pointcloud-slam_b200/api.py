@@ -133,6 +133,8 @@ def lib():
     L.b200_downsampler_create.argtypes = [i32, C.POINTER(vp)]
     L.b200_downsampler_destroy.argtypes = [vp]
     L.b200_voxel_downsample.argtypes = [vp, vp, i64, i64, C.c_float, i32, vp, vp, i64, vp]
+    L.b200_scan_undistort.argtypes = [vp, vp, i64, i64, i32, i32, vp, i32, vp, vp, vp]
+    L.b200_voxel_downsample_staged.argtypes = [vp, C.c_float, i32, vp]
     L.b200_downsampler_device_points.restype = vp
     L.b200_downsampler_device_points.argtypes = [vp, vp]
     L.b200_downsampler_last_ms.restype = C.c_float
@@ -614,6 +616,25 @@ class VoxelGrid:
         m = C.c_int64(0)
         _check(lib().b200_voxel_downsample(self.h, _p(a), n, a.strides[0], self.leaf, self.min_points, _p(out), _p(cnt), n, C.byref(m)))
         return out[:m.value].copy(), cnt[:m.value].copy()
+
+    def undistort(self, points, time_index, intensity_index, poses22, x_end26, want_host=True):
+        """ImuProcess::UndistortPcl (backward half) on the raw scan; the result stays staged on the device.
+        Returns (xyzi [n,4] in time order, order [n]) when want_host."""
+        a = np.ascontiguousarray(points, dtype=np.float32)
+        poses = np.ascontiguousarray(poses22, dtype=np.float64).reshape(-1, 22)
+        x = np.ascontiguousarray(x_end26, dtype=np.float64)
+        n = a.shape[0]
+        out = np.zeros((n, 4), np.float32) if want_host else None
+        order = np.zeros(n, np.int32) if want_host else None
+        _check(lib().b200_scan_undistort(self.h, _p(a), n, a.strides[0], time_index, intensity_index, _p(poses), poses.shape[0], _p(x),
+                                         _p(out) if want_host else None, _p(order) if want_host else None))
+        return out, order
+
+    def filter_staged(self):
+        """VoxelGrid on the staged (undistorted) scan; returns the number of voxels (result on the device)."""
+        m = C.c_int64(0)
+        _check(lib().b200_voxel_downsample_staged(self.h, self.leaf, self.min_points, C.byref(m)))
+        return m.value
 
     def device_points(self):
         n = C.c_int64(0)

@@ -105,6 +105,92 @@ __global__ void k_centroids(const float4* __restrict__ pts, const int32_t* __res
     out[r] = make_float4(sx / n, sy / n, sz / n, si / n);
 }
 
+// ------------------------------------------------------------------ per-point motion compensation
+// ImuProcess::UndistortPcl, backward half (jueying_lio/include/imu_processing.hpp:247-284): every point is moved from
+// the sensor pose at its own sampling time to the pose at the end of the scan, using the IMU poses of the forward
+// propagation (which stays on the host: a few dozen sequential esekf::predict calls).  fp64 like the reference.
+struct ImuPose {  // common::Pose6D (common_lib.h:111-123)
+    double t, acc[3], gyr[3], vel[3], pos[3], rot[9];
+};
+static_assert(sizeof(ImuPose) == 22 * 8, "22 doubles per pose");
+
+__device__ inline void und_cross(const double* a, const double* b, double* r) {
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ inline void und_qrot(const double* q /*x y z w*/, const double* v, double* r) {  // Eigen _transformVector
+    double uv[3], c2[3];
+    und_cross(q, v, uv);
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    und_cross(q, uv, c2);
+    for (int i = 0; i < 3; ++i) r[i] = v[i] + q[3] * uv[i] + c2[i];
+}
+// one compensation step of point p (float coordinates in / out) in segment (head, tail)
+__device__ inline void und_step(const ImuPose& head, const ImuPose& tail, const double* xe, double t, float* p) {
+    const double dt = t - head.t;
+    const double* w = tail.gyr;
+    const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (n > 0.0000001) {  // Exp(ang_vel, dt), so3_math.h:31-49
+        const double a[3] = {w[0] / n, w[1] / n, w[2] / n};
+        const double K[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+        const double ang = n * dt, s = sin(ang), c1 = 1.0 - cos(ang);
+        double cK[9], KK[9];
+        for (int i = 0; i < 9; ++i) cK[i] = c1 * K[i];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) KK[i * 3 + j] = cK[i * 3] * K[j] + cK[i * 3 + 1] * K[3 + j] + cK[i * 3 + 2] * K[6 + j];
+        for (int i = 0; i < 9; ++i) E[i] = (E[i] + s * K[i]) + KK[i];
+    }
+    double Ri[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = head.rot[i * 3] * E[j] + head.rot[i * 3 + 1] * E[3 + j] + head.rot[i * 3 + 2] * E[6 + j];
+    const double Pi[3] = {p[0], p[1], p[2]};
+    const double* offT = xe + 11;
+    const double rot_c[4] = {-xe[3], -xe[4], -xe[5], xe[6]}, offR_c[4] = {-xe[7], -xe[8], -xe[9], xe[10]};
+    double Tei[3], a[3], b[3], c[3], d[3], e[3];
+    for (int i = 0; i < 3; ++i) Tei[i] = ((head.pos[i] + head.vel[i] * dt) + 0.5 * tail.acc[i] * dt * dt) - xe[i];
+    und_qrot(xe + 7, Pi, a);
+    for (int i = 0; i < 3; ++i) a[i] += offT[i];
+    for (int i = 0; i < 3; ++i) b[i] = (Ri[i * 3] * a[0] + Ri[i * 3 + 1] * a[1] + Ri[i * 3 + 2] * a[2]) + Tei[i];
+    und_qrot(rot_c, b, c);
+    for (int i = 0; i < 3; ++i) d[i] = c[i] - offT[i];
+    und_qrot(offR_c, d, e);
+    p[0] = (float)e[0]; p[1] = (float)e[1]; p[2] = (float)e[2];
+}
+
+// raw records -> (time key, index); time as an order-preserving uint so that a stable radix sort = ascending time
+__global__ void k_und_keys(const float* __restrict__ raw, int n, int stride_f, int time_index, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t u = __float_as_uint(raw[(size_t)i * stride_f + time_index]);
+    keys[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    vals[i] = i;
+}
+__global__ void k_undistort(const float* __restrict__ raw, const int32_t* __restrict__ order, int n, int stride_f, int time_index, int intensity_index,
+                            const ImuPose* __restrict__ poses, int K, const double* __restrict__ xe, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = raw + (size_t)order[i] * stride_f;
+    float p[3] = {r[0], r[1], r[2]};
+    const double t = (double)r[time_index] / double(1000);
+    if (K >= 2) {
+        // segment = largest k <= K-2 whose head offset is before t (the reference walks the segments backwards)
+        int lo = -1, hi = K - 1;  // poses[lo].t < t (or lo == -1), poses[hi].t >= t or hi == K-1
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (poses[mid].t < t) lo = mid; else hi = mid;
+        }
+        if (lo >= 0) {
+            und_step(poses[lo], poses[lo + 1], xe, t, p);
+            // the earliest point is compensated again by every earlier segment (imu_processing.hpp:279-281)
+            if (i == 0)
+                for (int k = lo - 1; k >= 0; --k) und_step(poses[k], poses[k + 1], xe, t, p);
+        }
+    }
+    out[i] = make_float4(p[0], p[1], p[2], intensity_index >= 0 ? r[intensity_index] : 0.0f);
+}
+
 // ------------------------------------------------------------------ map builder
 struct __align__(16) Acc {
     double sx, sy, sz, si;
@@ -387,6 +473,13 @@ struct b200_downsampler {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     int64_t n_out = 0;
+    // undistortion stage
+    DevBuf<float> d_raw;
+    DevBuf<uint32_t> u_keys_in, u_keys_out;
+    DevBuf<int32_t> u_vals_in, u_vals_out;
+    DevBuf<double> d_poses;
+    PinnedBuf<double> h_poses;
+    int64_t n_staged = 0;  // undistorted points waiting in d_in
 };
 
 static int32_t downsample_run(b200_downsampler* d, int64_t n, float leaf, int32_t min_points) {
@@ -488,6 +581,8 @@ int32_t b200_downsampler_destroy(b200_downsampler* d) {
     d->d_in.release(); d->d_out.release(); d->d_cmp.release(); d->k_in.release(); d->k_out.release(); d->k_uniq.release();
     d->v_in.release(); d->v_out.release(); d->run_cnt.release(); d->run_off.release(); d->d_small.release(); d->d_cnt.release();
     d->d_cnt_cmp.release(); d->keep.release(); d->cub_tmp.release(); d->h_stage.release(); d->h_small.release();
+    d->d_raw.release(); d->u_keys_in.release(); d->u_keys_out.release(); d->u_vals_in.release(); d->u_vals_out.release();
+    d->d_poses.release(); d->h_poses.release();
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -516,6 +611,57 @@ int32_t b200_voxel_downsample(b200_downsampler* d, const float* xyzi, int64_t n,
     if (m > 0 && out_xyzi) CUDA_TRY(cudaMemcpyAsync(out_xyzi, d->d_cmp.p, m * sizeof(float4), cudaMemcpyDeviceToHost, d->stream));
     if (m > 0 && out_count) CUDA_TRY(cudaMemcpyAsync(out_count, d->d_cnt_cmp.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return B200_OK;
+}
+/* ImuProcess::UndistortPcl, backward half (jueying_lio/include/imu_processing.hpp:175-177,247-284): sorts the raw scan by
+ * its per-point time offset and moves every point to the end-of-scan frame.  Records are floats at stride_bytes: x y z
+ * first, the time offset in ms at float index time_index (pcl curvature: 9 in PointXYZINormal), intensity at
+ * intensity_index (< 0: none).  poses22: K x 22 doubles {offset_time, acc, gyr, vel, pos, rot(9, row-major)} = IMUpose_ of
+ * the forward propagation; x_end26: the state after the last predict.  The result stays on the device ("staged") for
+ * b200_voxel_downsample_staged; out_xyzi (n x 4) / out_order (n source indices) are optional host copies. */
+int32_t b200_scan_undistort(b200_downsampler* d, const float* points, int64_t n, int64_t stride, int32_t time_index, int32_t intensity_index,
+                            const double* poses22, int32_t K, const double* x_end26, float* out_xyzi, int32_t* out_order) {
+    if (!d || !points || n < 1 || stride < 16 || (stride & 3) || time_index < 3 || time_index * 4 >= stride || intensity_index * 4 >= stride ||
+        !poses22 || K < 1 || K > 4096 || !x_end26 || n > (int64_t)0x3fffff00)
+        B200_FAIL(B200_ERR_ARG, "bad argument");
+    using namespace vox;
+    CUDA_SET_DEVICE(d->device);
+    cudaStream_t s = d->stream;
+    const int sf = (int)(stride / 4);
+    CUDA_TRY(d->d_raw.reserve((size_t)n * sf));
+    CUDA_TRY(d->d_in.reserve(n));
+    CUDA_TRY(d->u_keys_in.reserve(n)); CUDA_TRY(d->u_keys_out.reserve(n)); CUDA_TRY(d->u_vals_in.reserve(n)); CUDA_TRY(d->u_vals_out.reserve(n));
+    CUDA_TRY(d->d_poses.reserve((size_t)K * 22 + 32)); CUDA_TRY(d->h_poses.reserve((size_t)K * 22 + 32));
+    memcpy(d->h_poses.p, poses22, (size_t)K * 22 * sizeof(double));
+    memcpy(d->h_poses.p + (size_t)K * 22, x_end26, 26 * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(d->d_poses.p, d->h_poses.p, ((size_t)K * 22 + 26) * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d->d_raw.p, points, (size_t)n * stride, cudaMemcpyHostToDevice, s));  // raw records, one copy
+    CUDA_TRY(cudaEventRecord(d->ev0, s));
+    const int nb = (int)((n + 255) / 256);
+    k_und_keys<<<nb, 256, 0, s>>>(d->d_raw.p, (int)n, sf, time_index, d->u_keys_in.p, d->u_vals_in.p);
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d->u_keys_in.p, d->u_keys_out.p, d->u_vals_in.p, d->u_vals_out.p, (int)n, 0, 32, s));
+    CUDA_TRY(d->cub_tmp.reserve(tmp));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->cub_tmp.p, tmp, d->u_keys_in.p, d->u_keys_out.p, d->u_vals_in.p, d->u_vals_out.p, (int)n, 0, 32, s));
+    k_undistort<<<nb, 256, 0, s>>>(d->d_raw.p, d->u_vals_out.p, (int)n, sf, time_index, intensity_index, (const ImuPose*)d->d_poses.p, K,
+                                   d->d_poses.p + (size_t)K * 22, d->d_in.p);
+    LAUNCH_COUNT(2);
+    CUDA_TRY(cudaEventRecord(d->ev1, s));
+    if (out_xyzi) CUDA_TRY(cudaMemcpyAsync(out_xyzi, d->d_in.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    if (out_order) CUDA_TRY(cudaMemcpyAsync(out_order, d->u_vals_out.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&d->last_ms, d->ev0, d->ev1);
+    d->n_staged = n;
+    return B200_OK;
+}
+/* pcl::VoxelGrid::filter on the points staged by b200_scan_undistort (no host round trip in between) */
+int32_t b200_voxel_downsample_staged(b200_downsampler* d, float leaf, int32_t min_points, int64_t* n_out) {
+    if (!d || d->n_staged < 1 || !(leaf > 0.f)) B200_FAIL(B200_ERR_ARG, "nothing staged");
+    CUDA_SET_DEVICE(d->device);
+    int32_t rc = downsample_run(d, d->n_staged, leaf, min_points);
+    if (rc) return rc;
+    if (n_out) *n_out = d->n_out;
     return B200_OK;
 }
 /* device view of the last result: float4 (x, y, z, intensity) per voxel - feeds b200_iekf_update_device without a host trip */

@@ -100,3 +100,75 @@ def test_full_map_capacity_error(api, synth):
     b.add_keyframe(frames[0], poses[0])
     with pytest.raises(api.B200Error):
         b.num_voxels()
+
+
+def imu_scene(synth, n=8000, first_time_ms=0.0, seed=4):
+    """A scan with per-point time offsets (ms, in curvature position 9 of a 12-float PointXYZINormal record) and the IMU
+    poses of a smooth motion: 21 poses, 5 ms apart."""
+    rng = np.random.default_rng(seed)
+    K = 21
+    w = np.array([0.3, -0.2, 0.8])          # rad/s
+    acc = np.array([0.5, -0.3, 0.1])
+    v0 = np.array([1.5, 0.2, -0.1])
+    poses = np.zeros((K, 22))
+    for k in range(K):
+        t = 0.005 * k
+        q = synth.quat_from_rotvec(w * t)
+        poses[k, 0] = t
+        poses[k, 1:4] = acc + rng.normal(0, 0.01, 3)
+        poses[k, 4:7] = w + rng.normal(0, 0.005, 3)
+        poses[k, 7:10] = v0 + acc * t
+        poses[k, 10:13] = v0 * t + 0.5 * acc * t * t
+        poses[k, 13:22] = synth.quat_to_R(q).reshape(9)
+    t_end = 0.1
+    x_end = synth.make_state(v0 * t_end + 0.5 * acc * t_end ** 2, w * t_end)
+    pts = np.zeros((n, 12), np.float32)
+    pts[:, :3] = rng.uniform(-30, 30, (n, 3))
+    pts[:, 8] = rng.uniform(0, 255, n)
+    pts[:, 9] = np.round(rng.uniform(first_time_ms, 100.0, n), 3)
+    pts[::97, 9] = pts[3::97, 9][: len(pts[::97])]     # ties in time
+    if first_time_ms == 0.0:
+        pts[5, 9] = 0.0                                 # a point at t = 0 is not compensated
+    return pts, poses, x_end
+
+
+@pytest.mark.parametrize("first_ms", [0.0, 12.5])
+def test_undistort_matches_oracle(oracle, api, synth, first_ms):
+    pts, poses, x_end = imu_scene(synth, first_time_ms=first_ms)
+    o_xyzi, o_order = oracle.undistort(pts, 9, 8, poses, x_end)
+    vg = api.VoxelGrid()
+    g_xyzi, g_order = vg.undistort(pts, 9, 8, poses, x_end)
+    np.testing.assert_array_equal(g_order, o_order)                 # same time order, ties in input order
+    np.testing.assert_array_equal(g_xyzi[:, 3], o_xyzi[:, 3])
+    # fp64 chain narrowed to fp32: device sin/cos may differ from libm in the last bit of the double
+    np.testing.assert_allclose(g_xyzi[:, :3], o_xyzi[:, :3], rtol=0, atol=4e-6)
+    assert (g_xyzi[:, :3] == o_xyzi[:, :3]).mean() > 0.999
+    moved = np.abs(o_xyzi[:, :3] - pts[o_order, :3]).max(1)
+    assert moved.max() > 0.05                                       # the motion is not a no-op
+    if first_ms == 0.0:
+        assert moved[pts[o_order, 9] == 0.0].max() == 0.0           # t = 0: untouched (imu_processing.hpp:262)
+
+
+def test_raw_scan_to_update_stays_on_device(oracle, api, synth, small_cfg):
+    """raw scan -> undistort -> VoxelGrid -> IEKF update, chained on the device, equals the same chain through the host."""
+    pts, poses, x_end = imu_scene(synth, n=len(small_cfg["scan"]))
+    pts[:, :3] = small_cfg["scan"]
+    vg = api.VoxelGrid()
+    vg.setLeafSize(0.5)
+    und, order = vg.undistort(pts, 9, 8, poses, x_end)
+    m = vg.filter_staged()
+    ptr, m2 = vg.device_points()
+    assert m == m2 > 100
+    o_und, _ = oracle.undistort(pts, 9, 8, poses, x_end)
+    c0, n0 = oracle.voxel_grid(und, 0.5)        # the device's own undistorted points through the oracle's VoxelGrid
+    assert len(c0) == m
+    g = api.IVox(resolution=0.5, nearby=18)
+    g.AddPoints(small_cfg["map"])
+    kf = api.Esekf(g)
+    kf.change_x(small_cfg["x_prop"]); kf.change_P(small_cfg["P"])
+    kf.update_device(ptr, m)
+    x_dev = kf.get_x().copy()
+    kf2 = api.Esekf(g)
+    kf2.change_x(small_cfg["x_prop"]); kf2.change_P(small_cfg["P"])
+    kf2.update_iterated_dyn_share_modified(c0[:, :3])
+    np.testing.assert_array_equal(x_dev, kf2.get_x())

@@ -57,3 +57,30 @@ def test_full_map_equals_voxel_grid_of_the_moved_union(oracle, synth):
     # float vs double transforms move a few points across voxel borders: compare the bulk statistics
     assert abs(len(c) - len(ref)) <= 0.002 * len(ref)
     np.testing.assert_allclose((c[:, :3] * n[:, None]).sum(0) / n.sum(), allp[:, :3].mean(0), atol=1e-4)
+
+
+def test_undistort_oracle_properties(oracle, synth):
+    """No motion -> points unchanged (only sorted); pure translation at constant velocity -> each point shifted by -v * (T - t)
+    expressed in the end frame."""
+    rng = np.random.default_rng(2)
+    n, K = 500, 11
+    pts = np.zeros((n, 12), np.float32)
+    pts[:, :3] = rng.uniform(-10, 10, (n, 3))
+    pts[:, 9] = rng.uniform(0.001, 100.0, n)
+    poses = np.zeros((K, 22))
+    for k in range(K):
+        poses[k, 0] = 0.01 * k
+        poses[k, 13:22] = np.eye(3).reshape(9)
+    x_end = synth.make_state([0, 0, 0], [0, 0, 0], ext_t=np.zeros(3))
+    out, order = oracle.undistort(pts, 9, -1, poses, x_end)
+    assert (np.diff(pts[order, 9]) >= 0).all()
+    np.testing.assert_array_equal(out[:, :3], pts[order, :3])
+    v = np.array([2.0, -1.0, 0.5])
+    for k in range(K):
+        poses[k, 7:10] = v
+        poses[k, 10:13] = v * poses[k, 0]
+    x_end = synth.make_state(v * 0.1, [0, 0, 0], ext_t=np.zeros(3))
+    out, order = oracle.undistort(pts, 9, -1, poses, x_end)
+    t = pts[order, 9].astype(np.float64) / 1000.0
+    expect = pts[order, :3].astype(np.float64) - v * (0.1 - t)[:, None]
+    np.testing.assert_allclose(out[:, :3], expect, atol=2e-6)
