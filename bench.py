@@ -201,10 +201,11 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
     launches0 = api.kernel_launches()
 
     # ---- reloc: strong scaling over ranks
-    b, e = api.shard_range(len(poses), world, rank)
-    mine = np.ascontiguousarray(poses[b:e])
+    # interleaved slices (hypothesis h on rank h mod N): neighbouring, similarly expensive hypotheses land on different ranks
+    mine = np.ascontiguousarray(poses[rank::world])
+    b, e = rank, rank + len(mine)
     for _ in range(3):
-        best, score, ms = api.relocalize(g, mine, comm, h_begin=b)
+        best, score, ms = api.relocalize(g, mine, comm, h_begin=rank, h_stride=world)
     dev, wall = [], []
     if world > 1:
         dist.barrier()
@@ -213,7 +214,7 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        best, score, ms = api.relocalize(g, mine, comm, h_begin=b)
+        best, score, ms = api.relocalize(g, mine, comm, h_begin=rank, h_stride=world)
         wall.append((time.perf_counter() - t0) * 1e3)
         dev.append(ms)
     t = torch.tensor([float(np.mean(dev)), float(np.mean(wall))], device="cuda", dtype=torch.float64)

@@ -189,6 +189,9 @@ int32_t b200_ndt_set_target_bcast(b200_comm* comm, b200_ndt* ndt, const float* x
  * comm may be NULL (single GPU).  best = -1 and B200_NO_EFFECTIVE_POINTS when no rank had a hypothesis. */
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t* best,
                           double* best_score, float* gpu_ms);
+/* same with an interleaved slice: local hypothesis i = global hypothesis h_begin + i * h_stride (rank r of N: h_begin r, stride N) */
+int32_t b200_reloc_argmin_strided(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t h_stride,
+                                  int64_t* best, double* best_score, float* gpu_ms);
 
 /* ------------------------------------------------------------------------- *
  * Voxel-grid reductions.

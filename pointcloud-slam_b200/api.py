@@ -121,6 +121,7 @@ def lib():
         L.b200_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
         L.b200_comm_destroy.argtypes = [vp]
         L.b200_reloc_argmin.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+        L.b200_reloc_argmin_strided.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp]
         L.b200_ndt_align_batch.argtypes = [vp, vp, i64, vp, vp]
         L.b200_ndt_grid.argtypes = [vp, vp, vp]
         L.b200_ndt_set_target_bcast.argtypes = [vp, vp, vp, i64, i64, i32]
@@ -570,13 +571,14 @@ def argmin_protocol_host(scores, h_begin, all_gather):
     return best_i, score_from_key(best_k)
 
 
-def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicator | None = None, h_begin=0):
-    """Global relocalization: scores this rank's hypothesis slice (poses_cm16 = the slice, h_begin = its offset in the
-    global grid) and returns (global best index, its score, device ms) - identical on every rank."""
+def relocalize(ndt: "NormalDistributionsTransform", poses_cm16, comm: Communicator | None = None, h_begin=0, h_stride=1):
+    """Global relocalization: scores this rank's hypothesis slice (poses_cm16 = the slice; local hypothesis i is global
+    hypothesis h_begin + i * h_stride) and returns (global best index, its score, device ms) - identical on every rank.
+    Contiguous slices: h_begin = shard_range(...)[0]; interleaved slices: poses[rank::nranks], h_begin = rank, h_stride = nranks."""
     poses = np.ascontiguousarray(poses_cm16, dtype=np.float32).reshape(-1, 16)
     best, score, ms = C.c_int64(-1), C.c_double(0), C.c_float(0)
-    rc = lib().b200_reloc_argmin(comm.h if comm is not None else None, ndt._handle(), _p(poses) if len(poses) else None,
-                                 poses.shape[0], h_begin, C.byref(best), C.byref(score), C.byref(ms))
+    rc = lib().b200_reloc_argmin_strided(comm.h if comm is not None else None, ndt._handle(), _p(poses) if len(poses) else None,
+                                         poses.shape[0], h_begin, h_stride, C.byref(best), C.byref(score), C.byref(ms))
     _check(rc)
     return best.value, score.value, ms.value
 

@@ -692,12 +692,13 @@ __device__ __forceinline__ unsigned long long dbl_key(double s) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 // This rank's winner: pair[0] = highest score key of the slice, pair[1] = lowest global index holding it (one block)
-__global__ void __launch_bounds__(256) k_local_best(const double* __restrict__ scores, int64_t h, int64_t h_begin, unsigned long long* __restrict__ pair) {
+__global__ void __launch_bounds__(256) k_local_best(const double* __restrict__ scores, int64_t h, int64_t h_begin, int64_t h_stride,
+                                                    unsigned long long* __restrict__ pair) {
     __shared__ unsigned long long sk[256], si[256];
     unsigned long long bk = 0, bi = ~0ull;
     for (int64_t i = threadIdx.x; i < h; i += blockDim.x) {
         const unsigned long long key = dbl_key(scores[i]);
-        if (key > bk) { bk = key; bi = (unsigned long long)(h_begin + i); }  // ascending i per thread: ties keep the lower index
+        if (key > bk) { bk = key; bi = (unsigned long long)(h_begin + i * h_stride); }  // ascending i per thread: ties keep the lower index
     }
     sk[threadIdx.x] = bk;
     si[threadIdx.x] = bi;
@@ -1401,9 +1402,9 @@ int64_t b200_ndt_nbhd_total(b200_ndt* n, const double* p6) {
  * minimised is -score, i.e. the winner is the most likely pose), then the argmin across ranks: every rank contributes its
  * local winner as a 16-byte (order-preserving fp64 score key, global index) pair to one ncclAllGather and all ranks take
  * the same maximum of the gathered pairs - exact in fp64, ties to the lowest hypothesis index. */
-int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t* best, double* best_score,
-                          float* gpu_ms) {
-    if (!n || (h > 0 && !poses16) || h < 0 || h_begin < 0) B200_FAIL(B200_ERR_ARG, "bad argument");
+static int32_t reloc_argmin_impl(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t h_stride, int64_t* best,
+                                 double* best_score, float* gpu_ms) {
+    if (!n || (h > 0 && !poses16) || h < 0 || h_begin < 0 || h_stride < 1) B200_FAIL(B200_ERR_ARG, "bad argument");
     Ndt& k = n->k;
     CUDA_SET_DEVICE(k.device);
     const int R = comm && comm->nranks > 1 ? comm->nranks : 1;
@@ -1421,7 +1422,7 @@ int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, in
         int32_t rc = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
         if (rc) return rc;
     }
-    ndt::k_local_best<<<1, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, d);
+    ndt::k_local_best<<<1, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, h_stride, d);
     LAUNCH_COUNT(1);
     if (R > 1) NCCL_TRY(comm, comm->AllGather(d, d + 2, 2, ncclUint64, comm->comm, k.stream));
     else CUDA_TRY(cudaMemcpyAsync(d + 2, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
@@ -1443,6 +1444,16 @@ int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, in
     if (best) *best = (int64_t)idx;
     if (best_score) *best_score = sc;
     return B200_OK;
+}
+int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t* best, double* best_score,
+                          float* gpu_ms) {
+    return reloc_argmin_impl(comm, n, poses16, h, h_begin, 1, best, best_score, gpu_ms);
+}
+/* same with the slice interleaved over the ranks: local hypothesis i is global hypothesis h_begin + i * h_stride (rank r of N
+ * passes h_begin = r, h_stride = N) - neighbouring, similarly expensive hypotheses land on different ranks */
+int32_t b200_reloc_argmin_strided(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t h_stride, int64_t* best,
+                                  double* best_score, float* gpu_ms) {
+    return reloc_argmin_impl(comm, n, poses16, h, h_begin, h_stride, best, best_score, gpu_ms);
 }
 
 }  // extern "C"

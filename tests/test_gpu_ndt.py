@@ -149,6 +149,8 @@ def test_score_batch_and_argmax(oracle, api, synth, ndt_small):
         b, e = api.shard_range(len(poses), 3, r)
         wins.append(api.relocalize(g, poses[b:e], h_begin=b)[:2])
     assert max(wins, key=lambda w: (w[1], -w[0]))[0] == best
+    wins = [api.relocalize(g, poses[r::3], h_begin=r, h_stride=3)[:2] for r in range(3)]   # interleaved slices
+    assert max(wins, key=lambda w: (w[1], -w[0]))[0] == best
 
 
 def test_ndt_errors(api, ndt_small):
