@@ -27,6 +27,7 @@ reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicate
            device time, the winner checked against the oracle's argmax at N=1.
 fullmap    configs[4]: construct_full_map - keyframes x 100k points merged into a 0.1 m voxel map, keyframes split over the
            ranks, partial voxel sums exchanged over NCCL; keyframes/s (--fullmap-frames, default 1600; 10000 = full).
+scan2map   jueying_slam's LOAM-style scan2MapOptimization for one scan: set_map + optimise times.
 sequence   configs[2]: sliding-map odometry (update + MapIncremental per scan) over --seq-scans scans (default 120;
            1000 is the full configuration and takes ~1 min of host-side ray casting).
 Skip them with --no-ndt / --seq-scans 0 (they add ~40 s of synthetic-data generation).
@@ -468,6 +469,42 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
     return out
 
 
+def loam_leg(args, local_rank, api, synth):
+    """jueying_slam's scan2MapOptimization (corner + surf features, 6x6 LM) for one scan."""
+    sc = synth.loam_scene(n_surf_map=400_000, surf_stride=4, corner_stride=2)
+    g = api.ScanToMap(max_map_points=1_000_000, device=local_rank)
+    t_set = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g.setInputCloud(sc["corner_map"], sc["surf_map"])
+        t_set.append((time.perf_counter() - t0) * 1e3)
+    guess = sc["t_true"] + np.array([0.01, -0.01, 0.02, 0.15, -0.1, 0.05], np.float32)
+    dev, wall = [], []
+    for k in range(args.steps + 3):
+        api.flush_l2(local_rank)
+        t0 = time.perf_counter()
+        t, rc = g.scan2MapOptimization(sc["corner"], sc["surf"], guess)
+        if k >= 3:
+            wall.append((time.perf_counter() - t0) * 1e3)
+            dev.append(g.stats.gpu_ms)
+    out = {"workload": f"jueying_slam scan2MapOptimization: {len(sc['corner'])} corner + {len(sc['surf'])} surf features vs "
+                       f"{len(sc['corner_map'])} / {len(sc['surf_map'])}-point feature maps, 0.18 m / 1 deg initial error",
+           "set_map_ms_e2e": float(np.min(t_set)), "optimize_ms": {"device": float(np.mean(dev)), "e2e_wall": float(np.mean(wall))},
+           "iters": g.stats.iters, "n_sel": g.stats.n_sel, "converged": bool(g.stats.converged),
+           "pose_error": {"trans_m": float(np.abs(t[3:] - sc["t_true"][3:]).max()), "rot_rad": float(np.abs(t[:3] - sc["t_true"][:3]).max())}}
+    if not args.no_cpu:
+        from oracle import binding as ob
+        o = ob.OracleLoam()
+        o.set_map(sc["corner_map"], sc["surf_map"])
+        t0 = time.perf_counter()
+        t_o, st = o.optimize(sc["corner"], sc["surf"], guess)
+        out["cpu_baseline"] = {"optimize_ms": (time.perf_counter() - t0) * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "one full optimisation; the port finds neighbours by brute force (exact, like the kd-tree, but slower than one)"}
+        out["parity"] = {"iters_equal": bool(st["iters"] == g.stats.iters), "max_transform_diff": float(np.abs(t_o - t).max())}
+    g.close()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = its restatement in oracle/
     (the reference cannot be compiled here: no PCL/Eigen/Boost/TBB), all host threads."""
@@ -608,6 +645,8 @@ def run_b200(args, rank, local_rank, world):
 
     if args.seq_scans > 1 and rank == 0:
         extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans)
+    if not args.no_ndt and rank == 0:
+        extra["scan2map"] = loam_leg(args, local_rank, api, synth)
 
     ms_step = float(np.mean(dev_ms))
     ms_e2e = float(np.mean(e2e_ms))

@@ -234,6 +234,32 @@ int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h);
 /* centroids held by this rank, ascending (z, y, x) voxel order; returns the voxel count */
 int64_t b200_mapbuild_extract(b200_mapbuild* h, float* out_xyzi, int32_t* out_count, int64_t max_out);
 
+/* ------------------------------------------------------------------------- *
+ * LOAM-style scan-to-map optimisation (the estimator of jueying_slam).  Replaces cornerOptimization, surfOptimization,
+ * combineOptimizationCoeffs, LMOptimization and the loop of scan2MapOptimization
+ * (jueying_slam/src/mapOptmization.cpp:1255-1590).  transformTobeMapped = t6 (roll, pitch, yaw, x, y, z), float.
+ * ------------------------------------------------------------------------- */
+typedef struct b200_loam b200_loam;
+typedef struct {
+    int32_t iters;        /* passes of the scan2MapOptimization loop that ran */
+    int32_t n_sel;        /* laserCloudSelNum of the last pass */
+    int32_t converged;    /* LMOptimization returned true */
+    int32_t degenerate;   /* isDegenerate */
+    float gpu_ms;
+    double AtA_first[36]; /* matAtA of the first pass (parity) */
+} b200_loam_stats;
+int32_t b200_loam_create(int64_t max_map_points, int32_t device, b200_loam** out);
+int32_t b200_loam_destroy(b200_loam* h);
+/* kdtreeCornerFromMap / kdtreeSurfFromMap ->setInputCloud(laserCloud{Corner,Surf}FromMapDS) (:1568-1569) */
+int32_t b200_loam_set_map(b200_loam* h, const float* corner_xyz, int64_t n_corner, int64_t stride_corner, const float* surf_xyz, int64_t n_surf,
+                          int64_t stride_surf);
+/* the optimisation loop for one scan (laserCloud{Corner,Surf}LastDS, lidar frame); t6 updated in place */
+int32_t b200_loam_optimize(b200_loam* h, const float* corner_xyz, int64_t n_corner, int64_t stride_corner, const float* surf_xyz, int64_t n_surf,
+                           int64_t stride_surf, float* t6, int32_t iter_num, b200_loam_stats* stats);
+/* one cornerOptimization + surfOptimization pass at t6 (parity probe) */
+int32_t b200_loam_features(b200_loam* h, const float* corner_xyz, int64_t n_corner, int64_t stride_corner, const float* surf_xyz, int64_t n_surf,
+                           int64_t stride_surf, const float* t6, uint8_t* flags, float* coeff4, int32_t* n_sel);
+
 #ifdef __cplusplus
 }
 #endif

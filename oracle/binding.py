@@ -46,7 +46,7 @@ class NdtResult(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "undistort_oracle.cpp", "smallmat.h", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "undistort_oracle.cpp", "loam_oracle.cpp", "smallmat.h", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -109,6 +109,14 @@ def lib():
         L.orc_full_map.restype = i64
         L.orc_full_map.argtypes = [vp, vp, i64, vp, C.c_float, vp, vp, i64]
         L.orc_undistort.argtypes = [vp, i64, i64, i32, i32, vp, i32, vp, vp, vp]
+        L.orc_loam_create.restype = vp
+        L.orc_loam_create.argtypes = [i32]
+        L.orc_loam_destroy.argtypes = [vp]
+        L.orc_loam_set_map.argtypes = [vp, vp, i64, i64, vp, i64, i64]
+        L.orc_loam_features.restype = i32
+        L.orc_loam_features.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, vp, vp]
+        L.orc_loam_optimize.restype = i32
+        L.orc_loam_optimize.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, i32, vp, vp, vp, vp]
         L.orc_euler_from_matrix.argtypes = [vp, vp]
         L.orc_matrix_from_pose.argtypes = [vp, vp]
         _LIB = L
@@ -368,3 +376,36 @@ def undistort(points, time_index, intensity_index, poses22, x_end26):
     order = np.zeros(a.shape[0], np.int32)
     lib().orc_undistort(_p(a), a.shape[0], a.strides[0], time_index, intensity_index, _p(poses), poses.shape[0], _p(x), _p(out), _p(order))
     return out, order
+
+
+class OracleLoam:
+    """jueying_slam scan2MapOptimization (corner + surf features, 6x6 LM); transforms are (roll, pitch, yaw, x, y, z) float32."""
+
+    def __init__(self, num_threads=0):
+        self.h = lib().orc_loam_create(num_threads)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_loam_destroy(self.h)
+            self.h = None
+
+    def set_map(self, corner, surf):
+        c, s = _f32(corner), _f32(surf)
+        lib().orc_loam_set_map(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0])
+
+    def features(self, corner, surf, t6):
+        c, s = _f32(corner), _f32(surf)
+        t = np.ascontiguousarray(t6, dtype=np.float32)
+        flags = np.zeros(len(c) + len(s), np.uint8)
+        coeff = np.zeros((len(c) + len(s), 4), np.float32)
+        n = lib().orc_loam_features(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), _p(flags), _p(coeff))
+        return n, flags, coeff
+
+    def optimize(self, corner, surf, t6, iter_num=30):
+        c, s = _f32(corner), _f32(surf)
+        t = np.array(t6, dtype=np.float32)
+        nsel, conv, deg = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        AtA = np.zeros((6, 6))
+        it = lib().orc_loam_optimize(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), iter_num,
+                                     C.byref(nsel), C.byref(conv), C.byref(deg), _p(AtA))
+        return t, dict(iters=it, n_sel=nsel.value, converged=bool(conv.value), degenerate=bool(deg.value), AtA=AtA)

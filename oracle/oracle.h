@@ -145,6 +145,16 @@ int64_t orc_full_map(const float* xyzi, const int64_t* offsets, int64_t n_frames
 void orc_undistort(const float* pts, int64_t n, int64_t stride, int32_t time_index, int32_t intensity_index, const double* poses22, int32_t K,
                    const double* x_end26, float* out_xyzi, int32_t* out_order);
 
+/* ---- LOAM-style scan-to-map optimisation of jueying_slam (mapOptmization.cpp:1255-1590) ---- */
+typedef struct orc_loam orc_loam;
+orc_loam* orc_loam_create(int32_t num_threads);
+void orc_loam_destroy(orc_loam* h);
+void orc_loam_set_map(orc_loam* h, const float* corner, int64_t nc, int64_t sc, const float* surf, int64_t ns, int64_t ss);
+int32_t orc_loam_features(orc_loam* h, const float* corner, int64_t nc, int64_t sc, const float* surf, int64_t ns, int64_t ss, const float* t6,
+                          uint8_t* flags, float* coeff4);
+int32_t orc_loam_optimize(orc_loam* h, const float* corner, int64_t nc, int64_t sc, const float* surf, int64_t ns, int64_t ss, float* t6,
+                          int32_t iter_num, int32_t* n_sel, int32_t* converged, int32_t* degenerate, double* AtA_first);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,11 @@ class NdtResult(C.Structure):
                 ("p_final", C.c_double * 6), ("gpu_ms", C.c_float)]
 
 
+class LoamStats(C.Structure):
+    _fields_ = [("iters", C.c_int32), ("n_sel", C.c_int32), ("converged", C.c_int32), ("degenerate", C.c_int32), ("gpu_ms", C.c_float),
+                ("AtA_first", C.c_double * 36)]
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, "libb200reg.so")
 
@@ -151,6 +156,11 @@ def lib():
     L.b200_mapbuild_extract.argtypes = [vp, vp, vp, i64]
     L.b200_mapbuild_last_exchange_ms.restype = C.c_float
     L.b200_mapbuild_last_exchange_ms.argtypes = [vp]
+    L.b200_loam_create.argtypes = [i64, i32, C.POINTER(vp)]
+    L.b200_loam_destroy.argtypes = [vp]
+    L.b200_loam_set_map.argtypes = [vp, vp, i64, i64, vp, i64, i64]
+    L.b200_loam_optimize.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, i32, C.POINTER(LoamStats)]
+    L.b200_loam_features.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -690,3 +700,41 @@ class FullMapBuilder:
         cnt = np.empty(max(m, 1), np.int32)
         lib().b200_mapbuild_extract(self.h, _p(out), _p(cnt), m)
         return out[:m].copy(), cnt[:m].copy()
+
+
+class ScanToMap:
+    """jueying_slam mapOptimization's scan2MapOptimization on the GPU (mapOptmization.cpp:1255-1590).
+    Transforms are transformTobeMapped: (roll, pitch, yaw, x, y, z) float32."""
+
+    def __init__(self, max_map_points=2_000_000, device=0):
+        self.h = C.c_void_p()
+        _check(lib().b200_loam_create(max_map_points, device, C.byref(self.h)))
+        self.stats = LoamStats()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_loam_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def setInputCloud(self, corner_map, surf_map):
+        c, s = _cloud(corner_map), _cloud(surf_map)
+        _check(lib().b200_loam_set_map(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0]))
+
+    def scan2MapOptimization(self, corner, surf, t6, iter_num=30):
+        c, s = _cloud(corner), _cloud(surf)
+        t = np.array(t6, dtype=np.float32)
+        rc = lib().b200_loam_optimize(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), iter_num, C.byref(self.stats))
+        _check(rc, soft=(0, 2))
+        return t, rc
+
+    def features(self, corner, surf, t6):
+        c, s = _cloud(corner), _cloud(surf)
+        t = np.ascontiguousarray(t6, dtype=np.float32)
+        n = len(c) + len(s)
+        flags = np.zeros(n, np.uint8)
+        coeff = np.zeros((n, 4), np.float32)
+        nsel = C.c_int32(0)
+        _check(lib().b200_loam_features(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), _p(flags), _p(coeff), C.byref(nsel)))
+        return nsel.value, flags, coeff

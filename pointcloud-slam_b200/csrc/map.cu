@@ -292,6 +292,17 @@ int32_t Map::init(const b200_map_params* p, int dev) {
     return B200_OK;
 }
 
+// IVox has no clear(); the LOAM front end rebuilds its two maps for every scan (kd-tree setInputCloud)
+int32_t Map::clear() {
+    CUDA_SET_DEVICE(device);
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(MapCounters), stream));
+    k_fill_keys<<<(tsize + 255) / 256, 256, 0, stream>>>(d_ent, d_aux, tsize);
+    LAUNCH_COUNT(1);
+    memset(&h_ctr, 0, sizeof h_ctr);
+    next_ord = 0;
+    return B200_OK;
+}
+
 void Map::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);

@@ -316,6 +316,7 @@ struct Map {
     }
     int32_t init(const b200_map_params* p, int dev);
     void destroy();
+    int32_t clear();
     int32_t insert_device(const float4* d_pts, int64_t n);  // points already on the device (x,y,z,*)
     int32_t insert_host(const float* xyz, int64_t n, int64_t stride);
     int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt);

@@ -274,3 +274,39 @@ def hypothesis_grid(p_center, nx=32, ny=32, nyaw=4, pitch=1.0) -> np.ndarray:
                 p[5] += k * (2 * np.pi / nyaw)
                 out.append(pose_vec_to_matrix(p).astype(np.float32).T.reshape(16))
     return np.ascontiguousarray(np.stack(out, 0))
+
+
+# ---- LOAM scene (jueying_slam scan-to-map): surface map + edge ("corner") map and a scan of both in the lidar frame ----
+def pcl_transform(t6):
+    """pcl::getTransformation(x, y, z, roll, pitch, yaw) for t6 = (roll, pitch, yaw, x, y, z): (R[3,3], t[3]) in fp64."""
+    r, p, y = [float(v) for v in t6[:3]]
+    A, B, Cc, D, E, F = np.cos(y), np.sin(y), np.cos(p), np.sin(p), np.cos(r), np.sin(r)
+    R = np.array([[A * Cc, A * D * F - B * E, B * F + A * D * E], [B * Cc, A * E + B * D * F, B * D * E - A * F], [-D, Cc * F, Cc * E]])
+    return R, np.asarray(t6[3:], dtype=np.float64)
+
+
+def loam_scene(n_surf_map=60_000, seed: int = SEED, t_true=(0.01, -0.02, 0.6, 3.0, -2.0, 1.2), surf_stride=6, corner_stride=3):
+    """Returns dict(corner_map, surf_map, corner, surf, t_true): the maps in the world frame, the scan features in the lidar frame."""
+    world = make_world(seed, beams=True)
+    _, boxes = world
+    rng = np.random.default_rng(seed + 11)
+    surf_map = sample_map(n_surf_map, seed, sigma=0.01, world=world)
+    edges = []
+    for b in boxes[:40]:
+        lo, hi = b
+        for x in (lo[0], hi[0]):
+            for y in (lo[1], hi[1]):
+                z = rng.uniform(lo[2], hi[2], 60)
+                edges.append(np.stack([np.full(60, x), np.full(60, y), z], 1))
+    corner_map = (np.concatenate(edges) + rng.normal(0, 0.01, (len(edges) * 60, 3))).astype(np.float32)
+    t_true = np.array(t_true, np.float32)
+    R, t = pcl_transform(t_true)
+
+    def to_body(pw):
+        return ((pw.astype(np.float64) - t) @ R).astype(np.float32)
+
+    near = np.linalg.norm(surf_map - t, axis=1) < 25
+    surf = to_body(surf_map[near][::surf_stride] + rng.normal(0, 0.01, (int(near.sum()), 3))[::surf_stride].astype(np.float32))
+    nearc = np.linalg.norm(corner_map - t, axis=1) < 30
+    corner = to_body(corner_map[nearc][::corner_stride])
+    return dict(corner_map=corner_map, surf_map=surf_map, corner=np.ascontiguousarray(corner), surf=np.ascontiguousarray(surf), t_true=t_true)
