@@ -7,6 +7,7 @@
 
 #include "esekf_gpu.hpp"
 #include "ndt_gpu.hpp"
+#include "scan2map_gpu.hpp"
 
 struct PointXYZINormal {  // layout of pcl::PointXYZINormal: 48 bytes
     float x, y, z, pad0, normal_x, normal_y, normal_z, pad1, intensity, curvature, pad2, pad3;
@@ -66,6 +67,33 @@ int main() {
         std::printf("ndt converged %d iters %d t %.4f %.4f %.4f prob %.4f\n", (int)ndt.hasConverged(), ndt.getFinalNumIteration(), T[12], T[13], T[14],
                     ndt.getTransformationProbability());
         if (!ndt.hasConverged() || aligned.points.size() != scan.size()) return 4;
+        std::printf("fitness %.5f\n", ndt.getFitnessScore());
+        // scan pre-processing chain: downsample on the device, then the update straight from device memory
+        ScanPreprocessor pre;
+        double pose22[2 * 22] = {0};
+        pose22[13] = pose22[17] = pose22[21] = 1.0;                       // identity rotation, no motion
+        pose22[22] = 0.1; pose22[22 + 13] = pose22[22 + 17] = pose22[22 + 21] = 1.0;
+        std::vector<PointXYZINormal> timed = scan;
+        for (size_t i = 0; i < timed.size(); ++i) timed[i].curvature = 100.0f * (float)i / (float)timed.size();
+        pre.undistort(timed, 9, 8, pose22, 2, x.data());
+        const int64_t n_down = pre.filterStaged(0.5f);
+        int64_t n_dev = 0;
+        const void* d_scan = pre.devicePoints(&n_dev);
+        b200_iekf_stats st{};
+        StateVec x2 = x;
+        CovMat P2 = P;
+        if (n_down < 100 || n_dev != n_down || b200_iekf_update_device(kf.handle(), d_scan, n_dev, x2.data(), P2.data(), &st) != B200_OK) return 5;
+        std::printf("preprocess %lld -> %lld points, update passes %d pos %.4f %.4f %.4f\n", (long long)timed.size(), (long long)n_down, st.passes, x2[0], x2[1], x2[2]);
+        if (std::fabs(x2[0] - 0.03) > 0.01) return 6;
+        // LOAM scan-to-map with the surface cloud as both feature maps' source
+        ScanToMap<Cloud> s2m(400000);
+        Cloud corner_map, corner_scan;   // no edge features in this scene: the surf features alone constrain the pose
+        s2m.setInputCloud(corner_map, *target);
+        float t6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool conv = s2m.scan2MapOptimization(corner_scan, *source, t6, 30);
+        std::printf("scan2map converged %d iters %d n_sel %d t %.4f %.4f %.4f degenerate %d\n", (int)conv, s2m.stats().iters, s2m.stats().n_sel, t6[3], t6[4], t6[5],
+                    (int)s2m.degenerate());
+        if (!conv || std::fabs(t6[3] - 0.03f) > 0.01f || std::fabs(t6[4] + 0.02f) > 0.01f) return 7;
     } catch (const std::exception& e) {
         std::printf("FAILED LOUDLY: %s\n", e.what());
         return 10;
