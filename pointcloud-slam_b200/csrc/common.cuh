@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <string>
 
@@ -14,7 +15,7 @@
 namespace b200 {
 
 extern thread_local std::string g_last_error;
-extern int64_t g_kernel_launches;  // counted by every launch site (bench.py "gpu_launches")
+extern std::atomic<int64_t> g_kernel_launches;  // counted by every launch site (bench.py "gpu_launches"); handles may live on different threads
 
 inline int32_t fail(int32_t code, const char* what, const char* file, int line) {
     char buf[512];
@@ -28,7 +29,7 @@ inline int32_t fail(int32_t code, const char* what, const char* file, int line) 
         cudaError_t _e = (expr);                                                         \
         if (_e != cudaSuccess) return ::b200::fail(B200_ERR_CUDA, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
-#define LAUNCH_COUNT(n) (::b200::g_kernel_launches += (n))
+#define LAUNCH_COUNT(n) (::b200::g_kernel_launches.fetch_add((n), std::memory_order_relaxed))
 // Entry of a public call: select the handle's device and drop a stale "last error" left behind by an earlier, unrelated
 // runtime call in this process (ours or anybody else's), so that it is not mistaken for a failure of this call.
 inline void drop_stale_error(const char* file, int line) {

@@ -11,7 +11,7 @@
 namespace b200 {
 
 thread_local std::string g_last_error;
-int64_t g_kernel_launches = 0;
+std::atomic<int64_t> g_kernel_launches{0};
 
 // ------------------------------------------------------------------ insert kernels
 // 1. voxel key of every incoming point (IVox::Pos2Grid, ivox3d.h:284-286)
@@ -533,7 +533,7 @@ extern "C" {
 
 const char* b200_version(void) { return "b200reg 0.1 (sm_100a)"; }
 const char* b200_last_error(void) { return b200::g_last_error.c_str(); }
-int64_t b200_kernel_launches(void) { return b200::g_kernel_launches; }
+int64_t b200_kernel_launches(void) { return b200::g_kernel_launches.load(); }
 
 int32_t b200_map_create(const b200_map_params* params, int32_t device, b200_map** out) {
     if (!params || !out) B200_FAIL(B200_ERR_ARG, "null argument");

@@ -183,3 +183,47 @@ def test_fitness_score_exact_nn(oracle, api, synth, ndt_small):
     rc0, T0, r0 = o.align(synth.pose_vec_to_matrix(ndt_small["p_true"]).astype(np.float32))
     g.align(synth.pose_vec_to_matrix(ndt_small["p_true"]).astype(np.float32))
     assert abs(g.getFitnessScore() - o.fitness(T0)[0]) <= 1e-6 * o.fitness(T0)[0]
+
+
+def test_full_size_properties(oracle, api, synth):
+    """BASELINE.json configs[1] / [3] at full size (10M-point prior map, 20k-point scan): size-independent properties.
+    The voxel build is deterministic and accounts for every point; align() from the perturbed guess ends at the same
+    optimum as the oracle; the hypothesis grid's winner is the true pose and survives any sharding."""
+    cfg = synth.config2()
+    g = api.NormalDistributionsTransform()
+    g.setTransformationEpsilon(0.01)
+    g.setInputTarget(cfg["map"])
+    g.setInputSource(cfg["scan"])
+    L1 = g.leaves()
+    g.setInputTarget(cfg["map"])                    # rebuild: bit-identical (sorted, input-order sums)
+    L2 = g.leaves()
+    for k in ("ids", "npts", "mean", "cov", "icov"):
+        np.testing.assert_array_equal(L1[k], L2[k])
+    assert (np.diff(L1["ids"]) > 0).all() and L1["npts"].min() >= 6 and L1["npts"].sum() <= len(cfg["map"])
+    # every valid leaf: icov * cov = I, eigenvalue ratio floor 0.01
+    sel = slice(None, None, 997)
+    prod = np.einsum("nij,njk->nik", L1["cov"][sel], L1["icov"][sel])
+    np.testing.assert_allclose(prod, np.broadcast_to(np.eye(3), prod.shape), atol=1e-6)
+    w = np.linalg.eigvalsh(0.5 * (L1["cov"][sel] + np.transpose(L1["cov"][sel], (0, 2, 1))))
+    assert (w[:, 0] >= 0.01 * w[:, 2] * (1 - 1e-6)).all()
+    # the mean of a leaf lies inside its voxel
+    mn, dv = g.grid()
+    ids = L1["ids"][sel]
+    ijk = np.stack([ids % dv[0], (ids // dv[0]) % dv[1], ids // (dv[0] * dv[1])], 1) + mn
+    assert ((L1["mean"][sel] >= ijk - 1e-4) & (L1["mean"][sel] <= ijk + 1 + 1e-4)).all()
+    # align: oracle parity at full size
+    o = oracle.OracleNdt(resolution=1.0, trans_eps=0.01)
+    o.set_target(cfg["map"])
+    o.set_source(cfg["scan"])
+    rc0, T0, r0 = o.align(cfg["guess"])
+    rc1 = g.align(cfg["guess"])
+    assert rc1 == rc0 and (g.result.iters, g.result.evals) == (r0.iters, r0.evals)
+    assert np.abs(np.array(g.result.p_final) - np.array(r0.p_final)).max() < POSE_TOL
+    # relocalization: the true pose wins, however the grid is cut
+    poses = synth.hypothesis_grid(cfg["p_true"], 16, 16, 4, 1.0)
+    best, score, _ = api.relocalize(g, poses)
+    assert best == (8 * 16 + 8) * 4
+    wins = [api.relocalize(g, poses[r::5], h_begin=r, h_stride=5)[:2] for r in range(5)]
+    assert max(wins, key=lambda w: (w[1], -w[0])) == (best, score)
+    fit = g.getFitnessScore()
+    assert 0 < fit < 0.05 and g.fitness_in_range == len(cfg["scan"])
