@@ -925,23 +925,28 @@ View Ndt::view() const {
     return v;
 }
 
-// strided host cloud -> pinned float4 staging (a few host threads) -> device
+// strided host cloud -> pinned float4 staging -> device, in chunks: while chunk c crosses PCIe, chunk c+1 is being packed
+// by a few host threads
 int32_t Ndt::upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>& dst) {
     CUDA_TRY(h_stage.reserve((size_t)n));
     CUDA_TRY(dst.reserve((size_t)n));
-    const int nt = n > (1 << 20) ? 8 : 1;
-    if (nt == 1) pack_xyz_float4(xyz, n, stride, h_stage.p);
-    else {
-        std::vector<std::thread> th;
-        const int64_t per = (n + nt - 1) / nt;
-        for (int t = 0; t < nt; ++t) {
-            const int64_t b = t * per, e = std::min<int64_t>(n, b + per);
-            if (b >= e) break;
-            th.emplace_back([=]() { pack_xyz_float4((const float*)((const char*)xyz + b * stride), e - b, stride, h_stage.p + b); });
+    const int64_t chunk = 1 << 20;
+    const int nt = n > chunk ? 8 : 1;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t c1 = std::min<int64_t>(n, c0 + chunk);
+        if (nt == 1) pack_xyz_float4((const float*)((const char*)xyz + c0 * stride), c1 - c0, stride, h_stage.p + c0);
+        else {
+            std::vector<std::thread> th;
+            const int64_t per = (c1 - c0 + nt - 1) / nt;
+            for (int t = 0; t < nt; ++t) {
+                const int64_t b = c0 + t * per, e = std::min<int64_t>(c1, b + per);
+                if (b >= e) break;
+                th.emplace_back([=]() { pack_xyz_float4((const float*)((const char*)xyz + b * stride), e - b, stride, h_stage.p + b); });
+            }
+            for (auto& t : th) t.join();
         }
-        for (auto& t : th) t.join();
+        CUDA_TRY(cudaMemcpyAsync(dst.p + c0, h_stage.p + c0, (size_t)(c1 - c0) * sizeof(float4), cudaMemcpyHostToDevice, stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(dst.p, h_stage.p, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, stream));
     return B200_OK;
 }
 

@@ -354,6 +354,11 @@ struct Builder {
     int64_t frames = 0, points = 0;
     float ms_accumulate = 0.f, last_ms = 0.f;
     int64_t n_sorted = -1;  // entries of d_slots valid for extraction, -1 = stale
+    static constexpr int NSTAGE = 3;
+    PinnedBuf<float4> stage_h[NSTAGE];
+    DevBuf<float4> stage_d[NSTAGE];
+    cudaEvent_t stage_ev[NSTAGE] = {nullptr, nullptr, nullptr};
+    int64_t host_frames = 0;
 
     int32_t alloc_table(Table& t) {
         const uint32_t T = next_pow2(2 * capacity);
@@ -395,6 +400,7 @@ struct Builder {
         h_ctr.release(); d_pts.release(); d_out.release(); d_M.release(); h_M.release(); h_stage.release(); d_keys.release(); d_keys2.release();
         d_counts.release(); d_slots.release(); d_slots2.release(); d_cnt.release(); cub_tmp.release(); d_send.release(); d_recv.release();
         h_counts.release();
+        for (int i = 0; i < NSTAGE; ++i) { stage_h[i].release(); stage_d[i].release(); if (stage_ev[i]) cudaEventDestroy(stage_ev[i]); }
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -696,16 +702,27 @@ int32_t b200_mapbuild_add_keyframe(b200_mapbuild* h, const float* xyzi, int64_t 
     if (!h || !xyzi || !pose7 || n < 1 || stride < 12) B200_FAIL(B200_ERR_ARG, "bad argument");
     vox::Builder& b = h->b;
     CUDA_SET_DEVICE(b.device);
-    CUDA_TRY(cudaStreamSynchronize(b.stream));  // the staging buffer is reused
-    CUDA_TRY(b.h_stage.reserve(n));
-    CUDA_TRY(b.d_pts.reserve(n));
+    // three staging slots (pinned host + device) used round robin: packing keyframe i+1 on the host overlaps the copy and the
+    // accumulation of keyframe i; a slot is reused only after the kernel that read it has finished (its event)
+    const int slot = (int)(b.host_frames % vox::Builder::NSTAGE);
+    ++b.host_frames;
+    if (!b.stage_ev[slot]) CUDA_TRY(cudaEventCreateWithFlags(&b.stage_ev[slot], cudaEventDisableTiming));
+    else CUDA_TRY(cudaEventSynchronize(b.stage_ev[slot]));
+    CUDA_TRY(b.stage_h[slot].reserve(n));
+    CUDA_TRY(b.stage_d[slot].reserve(n));
+    float4* dst = b.stage_h[slot].p;
     const char* src = (const char*)xyzi;
-    for (int64_t i = 0; i < n; ++i) {
-        const float* p = (const float*)(src + i * stride);
-        b.h_stage.p[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 0.0f);
-    }
-    CUDA_TRY(cudaMemcpyAsync(b.d_pts.p, b.h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, b.stream));
-    return b.add_device(b.d_pts.p, n, pose7);
+    if (stride == 16) memcpy(dst, src, (size_t)n * 16);  // already x y z intensity records
+    else
+        for (int64_t i = 0; i < n; ++i) {
+            const float* p = (const float*)(src + i * stride);
+            dst[i] = make_float4(p[0], p[1], p[2], stride >= 16 ? p[3] : 0.0f);
+        }
+    CUDA_TRY(cudaMemcpyAsync(b.stage_d[slot].p, dst, n * sizeof(float4), cudaMemcpyHostToDevice, b.stream));
+    int32_t rc = b.add_device(b.stage_d[slot].p, n, pose7);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(b.stage_ev[slot], b.stream));
+    return B200_OK;
 }
 /* same with the keyframe already on the device as float4 (x, y, z, intensity) */
 int32_t b200_mapbuild_add_keyframe_device(b200_mapbuild* h, const void* d_xyzi_float4, int64_t n, const double* pose7) {
