@@ -99,7 +99,8 @@ int32_t b200_iekf_destroy(b200_iekf* ekf);
 /* kf_.update_iterated_dyn_share_modified(R, t) for one downsampled scan (laser_mapping.cc:335-351). */
 int32_t b200_iekf_update(b200_iekf* ekf, const float* scan_body_xyz, int64_t n, int64_t stride_bytes, double* x26,
                          double* P23x23, b200_iekf_stats* stats);
-/* Same update with the scan already resident on the device (float4 per point: x,y,z,unused). */
+/* Same update with the scan already resident on the device (float4 per point: x,y,z,unused).  The buffer must stay
+ * valid and unchanged until the b200_iekf_map_incremental call that follows (it re-reads the scan). */
 int32_t b200_iekf_update_device(b200_iekf* ekf, const void* d_scan_float4, int64_t n, double* x26, double* P23x23,
                                 b200_iekf_stats* stats);
 /* h_x^T h_x (12x12 row-major) and h_x^T h of pass `pass` of the last update (H/b parity, 1e-6 relative) */
