@@ -201,7 +201,10 @@ class IVox:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_map_destroy(self.h)
+            try:
+                lib().b200_map_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -260,7 +263,10 @@ class Esekf:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_iekf_destroy(self.h)
+            try:
+                lib().b200_iekf_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -372,7 +378,10 @@ class NormalDistributionsTransform:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_ndt_destroy(self.h)
+            try:
+                lib().b200_ndt_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -531,7 +540,10 @@ class Communicator:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_comm_destroy(self.h)
+            try:
+                lib().b200_comm_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -604,7 +616,10 @@ class VoxelGrid:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_downsampler_destroy(self.h)
+            try:
+                lib().b200_downsampler_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -666,7 +681,10 @@ class FullMapBuilder:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_mapbuild_destroy(self.h)
+            try:
+                lib().b200_mapbuild_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close
@@ -713,7 +731,10 @@ class ScanToMap:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().b200_loam_destroy(self.h)
+            try:
+                lib().b200_loam_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already torn down
+                pass
             self.h = None
 
     __del__ = close

@@ -240,11 +240,12 @@ __device__ __forceinline__ int table_slot(const Table& t, unsigned long long key
 // One keyframe (or several: `frame_of` maps a point to its pose) through pcl::transformPointCloud and into the table.
 // Voxel cell = floor(p * inverse_leaf) per axis, exactly VoxelGrid's partition; the key orders voxels like VoxelGrid's
 // leaf index does (z slowest, then y, then x).
-__global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, const float* __restrict__ M12, float inv_leaf, Table t,
-                             unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
-    __shared__ float M[12];
-    if (threadIdx.x < 12) M[threadIdx.x] = M12[threadIdx.x];
-    __syncthreads();
+struct PoseM {
+    float m[12];  // row-major 3x4, travels as a kernel argument (no per-keyframe copy)
+};
+__global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM pose, float inv_leaf, Table t, unsigned int* n_voxels,
+                             unsigned int capacity, unsigned int* err) {
+    const float* M = pose.m;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 p = __ldg(pts + i);
         const float x = ((M[0] * p.x + M[1] * p.y) + M[2] * p.z) + M[3];
@@ -418,15 +419,10 @@ struct Builder {
     }
     int32_t add_device(const float4* d_frame, int64_t n, const double* pose7) {
         CUDA_SET_DEVICE(device);
-        // the 48-byte matrix rides in a small pinned ring so that keyframes can be queued back to back
-        const int slot = (int)(frames % 64);
-        CUDA_TRY(h_M.reserve(12 * 64));
-        CUDA_TRY(d_M.reserve(12 * 64));
-        if (slot == 0 && frames > 0) CUDA_TRY(cudaStreamSynchronize(stream));  // the ring is about to be reused
-        pose_matrix(pose7, h_M.p + 12 * slot);
-        CUDA_TRY(cudaMemcpyAsync(d_M.p + 12 * slot, h_M.p + 12 * slot, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        PoseM pm;
+        pose_matrix(pose7, pm.m);
         const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-        k_accumulate<<<blocks, 256, 0, stream>>>(d_frame, n, d_M.p + 12 * slot, inv_leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
+        k_accumulate<<<blocks, 256, 0, stream>>>(d_frame, n, pm, inv_leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
         LAUNCH_COUNT(1);
         ++frames;
         points += n;

@@ -27,7 +27,9 @@ def main():
         hdr, units = rows[0], rows[1]
         stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
         md.append(f"\n## {rep.split('/')[-1]}\n")
-        for r in rows[2:]:
+        import os
+        limit = int(os.environ.get("NCU_SUMMARY_LIMIT", "1000"))
+        for r in rows[2:2 + limit]:
             name = r[hdr.index("Kernel Name")]
             md.append(f"\n### {name.split('(')[0]}  (launch id {r[hdr.index('ID')]})\n\n| metric | value | unit |\n|---|---|---|")
             for w in WANT:
