@@ -58,7 +58,8 @@ class LoamStats(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libb200reg.so")
+    # B200REG_LIB: development override for A/B timing of two builds of the SAME engine (never a different implementation)
+    return os.environ.get("B200REG_LIB") or os.path.join(_HERE, "libb200reg.so")
 
 
 def build(verbose: bool = False) -> str:

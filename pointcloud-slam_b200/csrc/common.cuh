@@ -43,6 +43,30 @@ inline void drop_stale_error(const char* file, int line) {
         CUDA_TRY(cudaSetDevice(dev));                     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor on the
+// stream is still draining; pdl_wait() blocks until the predecessor grid has completed and its writes are visible (a
+// no-op when the kernel was launched normally), pdl_trigger() lets the successor's blocks be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+    static const bool on = !(getenv("B200_PDL") && atoi(getenv("B200_PDL")) == 0);
+    return on;
+}
+template <class... Params, class... Args>
+inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 template <class T>
 struct DevBuf {  // grow-only device buffer
     T* p = nullptr;

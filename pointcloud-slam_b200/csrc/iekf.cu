@@ -128,8 +128,10 @@ struct ObsSmem {
 // whole scan at high occupancy.  Results go to a scratch array that k_obs consumes; the kernel is a
 // no-op when the pass reuses the previous neighbours (decided on the device).
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == 0 ? 5 : 4) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+__global__ void __launch_bounds__(256, (MODE == 0 || MODE == 5) ? 5 : 4) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
                                                 float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
+    pdl_trigger();
+    pdl_wait();
     if (ctl->done || !ctl->converge) return;
     __shared__ PassConsts pc;
     const int tid = threadIdx.x;
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 5 : 4) k_search(MapView map, 
     const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
     uint64_t wkey;
     float4 mine;
-    const int c = knn5_group<KNN_G, MODE>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), wkey, mine);
+    __shared__ uint2 s_flat[MODE >= 5 ? (256 / KNN_G) * kFlatStride : 1];
+    const int c = knn5_group<KNN_G, MODE>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), wkey, mine,
+                                          MODE >= 5 ? s_flat + (tid / KNN_G) * kFlatStride : nullptr);
     if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
     if (lg == 0) nbc_out[q] = (unsigned char)c;
 }
@@ -161,26 +165,34 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
                                                         const unsigned char* __restrict__ nbc_new, PointState ps, Ctl* ctl, float thr,
                                                         int ext, double* partials, int max_iter, double Rcov,
                                                         const double* __restrict__ limit, int single_pass) {
+    pdl_trigger();
+    pdl_wait();
     if (ctl->done) return;
     __shared__ ObsSolveSmem smu;
     if (blockIdx.x == 0) {
         const int nworkers = (int)gridDim.x - 1;
+#ifdef B200_STAMPS
         const int pass_f = ctl->passes;
         const long long tf0 = clock64();
+#endif
         if (!single_pass) iekf_presolve(ctl, Rcov, ext, smu.solve);
         else if (threadIdx.x < 26) smu.solve.x[threadIdx.x] = ctl->x[threadIdx.x];
+#ifdef B200_STAMPS
         const long long tf1 = clock64();
+#endif
         if (threadIdx.x == 0) {
             volatile unsigned int* tk = &ctl->ticket;
-            while (*tk < (unsigned)nworkers) __nanosleep(100);
+            while (*tk < (unsigned)nworkers) __nanosleep(40);
             ctl->ticket = 0;
+#ifdef B200_STAMPS
             if (pass_f < B200_MAX_PASSES) {
                 ctl->dbg[pass_f][8] = tf1 - tf0;         // presolve cycles
                 ctl->dbg[pass_f][9] = clock64() - tf1;   // wait-for-workers cycles
             }
+#endif
+            __threadfence();  // acquire: the partials are read with ld.cg after the barrier below
         }
         __syncthreads();
-        __threadfence();
         iekf_postsolve(ctl, partials, nworkers, max_iter, limit, ext, single_pass, smu.solve);
         return;
     }
@@ -193,24 +205,29 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
     if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
     __syncthreads();
 
-    // Accumulators: the block's queries are cut into NSLICE contiguous slices per tile; thread
-    // (slice, col) owns column col (78 HTH pairs, 12 HTh entries, 1 count) of its slice across all tiles.
-    constexpr int NSLICE = OBS_THREADS / NPART;  // 5
-    const int slice = tid / NPART, col = tid % NPART;
+    // Accumulators: the block's queries are cut into nslice contiguous slices per tile; thread (slice, col) owns active
+    // column col (solve.cuh: 21 + 6 + 1 columns without extrinsic estimation, 78 + 12 + 1 with) of its slice across
+    // all tiles.  Fixed slice boundaries and query order: the sums are deterministic.
+    const int ncol = ext ? NPART : NCOL6;
+    const int nslice = OBS_THREADS / ncol;  // 5 or 18
+    const int slice = tid / ncol, col = tid % ncol;
     double acc = 0.0;
-    int pa = 0, pb_ = 0;
-    if (col < 78) { pa = c_pair_a[col]; pb_ = c_pair_b[col]; }
-    else if (col < 90) { pa = col - 78; pb_ = 12; }
-    const bool slice_active = slice < NSLICE;
-    const bool pair_active = slice_active && col < 90 && (ext || (pa < 6 && (pb_ < 6 || pb_ == 12)));
+    const int pa = c_col_a[ext ? 1 : 0][col], pb_ = c_col_b[ext ? 1 : 0][col];
+    const bool slice_active = slice < nslice;
+    const bool pair_active = slice_active && pa != 255;
 
+#ifdef B200_STAMPS
     long long tw0 = clock64(), tw1 = tw0, tw2 = tw0, tw3 = tw0;
+#define WSTAMP(v) v = clock64()
+#else
+#define WSTAMP(v) do { } while (0)
+#endif
     // each worker owns one contiguous chunk of the scan, processed in rounds of <= QCAP queries
     const int chunk = (n + wgrid - 1) / wgrid;
     const int c_begin = wblock * chunk, c_end = min(n, c_begin + chunk);
     for (int base = c_begin; base < c_end; base += QCAP) {
         const int q_here = min(QCAP, c_end - base);
-        tw1 = clock64();
+        WSTAMP(tw1);
         // phase 2: one thread per query
         if (tid < q_here) {
             const int i = base + tid;
@@ -227,15 +244,15 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
             }
         }
         __syncthreads();
-        tw2 = clock64();
+        WSTAMP(tw2);
         // phase 3: fp64 accumulation, fixed slice boundaries and query order (deterministic)
         {
-            const int per = (q_here + NSLICE - 1) / NSLICE;
+            const int per = (q_here + nslice - 1) / nslice;
             const int q0 = slice * per, q1 = min(q_here, q0 + per);
             if (pair_active) {
                 for (int q = q0; q < q1; ++q)
                     if (sm.eff[q]) acc += (double)sm.rows[q][pa] * (double)sm.rows[q][pb_];
-            } else if (slice_active && col == 90) {
+            } else if (slice_active) {
                 for (int q = q0; q < q1; ++q) acc += (double)sm.eff[q];
             }
         }
@@ -244,16 +261,16 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
     // combine the slices in a fixed order, then publish column-major by block so the filter block
     // reads each column coalesced
     double* red = (double*)&sm.rows[0][0];
-    if (slice_active) red[slice * NPART + col] = acc;
+    if (slice_active) red[slice * ncol + col] = acc;
     __syncthreads();
-    if (tid < NPART) {
+    if (tid < ncol) {
         double v = red[tid];
-#pragma unroll
-        for (int sl = 1; sl < NSLICE; ++sl) v += red[sl * NPART + tid];
+        for (int sl = 1; sl < nslice; ++sl) v += red[sl * ncol + tid];
         __stcg(partials + (size_t)tid * wgrid + wblock, v);
+        __threadfence();  // release: only the publishing threads need it
     }
-    __threadfence();
     __syncthreads();
+#ifdef B200_STAMPS
     tw3 = clock64();
     if (tid == 0 && wblock == 0) {
         const int pw_ = ctl->passes;
@@ -263,6 +280,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
             ctl->dbg[pw_][12] = tw3 - tw2;  // accumulate + publish
         }
     }
+#endif
     if (tid == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
@@ -371,6 +389,20 @@ static void init_pair_tables() {
         for (int j = i; j < 12; ++j) { a[k] = (unsigned char)i; b[k] = (unsigned char)j; ++k; }
     cudaMemcpyToSymbol(c_pair_a, a, sizeof a);
     cudaMemcpyToSymbol(c_pair_b, b, sizeof b);
+    // active accumulator columns: [0] without extrinsic estimation (leading 6 x 6 block), [1] with (all 12 x 12)
+    unsigned char ca[2][NPART], cb[2][NPART];
+    memset(ca, 255, sizeof ca);
+    memset(cb, 255, sizeof cb);
+    for (int mode = 0; mode < 2; ++mode) {
+        const int m = mode ? 12 : 6;
+        int c = 0;
+        for (int i = 0; i < m; ++i)
+            for (int j = i; j < m; ++j) { ca[mode][c] = (unsigned char)i; cb[mode][c] = (unsigned char)j; ++c; }
+        for (int i = 0; i < m; ++i) { ca[mode][c] = (unsigned char)i; cb[mode][c] = 12; ++c; }
+        // column c (= 27 or 90) stays (255, 255): the effective-point counter
+    }
+    cudaMemcpyToSymbol(c_col_a, ca, sizeof ca);
+    cudaMemcpyToSymbol(c_col_b, cb, sizeof cb);
 }
 
 int32_t Iekf::init(const b200_iekf_params* p, Map* m) {
@@ -447,11 +479,14 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
     const MapView mv = map->view();
     const int npass = single_pass ? 1 : prm.max_iter + 1;
     for (int it = 0; it < npass; ++it) {
-        if (map->knn_mode() == 1) k_search<1><<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
-        else k_search<0><<<search_grid, 256, 0, stream>>>(mv, d_pts, d_ctl, d_nb.p, d_nbc.p);
+        const int mode = map->knn_mode();
+        const bool pdl = !events;  // kernel -> kernel edges only (an event record in between makes it a full dependency anyway)
+        auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 1 ? k_search<1> : k_search<0>;
+        CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
-        k_obs<<<nblocks, OBS_THREADS, 0, stream>>>(d_pts, d_nb.p, d_nbc.p, ps, d_ctl, prm.plane_thr, prm.extrinsic_est_en, d_partials,
-                                                   prm.max_iter, prm.R, d_limit, single_pass);
+        CUDA_TRY(launch_k(k_obs, dim3(nblocks), dim3(OBS_THREADS), stream, pdl, d_pts, (const float4*)d_nb.p, (const unsigned char*)d_nbc.p, ps,
+                          d_ctl, prm.plane_thr, (int)prm.extrinsic_est_en, d_partials, (int)prm.max_iter, prm.R, (const double*)d_limit,
+                          single_pass));
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
     }
     n_kernels = events ? e - 1 : 0;

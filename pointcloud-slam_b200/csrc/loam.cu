@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 5 : 4) k_loam_search(MapView 
                 z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];  // pointAssociateToMap (:439-445)
     uint64_t wkey;
     float4 mine;
-    const int c = knn5_group<G, MODE>(map, x, y, z, lg, gmask, lane_stencil<G>(lg, map.nstencil), wkey, mine);
+    __shared__ uint2 s_flat[MODE == 5 ? (256 / G) * kFlatStride : 1];
+    const int c = knn5_group<G, MODE>(map, x, y, z, lg, gmask, lane_stencil<G>(lg, map.nstencil), wkey, mine,
+                                      MODE == 5 ? s_flat + (tid / G) * kFlatStride : nullptr);
     if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
     if (lg == 0) cnt_out[q] = (unsigned char)c;
 }
@@ -399,12 +401,14 @@ static void loam_search(b200_loam* h, int64_t nc, int64_t ns) {
     using namespace loam;
     if (nc) {
         const unsigned grid = (unsigned)((nc * G + 255) / 256);
-        if (h->corner.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
+        if (h->corner.knn_mode() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
+        else if (h->corner.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
         else k_loam_search<0><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
     }
     if (ns) {
         const unsigned grid = (unsigned)((ns * G + 255) / 256);
-        if (h->surf.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
+        if (h->surf.knn_mode() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
+        else if (h->surf.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
         else k_loam_search<0><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
     }
     LAUNCH_COUNT((nc ? 1 : 0) + (ns ? 1 : 0));

@@ -10,6 +10,11 @@
 namespace b200 {
 namespace mf {
 
+// The filter step runs these once per pass on a single thread, so their cost is the length of the dependent fp64 chain
+// (divisions, sqrt, sin / cos / atan).  Out-of-line copies were measured SLOWER on B200: the first call into far code
+// misses the instruction cache line by line (~30 cycles per instruction), inlined straight-line code streams.
+#define MF_COLD __device__ inline
+
 constexpr double kTol = 1e-11;
 constexpr double kGravLen = 98090.0 / 10000.0;
 
@@ -76,20 +81,20 @@ __device__ inline void cos_sinc_sqrt(double x2, double& c, double& sinc) {
     c = cosi;
     sinc = s;
 }
-__device__ inline Q so3_exp(const double* v, double scale_half) {
+MF_COLD Q so3_exp(const double* v, double scale_half) {
     double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     double c, sinc;
     cos_sinc_sqrt(scale_half * scale_half * n2, c, sinc);
     double mult = sinc * scale_half;
     return Q{mult * v[0], mult * v[1], mult * v[2], c};
 }
-__device__ inline void so3_log(const Q& q, double* r) {
+MF_COLD void so3_log(const Q& q, double* r) {
     double nv = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
     if (nv < kTol) nv = kTol;
     double s = 2.0 / nv * atan(nv / q.w);
     r[0] = s * q.x; r[1] = s * q.y; r[2] = s * q.z;
 }
-__device__ inline void A_matrix(const double* v, double* res) {
+MF_COLD void A_matrix(const double* v, double* res) {
     double sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     double n = sqrt(sq);
     for (int i = 0; i < 9; ++i) res[i] = (i % 4 == 0) ? 1.0 : 0.0;
@@ -100,23 +105,27 @@ __device__ inline void A_matrix(const double* v, double* res) {
     double a = (1 - cos(n)) / sq, b = (1 - sin(n) / n) / sq;
     for (int i = 0; i < 9; ++i) res[i] = res[i] + a * H[i] + b * HH[i];
 }
-__device__ inline void S2_Bx(const double* vec, double* Bx /*3x2*/) {
+MF_COLD void S2_Bx(const double* vec, double* Bx /*3x2*/) {
     const double len = kGravLen;
     if (vec[0] + len > kTol) {
-        Bx[0] = -vec[1];
-        Bx[1] = -vec[2];
-        Bx[2] = len - vec[1] * vec[1] / (len + vec[0]);
-        Bx[3] = -vec[2] * vec[1] / (len + vec[0]);
-        Bx[4] = -vec[2] * vec[1] / (len + vec[0]);
-        Bx[5] = len - vec[2] * vec[2] / (len + vec[0]);
-        for (int i = 0; i < 6; ++i) Bx[i] /= len;
+        // S2.hpp:166-200 divides ten times; the two denominators are inverted once instead (1 ulp apart, far inside
+        // the parity tolerance) because each fp64 division is a ~40-instruction dependent chain on the filter's critical path
+        const double rden = 1.0 / (len + vec[0]);
+        constexpr double rlen = 1.0 / kGravLen;
+        const double yz = -vec[2] * vec[1] * rden;
+        Bx[0] = -vec[1] * rlen;
+        Bx[1] = -vec[2] * rlen;
+        Bx[2] = (len - vec[1] * vec[1] * rden) * rlen;
+        Bx[3] = yz * rlen;
+        Bx[4] = yz * rlen;
+        Bx[5] = (len - vec[2] * vec[2] * rden) * rlen;
     } else {
         for (int i = 0; i < 6; ++i) Bx[i] = 0;
         Bx[3] = -1;
         Bx[4] = 1;
     }
 }
-__device__ inline void S2_boxplus(double* vec, const double* delta) {
+MF_COLD void S2_boxplus(double* vec, const double* delta) {
     double Bx[6], Bu[3], R[9], r[3];
     S2_Bx(vec, Bx);
     for (int i = 0; i < 3; ++i) Bu[i] = Bx[i * 2] * delta[0] + Bx[i * 2 + 1] * delta[1];
@@ -125,7 +134,7 @@ __device__ inline void S2_boxplus(double* vec, const double* delta) {
     for (int i = 0; i < 3; ++i) r[i] = R[i * 3] * vec[0] + R[i * 3 + 1] * vec[1] + R[i * 3 + 2] * vec[2];
     vec[0] = r[0]; vec[1] = r[1]; vec[2] = r[2];
 }
-__device__ inline void S2_boxminus(const double* vec, const double* other, double* res) {
+MF_COLD void S2_boxminus(const double* vec, const double* other, double* res) {
     double c[3];
     cross(vec, other, c);
     double v_sin = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
@@ -142,7 +151,7 @@ __device__ inline void S2_boxminus(const double* vec, const double* other, doubl
         for (int j = 0; j < 2; ++j) res[j] = (f * Bx[j]) * hv[0] + (f * Bx[2 + j]) * hv[1] + (f * Bx[4 + j]) * hv[2];
     }
 }
-__device__ inline void S2_Nx_yy(const double* vec, double* Nx /*2x3*/) {
+MF_COLD void S2_Nx_yy(const double* vec, double* Nx /*2x3*/) {
     double Bx[6], H[9];
     S2_Bx(vec, Bx);
     hat(vec, H);
@@ -150,7 +159,7 @@ __device__ inline void S2_Nx_yy(const double* vec, double* Nx /*2x3*/) {
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 3; ++j) Nx[i * 3 + j] = (f * Bx[i]) * H[j] + (f * Bx[2 + i]) * H[3 + j] + (f * Bx[4 + i]) * H[6 + j];
 }
-__device__ inline void S2_Mx(const double* vec, const double* delta, double* Mx /*3x2*/) {
+MF_COLD void S2_Mx(const double* vec, const double* delta, double* Mx /*3x2*/) {
     double Bx[6], H[9];
     S2_Bx(vec, Bx);
     hat(vec, H);

@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restric
     float4 p = __ldg(q + gid);
     uint64_t w;
     float4 mine;
-    int c = knn5_group<G, MODE>(m, p.x, p.y, p.z, lg, gmask, lane_stencil<G>(lg, m.nstencil), w, mine);
+    __shared__ uint2 s_flat[MODE == 5 ? (256 / G) * kFlatStride : 1];
+    int c = knn5_group<G, MODE>(m, p.x, p.y, p.z, lg, gmask, lane_stencil<G>(lg, m.nstencil), w, mine,
+                                MODE == 5 ? s_flat + (threadIdx.x / G) * kFlatStride : nullptr);
     if (lg < 5) {
         idx[gid * 5 + lg] = __float_as_int(mine.w);
         d2[gid * 5 + lg] = (w == kInfKey) ? 0.0f : __uint_as_float((uint32_t)(w >> 32));
@@ -511,7 +513,9 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     CUDA_TRY(cudaEventRecord(ev0, stream));
     {
         const unsigned grid = (unsigned)((threads + 255) / 256);
-        if (knn_mode() == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        const int mode = knn_mode();
+        if (mode >= 5) k_knn5<G, 5><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        else if (mode == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         else k_knn5<G, 0><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
     }
     CUDA_TRY(cudaEventRecord(ev1, stream));

@@ -110,9 +110,17 @@ __device__ __forceinline__ uint32_t lane_stencil(int lg, int nstencil) {
 #ifndef B200_KNN_MODE
 #define B200_KNN_MODE 0
 #endif
+// MODE 5 ("flattened"): the (cell, in-voxel index) pairs of all occupied stencil cells of a query are written as one list
+// into shared memory (kFlatCap entries per query) and the G lanes then take the list G entries at a time, four steps in
+// flight: every lane handles total/G candidates whatever the occupancy pattern of its own cells (two thirds of the cells
+// of a surface map are empty), so the divergent per-cell loops of MODE 0 disappear and all gathers of a query are
+// independent loads.  Queries with more than kFlatCap candidates (dense, long-lived maps) fall back to the cooperative
+// walk of MODE 1, decided per query.
+constexpr int kFlatCap = 64;
+constexpr int kFlatStride = kFlatCap + 1;  // uint2 entries per query list; odd stride spreads the groups of a warp over the banks
 template <int G, int MODE = B200_KNN_MODE>
 __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, float qz, int lg, unsigned gmask, uint32_t lst,
-                                          uint64_t& wkey, float4& mine) {
+                                          uint64_t& wkey, float4& mine, uint2* flat = nullptr) {
     constexpr int SLOTS = (27 + G - 1) / G;
     static_assert(SLOTS <= 4, "lane_stencil packs four cells per lane");
     static_assert(G >= 8, "lanes 0..4 of the group hold the running top-5");
@@ -164,7 +172,43 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
     // MODE 2/3: runs of <= SHORT points stay with the probing lane (2: two points of every cell of the lane in flight
     //           together, 3: cell by cell, four points in flight), longer runs are walked by the group
     // MODE 4: like 3 when the query's stencil holds more than DENSE candidates in total, like 0 otherwise (decided per query)
-    int SHORT = MODE == 0 ? (1 << 30) : MODE == 1 ? 0 : MODE == 2 ? 2 : 4;
+    int SHORT = MODE == 0 ? (1 << 30) : (MODE == 1 || MODE >= 5) ? 0 : MODE == 2 ? 2 : 4;
+    bool flat_done = false;
+    if (MODE >= 5) {
+        int mytot = 0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) mytot += ccount[t];
+        int incl = mytot;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const int v = __shfl_up_sync(gmask, incl, o, G);
+            if (lg >= o) incl += v;
+        }
+        const int total = __shfl_sync(gmask, incl, lane0 + G - 1);
+        if (total <= kFlatCap) {  // uniform inside the group
+            flat_done = true;
+            int w = incl - mytot;
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) {
+                const uint32_t rbase = (uint32_t)(lg + G * t) << kRankBits;
+                for (int j = 0; j < ccount[t]; ++j) flat[w++] = make_uint2((uint32_t)(cstart[t] + j), rbase | (uint32_t)j);
+            }
+            __syncwarp(gmask);
+            for (int c0 = lg; c0 < total; c0 += 4 * G) {
+                uint2 e[4];
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u * G < total) e[u] = flat[c0 + u * G];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u * G < total) p[u] = __ldg(m.pool + e[u].x);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u * G < total) consider(p[u], e[u].y);
+            }
+        }
+    }
     if (MODE == 4) {
         constexpr int DENSE = 80;
         int tot = 0;
@@ -204,7 +248,7 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
             for (int u = 0; u < 2; ++u)
                 if (ccount[t] <= SHORT && u < ccount[t]) consider(p[t][u], ((uint32_t)(lg + G * t) << kRankBits) | (uint32_t)u);
     }
-    if (MODE != 0) {
+    if (MODE != 0 && !flat_done) {
         // longer runs are walked by the whole group: G consecutive points per step (one or two 128-byte lines per query
         // instead of G scattered gathers), four steps in flight.  Which lane sees a candidate does not matter: the key
         // carries the full enumeration rank.
@@ -305,7 +349,7 @@ struct Map {
     // (measured on B200: 27 vs 47 us at 3 points/voxel, 100 vs 52 us at 25 points/voxel, 20k queries).
     int knn_mode() const {
         static const char* env = getenv("B200_KNN_MODE");
-        if (env) return atoi(env) ? 1 : 0;
+        if (env) return atoi(env) >= 5 ? atoi(env) : atoi(env) ? 1 : 0;
         return h_ctr.num_voxels > 0 && h_ctr.live_points > 6ull * h_ctr.num_voxels ? 1 : 0;
     }
     MapView view() const {

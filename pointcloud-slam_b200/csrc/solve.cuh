@@ -51,6 +51,13 @@ struct Ctl {
 
 static __constant__ unsigned char c_pair_a[78];
 static __constant__ unsigned char c_pair_b[78];
+// Active accumulator columns.  Without extrinsic estimation only the leading 6 x 6 block of h_x^T h_x and the first 6
+// entries of h_x^T h are non-zero (laser_mapping.cc:687-694), so a pass accumulates, publishes and reduces
+// NCOL6 = 21 + 6 + 1 columns instead of NPART = 78 + 12 + 1.  Column c multiplies row entries (a, b): b == 12 is the
+// residual h, a == 255 marks the effective-point counter.
+constexpr int NCOL6 = 28;
+static __constant__ unsigned char c_col_a[2][NPART];
+static __constant__ unsigned char c_col_b[2][NPART];
 
 __device__ inline void make_pass_consts(const double* x, PassConsts& pc) {
     using namespace mf;
@@ -91,11 +98,30 @@ struct SolveSmem {
     int conv;
 };
 
+// Stage stamps (clock64 into ctl->dbg) are a development aid, compiled in with -DB200_STAMPS only: the global stores and
+// the ordering they impose were measured to cost several microseconds per pass on the filter block's critical path.
+#ifdef B200_STAMPS
 #define STAMP(i) do { if (threadIdx.x == 0 && pass < B200_MAX_PASSES) ctl->dbg[pass][i] = clock64(); } while (0)
+#else
+#define STAMP(i) do { } while (0)
+#endif
 
 // In-register inverse of a symmetric positive-definite M x M matrix by ONE warp: Gauss-Jordan on
 // [A | I] without pivoting (safe for SPD); lane c < 2M owns column c of the augmented matrix.
 // src/dst are row-major with stride ld.
+// 1/x to fp64 accuracy without the IEEE division sequence: hardware seed (about 20 bits) + two Newton steps.  Only used
+// on pivots of SPD matrices (positive, normal range).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int M>
 __device__ inline void warp_inverse_spd(const double* src, double* dst, int ld) {
     const int lane = threadIdx.x & 31;
@@ -110,7 +136,7 @@ __device__ inline void warp_inverse_spd(const double* src, double* dst, int ld) 
 #pragma unroll
     for (int k = 0; k < M; ++k) {
         const double pivot = __shfl_sync(0xffffffffu, col[k], k);
-        const double prow = col[k] * (1.0 / pivot);
+        const double prow = col[k] * fast_rcp(pivot);
 #pragma unroll
         for (int r = 0; r < M; ++r) {
             if (r != k) {
@@ -159,6 +185,38 @@ __device__ inline void project_cols(double* M, const SolveSmem& s, int which) {
         M[i * NS + 21] = a * s.J2[0] + b * s.J2[1];
         M[i * NS + 22] = a * s.J2[2] + b * s.J2[3];
     }
+}
+
+// Row i of the block-diagonal re-linearisation Jacobian J = diag(I3, J_rot, J_offR, I12, J_grav): the block's first
+// index, its width and the row of coefficients.
+__device__ __forceinline__ void jrow(const SolveSmem& s, int i, int& base, double& c0, double& c1, double& c2) {
+    if (i >= 3 && i < 9) {
+        const int k = i < 6 ? 0 : 1;
+        base = k == 0 ? 3 : 6;
+        const double* J = s.J3[k] + (i - base) * 3;
+        c0 = J[0]; c1 = J[1]; c2 = J[2];
+    } else if (i >= 21) {
+        base = 21;
+        c0 = s.J2[(i - 21) * 2]; c1 = s.J2[(i - 21) * 2 + 1]; c2 = 0.0;
+    } else {
+        base = i;
+        c0 = 1.0; c1 = 0.0; c2 = 0.0;
+    }
+}
+// (J M J^T)[i][j] for a 23 x 23 row-major M: the three manifold blocks at once (the reference applies them one after
+// the other, esekfom.hpp:1561-1601; the blocks are disjoint, so the product is the same up to rounding).  Always a
+// 3 x 3 stencil with zero coefficients (and clamped indices) outside the block: no data-dependent loops.
+__device__ __forceinline__ double project_elem(const SolveSmem& s, const double* M, int i, int j) {
+    int bi, bj;
+    double a0, a1, a2, b0, b1, b2;
+    jrow(s, i, bi, a0, a1, a2);
+    jrow(s, j, bj, b0, b1, b2);
+    const int r0 = bi, r1 = min(bi + 1, NS - 1), r2 = min(bi + 2, NS - 1);
+    const int q0 = bj, q1 = min(bj + 1, NS - 1), q2 = min(bj + 2, NS - 1);
+    const double t0 = fma(M[r0 * NS + q2], b2, fma(M[r0 * NS + q1], b1, M[r0 * NS + q0] * b0));
+    const double t1 = fma(M[r1 * NS + q2], b2, fma(M[r1 * NS + q1], b1, M[r1 * NS + q0] * b0));
+    const double t2 = fma(M[r2 * NS + q2], b2, fma(M[r2 * NS + q1], b1, M[r2 * NS + q0] * b0));
+    return fma(a2, t2, fma(a1, t1, a0 * t0));
 }
 
 // Jacobians of the (+)/(-) re-linearisation for the tangent increment d (esekfom.hpp:1561-1601, 1739-1789).
@@ -237,9 +295,14 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int pass = ctl->passes;
     STAMP(0);
-    // 1. deterministic reduction of the per-block partial sums: warp w owns columns w, w+nwarp, ...;
-    //    lanes stride over blocks in a fixed order, then a fixed shuffle tree.
-    for (int col0 = warp; col0 < NPART; col0 += 2 * nwarp) {
+    // 1. deterministic reduction of the per-block partial sums (active columns only): warp w owns columns w and
+    //    w + nwarp, ...; lanes stride over blocks in a fixed order, then a fixed shuffle tree.
+    const int ncol = ext ? NPART : NCOL6;
+    for (int i = tid; i < 144 + 12; i += nt) {
+        if (i < 144) s.HTH[i] = 0.0; else s.HTh[i - 144] = 0.0;
+    }
+    __syncthreads();
+    for (int col0 = warp; col0 < ncol; col0 += 2 * nwarp) {
         double v[2][MAXB / 32];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -247,7 +310,7 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
 #pragma unroll
             for (int j = 0; j < MAXB / 32; ++j) {
                 const int b = lane + 32 * j;
-                v[u][j] = (col < NPART && b < nblocks) ? __ldcg(partials + (size_t)col * nblocks + b) : 0.0;
+                v[u][j] = (col < ncol && b < nblocks) ? __ldcg(partials + (size_t)col * nblocks + b) : 0.0;
             }
         }
 #pragma unroll
@@ -257,15 +320,15 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
 #pragma unroll
             for (int j = 0; j < MAXB / 32; ++j) sum += v[u][j];
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0 && col < NPART) {
-                if (col < 78) {
-                    const int a = c_pair_a[col], b = c_pair_b[col];
+            if (lane == 0 && col < ncol) {
+                const int a = c_col_a[ext ? 1 : 0][col], b = c_col_b[ext ? 1 : 0][col];
+                if (a == 255) {
+                    s.n_eff = (int)(sum + 0.5);
+                } else if (b == 12) {
+                    s.HTh[a] = sum;
+                } else {
                     s.HTH[a * 12 + b] = sum;
                     s.HTH[b * 12 + a] = sum;
-                } else if (col < 90) {
-                    s.HTh[col - 78] = sum;
-                } else {
-                    s.n_eff = (int)(sum + 0.5);
                 }
             }
         }
@@ -374,46 +437,48 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
     if (tid < 26) ctl->x[tid] = s.x[tid];
     if (s.finalize) {  // :1735-1831
         make_projection_par(s, s.dxu, s.x, s.xp);
-        for (int i = tid; i < NS * NS; i += nt) s.L[i] = s.P[i];
         __syncthreads();
         STAMP(6);
-        for (int which = 0; which < 3; ++which) {
-            project_rows(s.L, s.P, s, which, NS, NS);  // L rows <- J * P rows
-            if (tid >= 32 && tid < 32 + 12) {          // K_x rows <- J * K_x rows
-                const int c = tid - 32;
-                if (which < 2) {
-                    const int idx = which == 0 ? 3 : 6;
-                    const double* J = s.J3[which];
-                    const double a = s.Kx[idx * 12 + c], b = s.Kx[(idx + 1) * 12 + c], d = s.Kx[(idx + 2) * 12 + c];
-                    for (int r = 0; r < 3; ++r) s.Kx[(idx + r) * 12 + c] = J[r * 3] * a + J[r * 3 + 1] * b + J[r * 3 + 2] * d;
-                } else {
-                    const double a = s.Kx[21 * 12 + c], b = s.Kx[22 * 12 + c];
-                    s.Kx[21 * 12 + c] = s.J2[0] * a + s.J2[1] * b;
-                    s.Kx[22 * 12 + c] = s.J2[2] * a + s.J2[3] * b;
-                }
+        // L = J P J^T and K_x <- J K_x in one step (esekfom.hpp:1739-1789 applies the blocks one after the other)
+        {
+            double v[2] = {0.0, 0.0}, kx = 0.0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * nt;
+                if (e < NS * NS) v[u] = project_elem(s, s.P, e / NS, e % NS);
+            }
+            if (tid < NS * 12) {
+                int bi;
+                double a0, a1, a2;
+                jrow(s, tid / 12, bi, a0, a1, a2);
+                const int c = tid % 12;
+                kx = fma(a2, s.Kx[min(bi + 2, NS - 1) * 12 + c], fma(a1, s.Kx[min(bi + 1, NS - 1) * 12 + c], a0 * s.Kx[bi * 12 + c]));
             }
             __syncthreads();
-            project_cols(s.L, s, which);
-            if (tid >= 32 && tid < 32 + NS) {  // same column transform of P on another warp
-                const int i = tid - 32;
-                if (which < 2) {
-                    const int idx = which == 0 ? 3 : 6;
-                    const double* J = s.J3[which];
-                    const double a = s.P[i * NS + idx], b = s.P[i * NS + idx + 1], d = s.P[i * NS + idx + 2];
-                    for (int r = 0; r < 3; ++r) s.P[i * NS + idx + r] = a * J[r * 3] + b * J[r * 3 + 1] + d * J[r * 3 + 2];
-                } else {
-                    const double a = s.P[i * NS + 21], b = s.P[i * NS + 22];
-                    s.P[i * NS + 21] = a * s.J2[0] + b * s.J2[1];
-                    s.P[i * NS + 22] = a * s.J2[2] + b * s.J2[3];
-                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + u * nt;
+                if (e < NS * NS) s.L[e] = v[u];
             }
+            if (tid < NS * 12) s.Kx[tid] = kx;
             __syncthreads();
         }
+        // P_final = L - K_x (P J^T)[:12, :]
         for (int idx = tid; idx < NS * NS; idx += nt) {
             const int r = idx / NS, c = idx % NS;
-            double sum = 0.0;
-            for (int k = 0; k < 12; ++k) sum += s.Kx[r * 12 + k] * s.P[k * NS + c];
-            ctl->P[idx] = s.L[idx] - sum;
+            int bc;
+            double b0, b1, b2;
+            jrow(s, c, bc, b0, b1, b2);
+            const int q1 = min(bc + 1, NS - 1), q2 = min(bc + 2, NS - 1);
+            double sum0 = 0.0, sum1 = 0.0;  // two independent chains
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) {
+                const double pj0 = fma(s.P[k * NS + q2], b2, fma(s.P[k * NS + q1], b1, s.P[k * NS + bc] * b0));
+                const double pj1 = fma(s.P[(k + 1) * NS + q2], b2, fma(s.P[(k + 1) * NS + q1], b1, s.P[(k + 1) * NS + bc] * b0));
+                sum0 = fma(s.Kx[r * 12 + k], pj0, sum0);
+                sum1 = fma(s.Kx[r * 12 + k + 1], pj1, sum1);
+            }
+            ctl->P[idx] = s.L[idx] - (sum0 + sum1);
         }
         if (tid == 0) {
             ctl->converge = s.conv;

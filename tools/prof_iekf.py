@@ -20,7 +20,7 @@ st = (C.c_longlong * (8 * 16))()
 api.lib().b200_iekf_debug_stamps(kf.h, st)
 for p in range(kf.stats.passes):
     v = [st[p * 16 + i] for i in range(8)]
-    print('pass', p, 'post', [v[i + 1] - v[i] for i in range(7)], 'tot', v[7] - v[0], '| pre', st[p*16+8], 'wait', st[p*16+9], '| search/measure/accum', st[p*16+10], st[p*16+11], st[p*16+12])
+    print('pass', p, 'post', [v[i + 1] - v[i] for i in range(7)], 'tot', v[7] - v[0], '| pre', st[p*16+8], 'wait', st[p*16+9], '| search/measure/accum', st[p*16+10], st[p*16+11], st[p*16+12], '| pre stages', st[p*16+13], st[p*16+14], st[p*16+15])
 # per-kernel event timing (no graph)
 api.lib().b200_iekf_set_profiling(kf.h, 1)
 for r in range(3):
