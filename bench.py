@@ -381,7 +381,8 @@ def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
             "ms_update_device_median": float(np.median(ms_update)),
             "map_voxels": voxels, "map_points": points, "final_position_error_m": drift,
             "parity_vs_oracle": {"scans": len(par), "max_state_diff": max(par) if par else None,
-                                 "note": "both filters fed the same priors; posterior and inserted points compared per scan"}}
+                                 "note": "both filters fed the same priors; posterior and inserted points compared per scan"},
+            **({"trace_ms_update_device": [round(v, 4) for v in ms_update]} if os.environ.get("B200_SEQ_TRACE") else {})}
 
 
 def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):

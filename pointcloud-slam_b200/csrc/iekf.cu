@@ -18,6 +18,7 @@
 #include "solve.cuh"
 
 #include <cub/cub.cuh>
+#include <chrono>
 #include <vector>
 
 namespace b200 {
@@ -481,7 +482,7 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
     for (int it = 0; it < npass; ++it) {
         const int mode = map->knn_mode();
         const bool pdl = !events;  // kernel -> kernel edges only (an event record in between makes it a full dependency anyway)
-        auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 1 ? k_search<1> : k_search<0>;
+        auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 4 ? k_search<4> : mode == 1 ? k_search<1> : k_search<0>;
         CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
         CUDA_TRY(launch_k(k_obs, dim3(nblocks), dim3(OBS_THREADS), stream, pdl, d_pts, (const float4*)d_nb.p, (const unsigned char*)d_nbc.p, ps,
@@ -621,11 +622,21 @@ static int32_t stage_scan(Iekf& k, const float* xyz, int64_t n, int64_t stride, 
 int32_t b200_iekf_update(b200_iekf* ekf, const float* scan, int64_t n, int64_t stride, double* x26, double* P, b200_iekf_stats* stats) {
     if (!ekf || !scan || !x26 || !P || n < 1 || stride < 12 || n > (1 << 26)) B200_FAIL(B200_ERR_ARG, "bad argument");
     Iekf& k = ekf->k;
+    static const bool timing = getenv("B200_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     CUDA_SET_DEVICE(k.map->device);
     int32_t rc = stage_scan(k, scan, n, stride, x26, P);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     const size_t hdr_pad = (offsetof(Ctl, x_prop) + 255) / 256 * 256;
-    return k.run((const float4*)((const uint8_t*)k.d_scan.p + hdr_pad), (int)n, (const Ctl*)k.d_scan.p, x26, P, stats, 0, 1);
+    rc = k.run((const float4*)((const uint8_t*)k.d_scan.p + hdr_pad), (int)n, (const Ctl*)k.d_scan.p, x26, P, stats, 0, 1);
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200_iekf_update] stage (pack + H2D enqueue) %.1f us, run (launch + kernels + D2H + sync) %.1f us, device %.1f us\n",
+                std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count(),
+                stats ? stats->gpu_ms * 1e3 : 0.0);
+    }
+    return rc;
 }
 
 int32_t b200_iekf_update_device(b200_iekf* ekf, const void* d_scan_float4, int64_t n, double* x26, double* P, b200_iekf_stats* stats) {

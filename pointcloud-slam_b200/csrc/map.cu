@@ -79,6 +79,7 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     run_reloc[r] = reloc;
     run_oldcnt[r] = v.y;
     atomicAdd(&ctr->live_points, (unsigned long long)c);
+    if ((unsigned)newcount > ctr->max_count) atomicMax(&ctr->max_count, (unsigned)newcount);
     v.y = newcount;
     v.w = stamp;
     ent[slot].start = v.x;
@@ -515,6 +516,7 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
         const unsigned grid = (unsigned)((threads + 255) / 256);
         const int mode = knn_mode();
         if (mode >= 5) k_knn5<G, 5><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        else if (mode == 4) k_knn5<G, 4><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         else if (mode == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         else k_knn5<G, 0><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
     }

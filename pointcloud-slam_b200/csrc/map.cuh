@@ -24,6 +24,8 @@ struct MapCounters {
     unsigned int err_capacity; // voxel capacity reached
     unsigned long long num_points;
     unsigned long long live_points;  // sum of run counts (== num_points while nothing is evicted)
+    unsigned int max_count;          // largest run any voxel has ever had (never decreases: picks the search walk)
+    unsigned int pad;
 };
 
 struct __align__(16) MapEntry {
@@ -345,12 +347,15 @@ struct Map {
     DevBuf<float> q_d2;
 
     // Candidate-walk variant of the search kernels, picked per launch from the map's density: lane-owned cells (0) win while
-    // voxels hold a few points each (0.2 m voxels), the cooperative walk (1) once a long-lived map has dense voxels
-    // (measured on B200: 27 vs 47 us at 3 points/voxel, 100 vs 52 us at 25 points/voxel, 20k queries).
+    // every voxel holds a few points (0.2 m voxels: 27 vs 47 us per 20k queries at 3 points/voxel), the cooperative walk (1)
+    // as soon as the map has dense voxels - on average (100 vs 52 us at 25 points/voxel) or just somewhere: in the sliding-map
+    // sequence a handful of voxels near the sensor path collect hundreds of points while the mean is still below 6, and
+    // a lane walking such a run alone made the update 1.8 ms instead of 0.4 ms.
     int knn_mode() const {
         static const char* env = getenv("B200_KNN_MODE");
-        if (env) return atoi(env) >= 5 ? atoi(env) : atoi(env) ? 1 : 0;
-        return h_ctr.num_voxels > 0 && h_ctr.live_points > 6ull * h_ctr.num_voxels ? 1 : 0;
+        if (env) return atoi(env);
+        if (h_ctr.num_voxels == 0) return 0;
+        return (h_ctr.live_points > 6ull * h_ctr.num_voxels || h_ctr.max_count > 32u) ? 1 : 0;
     }
     MapView view() const {
         MapView v;

@@ -34,6 +34,17 @@ struct __align__(16) LeafD {
     double icov[9];
 };
 static_assert(sizeof(LeafF) == 64 && sizeof(LeafD) == 96, "leaf records are read with 16-byte loads");
+// One fp64 leaf record with three 256-bit loads (sm_100: ld.global.nc.v4.f64 -> LDG.E.256).  Records are 96 B apart in a
+// cudaMalloc'ed array, so every 32-byte piece is naturally aligned and never straddles a 128-byte line: half the load
+// instructions of the 16-byte version, and the L1 wavefronts of a warp request go with the instruction count.
+__device__ __forceinline__ void load_leafD_256(const LeafD* p, LeafD& L) {
+    double* d = reinterpret_cast<double*>(&L);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                     : "=d"(d[4 * q]), "=d"(d[4 * q + 1]), "=d"(d[4 * q + 2]), "=d"(d[4 * q + 3])
+                     : "l"(reinterpret_cast<const char*>(p) + 32 * q));
+}
 
 struct AngleTables {   // computeAngleDerivatives: j_ang_a_..h_ / h_ang_a2_..f3_ (double) and j_ang / h_ang (float)
     double jd[8][3];
