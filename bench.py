@@ -586,6 +586,9 @@ def run_b200(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.sm and time.perf_counter() - t_wait < 3.0:   # NVML start-up must not eat the (short) timed region
+        step_device()
     barrier()
     launches0 = api.kernel_launches()
     t_wall0 = time.perf_counter()

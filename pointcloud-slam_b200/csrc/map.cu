@@ -514,7 +514,10 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     CUDA_TRY(cudaEventRecord(ev0, stream));
     {
         const unsigned grid = (unsigned)((threads + 255) / 256);
-        const int mode = knn_mode();
+        // large batches on a sparse map: the flattened walk (27 % fewer instructions, 0.61 -> 0.54 ms per 1M queries); a single
+        // scan (one wave of blocks) is faster with the lane-owned walk, which needs no shared-memory list
+        int mode = knn_mode();
+        if (mode == 0 && n >= 200000 && !getenv("B200_KNN_MODE")) mode = 5;
         if (mode >= 5) k_knn5<G, 5><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         else if (mode == 4) k_knn5<G, 4><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         else if (mode == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);

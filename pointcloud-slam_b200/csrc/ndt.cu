@@ -205,6 +205,31 @@ __global__ void k_ndt_finalize(const uint32_t* __restrict__ uniq, const int32_t*
     atomicAdd(n_valid, 1);
 }
 
+// DIRECT7 neighbourhood table: one 32-byte record per grid cell = the leaf slots of the cell and its six face neighbours
+// in the reference's order (vgc_impl:423-430), -1 where the neighbour is outside the grid or holds no usable leaf, and the
+// number of leaves in [7].  A point whose own cell lies inside the grid then resolves its whole neighbourhood with ONE
+// 256-bit load instead of seven scattered 4-byte probes (the probes were most of the L1 wavefronts of the score kernel).
+__global__ void k_ndt_build_nbr7(const int32_t* __restrict__ cell2leaf, int64_t ncells, int d0, int d1, int d2, int32_t* __restrict__ nbr7) {
+    const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (id >= ncells) return;
+    const int ix = (int)(id % d0), iy = (int)((id / d0) % d1), iz = (int)(id / ((int64_t)d0 * d1));
+    int out[8], cnt = 0;
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        int dx, dy, dz;
+        nbr_offset(7, s, dx, dy, dz);
+        const int x = ix + dx, y = iy + dy, z = iz + dz;
+        int lf = -1;
+        if (x >= 0 && x < d0 && y >= 0 && y < d1 && z >= 0 && z < d2) lf = cell2leaf[x + (int64_t)y * d0 + (int64_t)z * d0 * d1];
+        out[s] = lf;
+        cnt += lf >= 0 ? 1 : 0;
+    }
+    out[7] = cnt;
+    int4* dst = reinterpret_cast<int4*>(nbr7 + id * 8);
+    dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+}
+
 // ------------------------------------------------------------------ source ordering
 // The derivative and score kernels read, per source point, up to 7 cells of the dense table and a 64/96-byte leaf record
 // for every hit.  In scan order (a Livox rosette) the 32 lanes of a warp touch 32 unrelated voxels and every load
@@ -631,10 +656,27 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_ndt_score_batch(View v, const
         xform(M, p.x, p.y, p.z, tx, ty, tz);
         int lf[NST];
         int cnt = 0;
+        bool looked_up = false;
+        if (NST == 7 && v.nbr7) {  // the whole neighbourhood with one 256-bit load when the point's own cell is inside the grid
+            const int ix = (int)floorf(tx / v.leaf) - v.min_b[0], iy = (int)floorf(ty / v.leaf) - v.min_b[1], iz = (int)floorf(tz / v.leaf) - v.min_b[2];
+            if (ix >= 0 && iy >= 0 && iz >= 0 && ix <= v.max_b[0] - v.min_b[0] && iy <= v.max_b[1] - v.min_b[1] && iz <= v.max_b[2] - v.min_b[2]) {
+                const int* rec = v.nbr7 + ((size_t)ix * v.mul[0] + (size_t)iy * v.mul[1] + (size_t)iz * v.mul[2]) * 8;
+                int r[8];
+                asm volatile("ld.global.nc.v8.s32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                             : "l"(rec));
 #pragma unroll
-        for (int s = 0; s < NST; ++s) {
-            lf[s] = nbr_leaf(v, tx, ty, tz, s);
-            cnt += lf[s] >= 0 ? 1 : 0;
+                for (int s = 0; s < NST; ++s) lf[s] = r[s < 7 ? s : 0];
+                cnt = r[7];
+                looked_up = true;
+            }
+        }
+        if (!looked_up) {
+#pragma unroll
+            for (int s = 0; s < NST; ++s) {
+                lf[s] = nbr_leaf(v, tx, ty, tz, s);
+                cnt += lf[s] >= 0 ? 1 : 0;
+            }
         }
         // score_inc / neighborhood.size() (:876): the size is inverted once per point (<= 1 ulp per term, far inside the
         // 1e-12 score tolerance) - the fp64 division was 13 % of this kernel's instructions
@@ -830,7 +872,7 @@ struct Ndt {
     DevBuf<double> d_fit;
     bool have_fitness_index = false;
     int64_t n_tgt = 0;
-    DevBuf<int32_t> d_cell2leaf;
+    DevBuf<int32_t> d_cell2leaf, d_nbr7;
     DevBuf<LeafF> d_leafF;
     DevBuf<LeafD> d_leafD;
     DevBuf<double> d_cov, d_sums;
@@ -840,7 +882,7 @@ struct Ndt {
     PinnedBuf<float4> h_stage;
     PinnedBuf<int32_t> h_small;
     int n_src = 0;
-    bool have_target = false;
+    bool have_target = false, have_nbr7 = false;
     // align
     DevBuf<Ctl> d_ctl;
     DevBuf<double> d_partials, d_p_in, d_scores;
@@ -894,7 +936,7 @@ void Ndt::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     d_tgt.release(); d_src.release(); d_src_raw.release(); d_tgt_sorted.release(); s_keys_in.release(); s_keys_out.release();
-    s_vals_in.release(); s_vals_out.release(); d_cell2run.release(); s_tmp.release(); d_fit.release(); d_cell2leaf.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
+    s_vals_in.release(); s_vals_out.release(); d_cell2run.release(); s_tmp.release(); d_fit.release(); d_cell2leaf.release(); d_nbr7.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
     d_npts.release(); d_vals_in.release(); d_vals_out.release(); d_run_cnt.release(); d_run_off.release(); d_small.release();
     d_keys_in.release(); d_keys_out.release(); d_uniq.release(); d_valid.release(); cub_tmp.release();
     h_stage.release(); h_small.release(); d_ctl.release(); d_partials.release(); d_p_in.release(); d_scores.release(); d_poses.release();
@@ -917,6 +959,7 @@ View Ndt::view() const {
     View v;
     v.src = d_src.p; v.n_src = n_src;
     v.cell2leaf = d_cell2leaf.p; v.leafF = d_leafF.p; v.leafD = d_leafD.p;
+    v.nbr7 = have_nbr7 ? d_nbr7.p : nullptr;
     for (int k = 0; k < 3; ++k) { v.min_b[k] = gd.min_b[k]; v.max_b[k] = gd.max_b[k]; v.mul[k] = gd.mul[k]; }
     v.leaf = prm.resolution;
     v.nst = prm.search;
@@ -1024,6 +1067,12 @@ int32_t Ndt::build_target(int64_t n) {
     k_ndt_finalize<<<(nruns + 127) / 128, 128, 0, stream>>>(d_uniq.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p, prm.min_pts, prm.eig_ratio, d_leafF.p,
                                                             d_leafD.p, d_cov.p, d_npts.p, d_valid.p, d_cell2leaf.p, d_nvalid);
     LAUNCH_COUNT(5);
+    have_nbr7 = prm.search == 7 && ncells <= ((int64_t)1 << 26);  // 32 B per cell: at most 2 GB
+    if (have_nbr7) {
+        CUDA_TRY(d_nbr7.reserve((size_t)ncells * 8));
+        k_ndt_build_nbr7<<<(unsigned)((ncells + 255) / 256), 256, 0, stream>>>(d_cell2leaf.p, ncells, gd.div_b[0], gd.div_b[1], gd.div_b[2], d_nbr7.p);
+        LAUNCH_COUNT(1);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaMemcpyAsync(h_small.p, d_nvalid, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));

@@ -57,6 +57,7 @@ struct View {
     const float4* src;
     int n_src;
     const int* cell2leaf;
+    const int* nbr7;   // [cells][8]: leaf slot (or -1) of the DIRECT7 neighbourhood cells of every grid cell, [7] = how many exist
     const LeafF* leafF;
     const LeafD* leafD;
     int min_b[3], max_b[3], mul[3];
