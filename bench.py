@@ -621,12 +621,13 @@ def run_b200(args, rank, local_rank, world):
 
     # per-kernel durations by CUDA events (profiling mode launches kernel by kernel)
     kf.set_profiling(True)
-    search_ms, obs_ms, init_ms = [], [], []
+    search_ms, obs_ms, init_ms, prof_totals = [], [], [], []
     for k in range(args.steps + 2):
         api.flush_l2(local_rank)
         step_device()
         if k >= 2:
             t = kf.kernel_times_ms()
+            prof_totals.append(list(t[:1 + 2 * passes]))
             init_ms.append(t[0])
             for p in range(passes):
                 if kf.stats.knn[p]:
@@ -679,9 +680,12 @@ def run_b200(args, rank, local_rank, world):
                 # ncu --set full capture summarised in profiles/r01_iekf_ncu_full_summary.md (prof_iekf_r1c, launch id 0)
                 "traffic": 29512704 + 2816000 if args.params == "livox" else None, "algorithmic_bytes": int(algo_bytes),
                 "kernel_ms": k_ms, "candidates_per_query": sum_c / n, "occupied_cells_per_query": cells / n,
+                "share_of_step": (knn_passes * k_ms) / float(np.mean([sum(x) for x in prof_totals])) if prof_totals else None,
                 "note": "kernel_ms is event-to-event inside the update's stream (includes ~4 us of launch/event gap); traffic = ncu dram bytes "
                         "per launch with a cold L2 (2.3x the algorithmic bytes: 32-byte sectors around 16-byte table entries and short runs); "
-                        "the kernel is bound by L1 wavefronts of scattered 16-byte gathers, not by DRAM (profiles/README.md)"}
+                        "one scan is a single wave of 625 blocks: the kernel is bound by instruction issue (425 warp instructions per query, "
+                        "half of them the 64-bit top-5 insertion, 15 of 32 lanes active) and by the latency of two dependent gathers, not by "
+                        "DRAM (profiles/README.md, r02 source-level counters)"}
     # the same search kernel with enough parallelism to leave the launch-latency regime: 50 scans' worth of queries in one call
     rng = np.random.default_rng(1)
     qbig = np.ascontiguousarray(np.concatenate([qw + rng.normal(0, 0.05, qw.shape).astype(np.float32) for _ in range(50)], 0))
@@ -699,7 +703,12 @@ def run_b200(args, rank, local_rank, world):
                            "frac": big_bytes / (float(np.mean(big_ms)) * 1e-3) / 1e9 / peak, "queries_per_s": nb_ / (float(np.mean(big_ms)) * 1e-3),
                            "note": "L2 flushed before each launch; the 32 MB map becomes L2-resident during the launch"}
     kernels = {"k_iekf_init_ms": float(np.mean(init_ms)), "k_search_ms": k_ms, "k_obs_ms": float(np.mean(obs_ms)),
-               "per_update": f"1 init + {passes} x (k_search, k_obs); k_search is a no-op on non-search passes"}
+               "per_update": f"1 init + {passes} x (k_search, k_obs); k_search is a no-op on non-search passes",
+               "share_of_step": {"k_search": (knn_passes * k_ms) / float(np.mean([sum(x) for x in prof_totals])),
+                                 "k_obs": (passes * float(np.mean(obs_ms))) / float(np.mean([sum(x) for x in prof_totals]))},
+               "note": "event-to-event per kernel with plain launches (each interval carries ~3-4 us of launch / event gap that the graph "
+                       "replay of the timed steps does not pay); k_obs is bound by the latency of its serial parts - the per-point 5x3 QR "
+                       "on 137 threads per SM and the filter block's fp64 chain - not by bytes (profiles/README.md)"}
 
     line = {
         "metric": "registered points/sec (IEKF update)", "value": world * n / (ms_step * 1e-3), "unit": "points/s",
