@@ -76,6 +76,30 @@ __device__ inline void make_pass_consts(const double* x, PassConsts& pc) {
     for (int i = 0; i < 3; ++i) pc.offt[i] = (float)x[11 + i];
 }
 
+// the same constants for the next pass, the four independent pieces on lane 0 of four warps (block-wide call)
+__device__ inline void make_pass_consts_par(const double* x, PassConsts& pc) {
+    using namespace mf;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const Q qd = qmul(ldq(x + 3), ldq(x + 7));
+        pc.qx = (float)qd.x; pc.qy = (float)qd.y; pc.qz = (float)qd.z; pc.qw = (float)qd.w;
+    } else if (tid == 32) {
+        double td[3];
+        qrot(ldq(x + 3), x + 11, td);
+        pc.tx = (float)(td[0] + x[0]); pc.ty = (float)(td[1] + x[1]); pc.tz = (float)(td[2] + x[2]);
+        for (int i = 0; i < 3; ++i) pc.offt[i] = (float)x[11 + i];
+    } else if (tid == 64) {
+        double Ro[9];
+        qtoR(ldq(x + 7), Ro);
+        for (int i = 0; i < 9; ++i) pc.offR[i] = (float)Ro[i];
+    } else if (tid == 96) {
+        double Rr[9];
+        qtoR(ldq(x + 3), Rr);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) pc.Rt[i * 3 + j] = (float)Rr[j * 3 + i];
+    }
+}
+
 struct SolveSmem {
     double P[NS * NS];
     double L[NS * NS];
@@ -88,6 +112,7 @@ struct SolveSmem {
     double HTh[12];
     double Kx[NS * 12];
     double Kh[NS];
+    double vw[12], vy[12], vu[12];  // m-vectors of the gain product
     double x[26], xp[26];
     double dx[NS], dxn[NS], dxu[NS];
     double J3[2][9];  // A(dx)^T for rot / offR
@@ -359,53 +384,41 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
         return;
     }
     if (tid == 0) ctl->any_valid = 1;
-    // 4. P_inv[:, :m] by the conditional-Gaussian form (see the header comment)
+    // 4.-6. dx_ = K_h + (K_x - I) dx_new (:1708-1719) without forming the gain matrices: with K = P_inv[:, :m] = B[:, :m] G,
+    //    G = B_aa^-1 (B_aa^-1 + A)^-1 (header comment),  K_h + K_x dx_new = K (H^T h + A dx_new[:m]), so the step needs three
+    //    m-vectors and one 23 x m product.  One warp does it with warp barriers only (the other warps wait at the block
+    //    barrier below); K_x itself is only needed for the final covariance and is built in the finalising pass.
     const int m = ext ? 12 : 6;
-    for (int i = tid; i < m * m; i += nt) {
-        const int r = i / m, c = i % m;
-        s.Minv[r * 12 + c] = s.BaaInv[r * 12 + c] + s.HTH[r * 12 + c];
-    }
-    __syncthreads();
-    if (warp == 0) warp_inverse_spd_m(s.Minv, s.Minv, m, 12);  // (B_aa^-1 + A)^-1 = P_inv[a, a]
-    __syncthreads();
-    STAMP(2);
-    for (int idx = tid; idx < m * m; idx += nt) {  // G = B_aa^-1 * P_inv[a,a]
-        const int r = idx / m, c = idx % m;
-        double v = 0.0;
-        for (int k = 0; k < m; ++k) v += s.BaaInv[r * 12 + k] * s.Minv[k * 12 + c];
-        s.G[r * 12 + c] = v;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NS * 12; idx += nt) {  // P_inv[:, :m] = B[:, :m] G ; columns >= m are never used
-        const int r = idx / 12, c = idx % 12;
-        double v = 0.0;
-        if (c < m)
-            for (int k = 0; k < m; ++k) v += s.B12[r * 12 + k] * s.G[k * 12 + c];
-        s.Pinv12[idx] = v;
-    }
-    __syncthreads();
-    STAMP(3);
-    // 5. K_h = P_inv[:, :12] H^T h ; K_x[:, :12] = P_inv[:, :12] HTH   (esekfom.hpp:1708-1713)
-    for (int idx = tid; idx < NS * 13; idx += nt) {
-        const int r = idx / 13, c = idx % 13;
-        double sum = 0.0;
-        if (c < 12) {
-            for (int k = 0; k < m; ++k) sum += s.Pinv12[r * 12 + k] * s.HTH[k * 12 + c];
-            s.Kx[r * 12 + c] = sum;
-        } else {
-            for (int k = 0; k < m; ++k) sum += s.Pinv12[r * 12 + k] * s.HTh[k];
-            s.Kh[r] = sum;
+    if (warp == 0) {
+        for (int i = lane; i < m * m; i += 32) {
+            const int r = i / m, c = i % m;
+            s.Minv[r * 12 + c] = s.BaaInv[r * 12 + c] + s.HTH[r * 12 + c];
         }
-    }
-    __syncthreads();
-    // 6. dx_ = K_h + (K_x - I) dx_new   (:1719)
-    if (tid < NS) {
-        double sum = 0.0;
-        for (int c = 0; c < NS; ++c) {
-            const double kx = c < 12 ? s.Kx[tid * 12 + c] : 0.0;
-            sum += (kx - (c == tid ? 1.0 : 0.0)) * s.dxn[c];
+        __syncwarp();
+        warp_inverse_spd_m(s.Minv, s.Minv, m, 12);  // (B_aa^-1 + A)^-1 = P_inv[a, a]
+        if (lane < m) {  // w = H^T h + A dx_new[:m]
+            double v = s.HTh[lane];
+            for (int k = 0; k < m; ++k) v = fma(s.HTH[lane * 12 + k], s.dxn[k], v);
+            s.vw[lane] = v;
         }
-        s.dxu[tid] = s.Kh[tid] + sum;
+        __syncwarp();
+        if (lane < m) {  // y = (B_aa^-1 + A)^-1 w
+            double v = 0.0;
+            for (int k = 0; k < m; ++k) v = fma(s.Minv[lane * 12 + k], s.vw[k], v);
+            s.vy[lane] = v;
+        }
+        __syncwarp();
+        if (lane < m) {  // u = B_aa^-1 y
+            double v = 0.0;
+            for (int k = 0; k < m; ++k) v = fma(s.BaaInv[lane * 12 + k], s.vy[k], v);
+            s.vu[lane] = v;
+        }
+        __syncwarp();
+        if (lane < NS) {  // dx_ = B[:, :m] u - dx_new
+            double v = -s.dxn[lane];
+            for (int k = 0; k < m; ++k) v = fma(s.B12[lane * 12 + k], s.vu[k], v);
+            s.dxu[lane] = v;
+        }
     }
     __syncthreads();
     STAMP(4);
@@ -437,6 +450,28 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
     if (tid < 26) ctl->x[tid] = s.x[tid];
     if (s.finalize) {  // :1735-1831
         make_projection_par(s, s.dxu, s.x, s.xp);
+        // K_x[:, :12] = P_inv[:, :12] HTH = B[:, :m] G A   (esekfom.hpp:1713), only needed here
+        for (int idx = tid; idx < m * m; idx += nt) {  // G = B_aa^-1 * P_inv[a,a]
+            const int r = idx / m, c = idx % m;
+            double v = 0.0;
+            for (int k = 0; k < m; ++k) v = fma(s.BaaInv[r * 12 + k], s.Minv[k * 12 + c], v);
+            s.G[r * 12 + c] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NS * 12; idx += nt) {  // P_inv[:, :m] = B[:, :m] G ; columns >= m are never used
+            const int r = idx / 12, c = idx % 12;
+            double v = 0.0;
+            if (c < m)
+                for (int k = 0; k < m; ++k) v = fma(s.B12[r * 12 + k], s.G[k * 12 + c], v);
+            s.Pinv12[idx] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NS * 12; idx += nt) {
+            const int r = idx / 12, c = idx % 12;
+            double sum = 0.0;
+            for (int k = 0; k < m; ++k) sum = fma(s.Pinv12[r * 12 + k], s.HTH[k * 12 + c], sum);
+            s.Kx[idx] = sum;
+        }
         __syncthreads();
         STAMP(6);
         // L = J P J^T and K_x <- J K_x in one step (esekfom.hpp:1739-1789 applies the blocks one after the other)
@@ -492,9 +527,9 @@ __device__ inline void iekf_postsolve(Ctl* ctl, const double* partials, int nblo
         if (tid == 0) {
             ctl->converge = s.conv;
             ctl->iter = iter + 1;
-            make_pass_consts(s.x, ctl->pc);
             if (iter + 1 >= max_iter) ctl->done = 1;
         }
+        make_pass_consts_par(s.x, ctl->pc);
         STAMP(7);
     }
 }
