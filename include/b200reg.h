@@ -20,6 +20,7 @@
  */
 #ifndef B200REG_H_
 #define B200REG_H_
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -93,6 +94,12 @@ typedef struct {
     int32_t knn[B200_MAX_PASSES];
     float gpu_ms; /* device time of the whole update (CUDA events on the handle's stream) */
 } b200_iekf_stats;
+
+/* Page-locked host buffers (cudaHostAlloc).  A scan handed to b200_iekf_update in such a buffer (or in any memory the
+ * caller registered with cudaHostRegister) crosses PCIe straight from the caller's memory and is unpacked on the device:
+ * no host-side packing pass.  Pageable buffers (a PCL cloud) keep working and are packed through an internal pinned stage. */
+int32_t b200_host_alloc(size_t bytes, void** out);
+int32_t b200_host_free(void* p);
 
 int32_t b200_iekf_create(const b200_iekf_params* params, b200_map* map, b200_iekf** out);
 int32_t b200_iekf_destroy(b200_iekf* ekf);

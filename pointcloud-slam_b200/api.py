@@ -110,6 +110,8 @@ def lib():
     L.b200_map_evicted.restype = i64
     L.b200_map_evicted.argtypes = [vp]
     L.b200_flush_l2.argtypes = [i32]
+    L.b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.b200_host_free.argtypes = [vp]
     if hasattr(L, "b200_ndt_create"):
         L.b200_ndt_create.argtypes = [C.POINTER(NdtParams), i32, C.POINTER(vp)]
         L.b200_ndt_destroy.argtypes = [vp]
@@ -182,6 +184,29 @@ def _cloud(a):
     if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or a.strides[1] != 4:
         a = np.ascontiguousarray(a, dtype=np.float32)
     return a
+
+
+class PinnedCloud:
+    """A page-locked host array (b200_host_alloc) shaped like a point cloud: scans written into `.array` reach the device
+    without the host-side packing pass (include/b200reg.h).  Keep the object alive while the array is in use."""
+
+    def __init__(self, n, cols=3):
+        self.ptr = C.c_void_p()
+        self.nbytes = int(n) * int(cols) * 4
+        _check(lib().b200_host_alloc(C.c_size_t(self.nbytes), C.byref(self.ptr)))
+        buf = (C.c_float * (int(n) * int(cols))).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(int(n), int(cols))
+
+    def close(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            self.array = None
+            try:
+                lib().b200_host_free(self.ptr)
+            except TypeError:
+                pass
+            self.ptr = C.c_void_p()
+
+    __del__ = close
 
 
 def flush_l2(device=0):

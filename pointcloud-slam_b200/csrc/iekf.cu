@@ -75,6 +75,15 @@ __global__ void k_iekf_init(Ctl* ctl, const Ctl* hdr, PointState ps, int force_c
     }
 }
 
+// strided xyz records (12-byte packed, 16-byte, 48-byte PointXYZINormal ...) -> float4, for scans that arrived unpacked
+// from page-locked caller memory
+__global__ void k_unpack_xyz(const uint8_t* __restrict__ raw, int64_t stride, int n, float4* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    dst[i] = make_float4(p[0], p[1], p[2], 0.0f);
+}
+
 // ------------------------------------------------------------------ ObsModel
 // Residual / validity / Jacobian row of point i given its (possibly refreshed) neighbour set.
 // Returns whether the point is an effective feature; fills row[0..11] and h.
@@ -342,6 +351,7 @@ struct Iekf {
     PointState ps{};
     size_t ps_cap = 0;
     DevBuf<float4> d_scan, d_nb;
+    DevBuf<uint8_t> d_raw;  // unpacked scan bytes when they come straight from page-locked caller memory
     DevBuf<unsigned char> d_nbc;
     int last_n = 0;       // size the per-point arrays were last resized to
     const float4* last_scan = nullptr;
@@ -438,7 +448,7 @@ void Iekf::destroy() {
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(d_ctl); cudaFree(d_limit); cudaFree(d_partials);
     cudaFree(ps.plane); cudaFree(ps.resid); cudaFree(ps.sel); cudaFree(ps.nn_cnt); cudaFree(ps.nn);
-    d_scan.release(); d_nb.release(); d_nbc.release(); h_stage.release(); h_out.release();
+    d_scan.release(); d_raw.release(); d_nb.release(); d_nbc.release(); h_stage.release(); h_out.release();
     d_world.release(); d_sel_pts.release(); d_flag.release(); d_flag2.release(); cub_tmp.release(); d_count.release(); d_x.release();
     h_count.release(); h_x.release();
     if (gexec) cudaGraphExecDestroy(gexec);
@@ -580,6 +590,16 @@ struct b200_iekf { Iekf k; b200_map* owner = nullptr; };
 
 extern "C" {
 
+int32_t b200_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) B200_FAIL(B200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return B200_OK;
+}
+int32_t b200_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return B200_OK;
+}
+
 int32_t b200_iekf_create(const b200_iekf_params* params, b200_map* map, b200_iekf** out) {
     if (!params || !map || !out) B200_FAIL(B200_ERR_ARG, "null argument");
     b200_iekf* h = new b200_iekf();
@@ -613,6 +633,19 @@ static int32_t stage_scan(Iekf& k, const float* xyz, int64_t n, int64_t stride, 
     if (P) memcpy(hc->P, P, sizeof(double) * NS * NS); else memset(hc->P, 0, sizeof(double) * NS * NS);
     hc->n = (int)n;
     hc->prev_n = k.last_n < (int)n ? k.last_n : (int)n;
+    // page-locked caller memory: the raw records cross PCIe as they are and are unpacked on the device
+    cudaPointerAttributes at{};
+    if (stride % 4 == 0 && cudaPointerGetAttributes(&at, xyz) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+        const size_t raw_bytes = (size_t)(n - 1) * stride + 12;
+        CUDA_TRY(k.d_raw.reserve(raw_bytes));
+        CUDA_TRY(cudaMemcpyAsync(k.d_scan.p, k.h_stage.p, hdr_pad, cudaMemcpyHostToDevice, k.stream));
+        CUDA_TRY(cudaMemcpyAsync(k.d_raw.p, xyz, raw_bytes, cudaMemcpyHostToDevice, k.stream));
+        k_unpack_xyz<<<(unsigned)((n + 255) / 256), 256, 0, k.stream>>>(k.d_raw.p, stride, (int)n,
+                                                                         (float4*)((uint8_t*)k.d_scan.p + hdr_pad));
+        LAUNCH_COUNT(1);
+        return B200_OK;
+    }
+    cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave an error behind on old drivers
     pack_xyz_float4(xyz, n, stride, (float4*)(k.h_stage.p + hdr_pad));
     // the device scan buffer mirrors the pinned layout; k_iekf_init forwards the header to the control block
     CUDA_TRY(cudaMemcpyAsync(k.d_scan.p, k.h_stage.p, hdr_pad + (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, k.stream));

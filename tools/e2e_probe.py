@@ -11,3 +11,10 @@ for r in range(12):
     kf.change_x(c['x_prop']); kf.change_P(c['P'])
     t = time.perf_counter(); kf.update_iterated_dyn_share_modified(c['scan']); ts.append((time.perf_counter() - t) * 1e6)
 print('python wall us', ['%.0f' % t for t in ts])
+pin = api.PinnedCloud(len(c['scan']), 3); pin.array[:] = c['scan']
+ts = []
+for r in range(12):
+    api.flush_l2(0)
+    kf.change_x(c['x_prop']); kf.change_P(c['P'])
+    t = time.perf_counter(); kf.update_iterated_dyn_share_modified(pin.array); ts.append((time.perf_counter() - t) * 1e6)
+print('pinned wall us', ['%.0f' % t for t in ts], kf.get_x()[:3])
