@@ -145,6 +145,27 @@ def test_iekf_update_parity(oracle, api, small_cfg, pname):
         np.testing.assert_array_equal(s1[key], s0[key], err_msg=key)
 
 
+def test_pinned_scan_takes_the_unpacked_path_with_identical_results(oracle, api, small_cfg):
+    """A scan in page-locked memory (b200_host_alloc) is unpacked on the device: same posterior, bit for bit, for packed
+    12-byte records and for 48-byte PointXYZINormal-strided records."""
+    scan = small_cfg["scan"]
+
+    def run(cloud):  # fresh filter every time: the per-point arrays persist across scans by design
+        o, g, kf = pair(oracle, api, "livox", small_cfg["map"])
+        kf.change_x(small_cfg["x_prop"]); kf.change_P(small_cfg["P"])
+        assert kf.update_iterated_dyn_share_modified(cloud) == 0
+        return kf.get_x().copy(), kf.get_P().copy()
+
+    x_ref, P_ref = run(scan)
+    for cols in (3, 12):
+        pin = api.PinnedCloud(len(scan), cols)
+        pin.array[:] = 7.0
+        pin.array[:, :3] = scan
+        x, P = run(pin.array)
+        assert np.array_equal(x, x_ref) and np.array_equal(P, P_ref)
+        pin.close()
+
+
 def test_update_without_map_reports_no_effective_points(oracle, api, small_cfg):
     o, g, kf = pair(oracle, api, "horizon", None)
     kf.change_x(small_cfg["x_prop"])
