@@ -449,7 +449,7 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
     out = {"workload": f"configs[4] scaled: {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes, {reuse} passes per tile, tiles side by side), leaf 0.1 m; "
                        "10000 keyframes = full size (--fullmap-frames)",
            "metric": "keyframes/s", "value": n_frames / t_dev, "unit": "keyframes/s", "points_per_s": n_frames * n_pts / t_dev, "n_gpus": world,
-           "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.mean(exch)) if exch else 0.0,
+           "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.min(exch)) if exch else 0.0,  # best of the repetitions, like `seconds` (the first one sets up the NCCL channels)
            "timing": "wall clock around add_keyframe_device x frames + merge (NCCL exchange) + final sync, keyframes resident in HBM; max over ranks, best of 3",
            "e2e": {"value": n_frames / t_e2e, "unit": "keyframes/s", "seconds": t_e2e, "h2d_bytes_per_keyframe": n_pts * 16,
                    "note": "b200_mapbuild_add_keyframe with host buffers: pack + H2D per keyframe"}}

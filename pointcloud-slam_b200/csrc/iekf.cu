@@ -12,6 +12,9 @@
 //            inversions, gain, (+), convergence logic, next-pass constants
 // Whether a pass searches the map (dyn_share.converge) and whether it runs at all (early exit)
 // is decided on the device through the control block, so the host just enqueues max_iter+1 pairs.
+#ifndef B200_KNN_BLOCK
+#define B200_KNN_BLOCK 256
+#endif
 #include "map.cuh"
 #include "manifold.cuh"
 #include "pointmath.cuh"
@@ -137,8 +140,9 @@ struct ObsSmem {
 // Stencil search of a pass (dyn_share.converge == true): 8 lanes per scan point, one wave over the
 // whole scan at high occupancy.  Results go to a scratch array that k_obs consumes; the kernel is a
 // no-op when the pass reuses the previous neighbours (decided on the device).
+constexpr int KNN_BLOCK = B200_KNN_BLOCK;  // threads per search block
 template <int MODE>
-__global__ void __launch_bounds__(256, (MODE == 0 || MODE == 5) ? 5 : 4) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+__global__ void __launch_bounds__(KNN_BLOCK, (MODE == 0 ? 1280 : MODE == 5 ? 1152 : 1024) / KNN_BLOCK) k_search(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
                                                 float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
     pdl_trigger();
     pdl_wait();
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 || MODE == 5) ? 5 : 4) k_searc
     const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
     uint64_t wkey;
     float4 mine;
-    __shared__ uint2 s_flat[MODE >= 5 ? (256 / KNN_G) * kFlatStride : 1];
+    __shared__ uint2 s_flat[MODE >= 5 ? (KNN_BLOCK / KNN_G) * kFlatStride : 1];
     const int c = knn5_group<KNN_G, MODE>(map, pw.x, pw.y, pw.z, lg, gmask, lane_stencil<KNN_G>(lg, map.nstencil), wkey, mine,
                                           MODE >= 5 ? s_flat + (tid / KNN_G) * kFlatStride : nullptr);
     if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
@@ -493,7 +497,7 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
         const int mode = map->knn_mode();
         const bool pdl = !events;  // kernel -> kernel edges only (an event record in between makes it a full dependency anyway)
         auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 4 ? k_search<4> : mode == 1 ? k_search<1> : k_search<0>;
-        CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(KNN_BLOCK), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
         CUDA_TRY(launch_k(k_obs, dim3(nblocks), dim3(OBS_THREADS), stream, pdl, d_pts, (const float4*)d_nb.p, (const unsigned char*)d_nbc.p, ps,
                           d_ctl, prm.plane_thr, (int)prm.extrinsic_est_en, d_partials, (int)prm.max_iter, prm.R, (const double*)d_limit,
@@ -524,7 +528,7 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
     }
     // search grid sized for the scan rounded up to 8192 points (blocks past ctl->n exit at once), so scans of
     // similar size replay the same graph
-    const unsigned search_grid = (unsigned)((((size_t)n + 8191) / 8192 * 8192 * KNN_G + 255) / 256);
+    const unsigned search_grid = (unsigned)((((size_t)n + 8191) / 8192 * 8192 * KNN_G + KNN_BLOCK - 1) / KNN_BLOCK);
     const int npass = single_pass ? 1 : prm.max_iter + 1;
     CUDA_TRY(cudaEventRecord(ev0, stream));
     if (profiling || !use_graph) {
