@@ -236,6 +236,10 @@ int32_t b200_mapbuild_destroy(b200_mapbuild* h);
 /* one keyframe (frames/<i>.pcd, x y z intensity) with its pose (a line of poses.txt: x y z qw qx qy qz); asynchronous */
 int32_t b200_mapbuild_add_keyframe(b200_mapbuild* h, const float* xyzi, int64_t n, int64_t stride_bytes, const double* pose7);
 int32_t b200_mapbuild_add_keyframe_device(b200_mapbuild* h, const void* d_xyzi_float4, int64_t n, const double* pose7);
+/* `count` device-resident keyframes in one call (poses7 = count x 7 doubles): they are accumulated several per kernel
+ * launch, which is what fills the GPU - one 100k-point keyframe alone is latency bound. */
+int32_t b200_mapbuild_add_keyframes_device(b200_mapbuild* h, const void* const* d_xyzi_float4, const int64_t* n, const double* poses7,
+                                           int64_t count);
 int64_t b200_mapbuild_num_voxels(b200_mapbuild* h);
 /* collective: afterwards every voxel lives on exactly one rank with the sums of all ranks */
 int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h);

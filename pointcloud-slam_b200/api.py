@@ -152,6 +152,7 @@ def lib():
     L.b200_mapbuild_destroy.argtypes = [vp]
     L.b200_mapbuild_add_keyframe.argtypes = [vp, vp, i64, i64, vp]
     L.b200_mapbuild_add_keyframe_device.argtypes = [vp, vp, i64, vp]
+    L.b200_mapbuild_add_keyframes_device.argtypes = [vp, vp, vp, vp, i64]
     L.b200_mapbuild_num_voxels.restype = i64
     L.b200_mapbuild_num_voxels.argtypes = [vp]
     L.b200_mapbuild_merge.argtypes = [vp, vp]
@@ -723,6 +724,14 @@ class FullMapBuilder:
     def add_keyframe_device(self, d_ptr, n, pose7):
         p = np.ascontiguousarray(pose7, dtype=np.float64)
         _check(lib().b200_mapbuild_add_keyframe_device(self.h, C.c_void_p(d_ptr), n, _p(p)))
+
+    def add_keyframes_device(self, d_ptrs, ns, poses7):
+        """A batch of device-resident keyframes (pointers, point counts, count x 7 poses) in one call."""
+        ptrs = np.ascontiguousarray(d_ptrs, dtype=np.uint64)
+        ns = np.ascontiguousarray(ns, dtype=np.int64)
+        p = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
+        assert len(ptrs) == len(ns) == len(p)
+        _check(lib().b200_mapbuild_add_keyframes_device(self.h, _p(ptrs), _p(ns), _p(p), len(ptrs)))
 
     def num_voxels(self):
         n = lib().b200_mapbuild_num_voxels(self.h)

@@ -94,6 +94,30 @@ def test_full_map_builder_matches_oracle(oracle, api, synth):
     np.testing.assert_allclose(c2, c1, rtol=0, atol=1e-6)
 
 
+def test_full_map_batched_device_keyframes_match_one_by_one(oracle, api, synth):
+    """b200_mapbuild_add_keyframes_device (several keyframes per launch, ragged sizes, more keyframes than one launch
+    batch) builds the same map as the one-by-one host path."""
+    import torch
+    frames, poses = make_frames(synth)
+    frames = [f[: len(f) - 37 * i] for i, f in enumerate(frames)] * 9        # ragged, and > 24 keyframes
+    poses = list(poses) * 9
+    b = api.FullMapBuilder(leaf=0.1, capacity_voxels=500_000)
+    for f, p in zip(frames, poses):
+        b.add_keyframe(f, p)
+    c0, n0 = b.extract()
+    dev = []
+    for f in frames:
+        a = np.zeros((len(f), 4), np.float32)
+        a[:, : f.shape[1]] = f
+        dev.append(torch.from_numpy(a).cuda())
+    b2 = api.FullMapBuilder(leaf=0.1, capacity_voxels=500_000)
+    b2.add_keyframes_device([d.data_ptr() for d in dev], [len(f) for f in frames], np.stack(poses))
+    assert b2.num_voxels() == len(c0)
+    c1, n1 = b2.extract()
+    np.testing.assert_array_equal(n1, n0)
+    np.testing.assert_allclose(c1, c0, rtol=0, atol=1e-6)
+
+
 def test_full_map_capacity_error(api, synth):
     frames, poses = make_frames(synth, k=2)
     b = api.FullMapBuilder(leaf=0.1, capacity_voxels=100)
