@@ -507,7 +507,10 @@ __device__ void advance(Ctl& c, const AlignConsts& k, const double* res) {
 }
 
 // ------------------------------------------------------------------ evaluation kernel
+constexpr int kPairCap = 2048;  // (point, leaf) pairs a block can queue
 struct EvalSmem {
+    int2 pairs[kPairCap];
+    int wcnt[2][EVAL_THREADS / 32];
     float M[12];
     AngleTables tab;
     int mode;
@@ -530,13 +533,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-    for (int item = blockIdx.x * EVAL_THREADS + tid; item < nitems; item += nbx * EVAL_THREADS) {
-        const int i = item / v.nst, s = item - i * v.nst;
+    auto evaluate = [&](int i, int lf) {
         const float4 p = __ldg(v.src + i);
         float tx, ty, tz;
         xform(sm.M, p.x, p.y, p.z, tx, ty, tz);
-        const int lf = nbr_leaf(v, tx, ty, tz, s);
-        if (lf < 0) continue;
         if (mode == MODE_HESS_D) {
             LeafD L;
             const double2* src = reinterpret_cast<const double2*>(v.leafD + lf);
@@ -551,6 +551,54 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = __ldg(src + q);
             deriv_pair_f(v, sm.tab, L, p.x, p.y, p.z, tx, ty, tz, mode == MODE_DERIV_H, acc);
+        }
+    };
+    // Two thirds of the (point, neighbourhood cell) items hold no leaf.  Evaluating items in place leaves each warp
+    // running as long as its unluckiest lane (3-4 evaluations of ~500 instructions where the mean is 1.3), so the block
+    // first compacts its valid pairs into a shared-memory list - positions from ballots and a fixed scan over the warps:
+    // deterministic, so the fp64 sums stay reproducible - and then takes the list 256 entries at a time.
+    const int first = blockIdx.x * EVAL_THREADS, stride = nbx * EVAL_THREADS;
+    const int rounds = first < nitems ? (nitems - first + stride - 1) / stride : 0;
+    if (rounds * EVAL_THREADS <= kPairCap) {
+        const int lane = tid & 31, warp = tid >> 5;
+        int base = 0;
+        for (int r = 0; r < rounds; ++r) {
+            const int item = first + tid + r * stride;
+            int i = 0, lf = -1;
+            if (item < nitems) {
+                i = item / v.nst;
+                const int s = item - i * v.nst;
+                const float4 p = __ldg(v.src + i);
+                float tx, ty, tz;
+                xform(sm.M, p.x, p.y, p.z, tx, ty, tz);
+                lf = nbr_leaf(v, tx, ty, tz, s);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, lf >= 0);
+            if (lane == 0) sm.wcnt[r & 1][warp] = __popc(bal);
+            __syncthreads();  // the other buffer is free again: every warp passed the barrier of the previous round
+            int off = base, total = 0;
+#pragma unroll
+            for (int w = 0; w < EVAL_THREADS / 32; ++w) {
+                const int c = sm.wcnt[r & 1][w];
+                if (w < warp) off += c;
+                total += c;
+            }
+            if (lf >= 0) sm.pairs[off + __popc(bal & ((1u << lane) - 1u))] = make_int2(i, lf);
+            base += total;
+        }
+        __syncthreads();
+        for (int e = tid; e < base; e += EVAL_THREADS) {
+            const int2 pr = sm.pairs[e];
+            evaluate(pr.x, pr.y);
+        }
+    } else {  // more items per block than the list holds (scans beyond ~40k points): in place
+        for (int item = first + tid; item < nitems; item += stride) {
+            const int i = item / v.nst, s = item - i * v.nst;
+            const float4 p = __ldg(v.src + i);
+            float tx, ty, tz;
+            xform(sm.M, p.x, p.y, p.z, tx, ty, tz);
+            const int lf = nbr_leaf(v, tx, ty, tz, s);
+            if (lf >= 0) evaluate(i, lf);
         }
     }
     // block reduction in a fixed order: xor-tree inside the warp, warps in index order
@@ -1299,6 +1347,13 @@ int32_t b200_ndt_set_source(b200_ndt* n, const float* xyz, int64_t cnt, int64_t 
 int64_t b200_ndt_num_voxels(b200_ndt* n) { return n ? (int64_t)n->k.n_valid : 0; }
 float b200_ndt_last_ms(b200_ndt* n) { return n ? n->k.last_ms : 0.f; }
 int32_t b200_ndt_last_launches(b200_ndt* n) { return n ? n->k.last_launches : 0; }
+/* profiling aid: SM cycles the state machine (advance) and its Newton solves took over the last align */
+int32_t b200_ndt_debug_cycles(b200_ndt* n, int64_t* step_cycles, int64_t* solve_cycles) {
+    if (!n || !n->k.h_ctl.p) return -1;
+    if (step_cycles) *step_cycles = (int64_t)n->k.h_ctl.p[0].step_cycles;
+    if (solve_cycles) *solve_cycles = (int64_t)n->k.h_ctl.p[0].solve_cycles;
+    return 0;
+}
 
 int64_t b200_ndt_leaves(b200_ndt* n, int64_t max, int64_t* ids, int32_t* npts, double* mean3, double* cov9, double* icov9) {
     if (!n || !n->k.have_target) return 0;
