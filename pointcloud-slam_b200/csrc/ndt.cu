@@ -516,17 +516,25 @@ struct EvalSmem {
     int mode;
     double red[EVAL_THREADS / 32][NACC];
     double res[NACC];
-    int is_last;
+    int is_last, abort;
 };
 
-__global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls, AlignConsts k, double* partials /*[h][NACC][nbx]*/) {
+// LOOP = false: one evaluation per launch (the host enqueues launches back to back; batched alignments, single derivative
+// evaluations).  LOOP = true: ONE cooperative launch runs a whole alignment - after every evaluation the last block to
+// arrive advances the state machine and releases a generation counter the other blocks wait on (all blocks are resident:
+// the launch is cooperative and the grid is one wave), so an align pays neither launch gaps, nor no-op launches after
+// convergence, nor done-flag polls from the host.  Control-block reads bypass L1 (ld.cg): it changes between evaluations.
+template <bool LOOP>
+__global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls, AlignConsts k, double* partials /*[h][NACC][nbx]*/,
+                                                              unsigned int* gen /*LOOP: generation counter, zero at launch*/, int max_evals) {
     Ctl* ctl = ctls + blockIdx.y;
-    if (ctl->done) return;
     __shared__ EvalSmem sm;
     const int tid = threadIdx.x, nbx = gridDim.x;
-    if (tid < 12) sm.M[tid] = ctl->M[tid];
-    for (int i = tid; i < (int)(sizeof(AngleTables) / 4); i += EVAL_THREADS) ((int*)&sm.tab)[i] = ((const int*)&ctl->tab)[i];
-    if (tid == 0) sm.mode = ctl->mode;
+  for (int ev = 0; ev < max_evals; ++ev) {
+    if (__ldcg(&ctl->done)) return;
+    if (tid < 12) sm.M[tid] = __ldcg(&ctl->M[tid]);
+    for (int i = tid; i < (int)(sizeof(AngleTables) / 4); i += EVAL_THREADS) ((int*)&sm.tab)[i] = __ldcg((const int*)&ctl->tab + i);
+    if (tid == 0) sm.mode = __ldcg(&ctl->mode);
     __syncthreads();
     const int mode = sm.mode;
     const int nitems = v.n_src * v.nst;
@@ -623,7 +631,23 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
         sm.is_last = (t == (unsigned)nbx - 1u);
     }
     __syncthreads();
-    if (!sm.is_last) return;
+    if (!sm.is_last) {
+        if (!LOOP) return;
+        // wait for the last block to publish the next request (or the end of the alignment)
+        if (tid == 0) {
+            volatile unsigned int* g = gen;
+            unsigned spins = 0;
+            sm.abort = 0;
+            while (*g == (unsigned)ev) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) { sm.abort = 1; break; }  // watchdog (~seconds): never hang the device
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (sm.abort) return;
+        continue;
+    }
     __threadfence();
     // The last block finishes the evaluation.  Everything below is a serial chain on ONE thread, so what matters is its
     // latency: (1) the partials are reduced by whole warps (lanes stride over the blocks, fixed shuffle tree: deterministic)
@@ -652,7 +676,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
         sctl.step_cycles += clock64() - t0;
     }
     __syncthreads();
-    for (int i = tid; i < (int)(sizeof(Ctl) / 4); i += EVAL_THREADS) ((int*)ctl)[i] = ((const int*)&sctl)[i];
+    for (int i = tid; i < (int)(sizeof(Ctl) / 4); i += EVAL_THREADS) __stcg((int*)ctl + i, ((const int*)&sctl)[i]);
+    if (!LOOP) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(gen, 1u);  // release: generation ev -> ev + 1
+    __syncthreads();
+  }
 }
 
 // one thread per alignment: computeTransformation prologue (:77-105)
@@ -923,6 +953,7 @@ struct Ndt {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    bool coop_launch = false;  // device supports cooperative launches (one-launch align)
     int eval_blocks_per_sm = 0;
     // target
     GridDims gd{};
@@ -985,6 +1016,7 @@ int32_t Ndt::init(const b200_ndt_params* p, int dev) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     sm_count = prop.multiProcessorCount;
+    coop_launch = prop.cooperativeLaunch != 0;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(d_small.reserve(16));
@@ -1175,7 +1207,7 @@ int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
     CUDA_TRY(h_ctl.reserve(h));
     const int64_t items = (int64_t)n_src * prm.search;
     if (!eval_blocks_per_sm) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_blocks_per_sm, k_ndt_eval, EVAL_THREADS, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_blocks_per_sm, k_ndt_eval<false>, EVAL_THREADS, 0));
         if (eval_blocks_per_sm < 1) eval_blocks_per_sm = 1;
     }
     // one resident wave: blocks of all alignments together fill the SMs once (grid-stride inside)
@@ -1192,11 +1224,22 @@ int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
     int* d_left = d_small.p + 10;
     // worst case per alignment: (max_iter + 2) iterations x (1 + 10 trials + 1 Hessian) evaluations
     const int max_launches = single ? 1 : (prm.max_iter + 3) * 12 + 1;
+    static const bool persistent_ok = !(getenv("B200_NDT_LOOP") && atoi(getenv("B200_NDT_LOOP")) == 0);
+    if (!single && h == 1 && persistent_ok && coop_launch) {  // one alignment: the whole Newton / line-search loop in one launch
+        unsigned int* d_gen = (unsigned int*)(d_small.p + 11);
+        CUDA_TRY(cudaMemsetAsync(d_gen, 0, sizeof(unsigned int), stream));
+        Ctl* ctls = d_ctl.p;
+        double* parts = d_partials.p;
+        int max_evals = max_launches;
+        void* args[] = {(void*)&v, (void*)&ctls, (void*)&k, (void*)&parts, (void*)&d_gen, (void*)&max_evals};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ndt_eval<true>, dim3(nbx, 1), dim3(EVAL_THREADS), args, 0, stream));
+        ++launches;
+    } else
     while (launches - 1 < max_launches) {
         // first poll after 12 evaluations: a typical relocalization align (8 iterations, 9-10 evaluations) then ends with one
         // poll and two or three no-op launches instead of two polls and seven no-ops
         const int batch = single ? 1 : (launches == 1 ? LAUNCH_BATCH + 4 : LAUNCH_BATCH);
-        for (int b = 0; b < batch; ++b) k_ndt_eval<<<dim3(nbx, h), EVAL_THREADS, 0, stream>>>(v, d_ctl.p, k, d_partials.p);
+        for (int b = 0; b < batch; ++b) k_ndt_eval<false><<<dim3(nbx, h), EVAL_THREADS, 0, stream>>>(v, d_ctl.p, k, d_partials.p, nullptr, 1);
         launches += batch;
         if (single) break;
         CUDA_TRY(cudaMemsetAsync(d_left, 0, sizeof(int), stream));
