@@ -47,7 +47,7 @@ struct Ctl {  // one per alignment, global memory
     double x_t[6], dir[6];
     double a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_0, d_phi_0, phi_t, d_phi_t, psi_t, d_psi_t;
     double step_min, step_max;
-    int step_iterations, interval_converged, open_interval;
+    int step_iterations, interval_converged, open_interval, req;
     long long solve_cycles, step_cycles;
 };
 
@@ -273,7 +273,7 @@ __device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, doub
         for (int j = 0; j < 6; ++j) a[i][j] = Hs[i * 6 + j];
         a[i][6] = rhs[i];
     }
-    double pmax = 0.0, pmin = 1.7976931348623157e308;
+    double pmax = 0.0, pmin = 1.7976931348623157e308, rinv[6];
     for (int k = 0; k < 6; ++k) {
         int piv = k;
         double best = fabs(a[k][k]);
@@ -285,6 +285,7 @@ __device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, doub
         pmax = fmax(pmax, best);
         pmin = fmin(pmin, best);
         const double inv = 1.0 / a[k][k];
+        rinv[k] = inv;
         for (int i = k + 1; i < 6; ++i) {
             const double f = a[i][k] * inv;
             for (int j = k + 1; j < 7; ++j) a[i][j] -= f * a[k][j];
@@ -294,7 +295,7 @@ __device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, doub
     for (int i = 5; i >= 0; --i) {
         double sacc = a[i][6];
         for (int j = i + 1; j < 6; ++j) sacc -= a[i][j] * x[j];
-        x[i] = sacc / a[i][i];
+        x[i] = sacc * rinv[i];  // the pivots' reciprocals are already there: six fewer fp64 divisions on the serial path
     }
     return true;
 }
@@ -366,11 +367,18 @@ __device__ inline double mt_trial_value(const Ctl& c, double f_t, double g_t) {
     return cubic_min(a_u, f_u, g_u, a_t, f_t, g_t);
 }
 
+// The next evaluation is requested at x_t; its transform and angle tables are built after the state machine returns
+// (fulfil_request), with the six sine / cosine pairs computed on six lanes.
 __device__ inline void request_eval(Ctl& c, const double* x, int mode) {
-    pose_matrix(x, c.M);
-    for (int i = 0; i < 16; ++i) c.final_T[i] = c.M[i];  // final_transformation_ follows every trial (:749-753,783-788)
-    angle_tables(x, c.tab);
+    (void)x;  // always c.x_t
     c.mode = mode;
+    c.req = 1;
+}
+__device__ inline void fulfil_request(Ctl& c, const Trig& t) {
+    pose_matrix_core(c.x_t, t.cf[0], t.sf[0], t.cf[1], t.sf[1], t.cf[2], t.sf[2], c.M);
+    for (int i = 0; i < 16; ++i) c.final_T[i] = c.M[i];  // final_transformation_ follows every trial (:749-753,783-788)
+    angle_tables_core(t.cd[0], t.sd[0], t.cd[1], t.sd[1], t.cd[2], t.sd[2], c.tab);
+    c.req = 0;
 }
 
 __device__ inline void finish(Ctl& c, const AlignConsts& k, bool converged) {
@@ -517,6 +525,7 @@ struct EvalSmem {
     double red[EVAL_THREADS / 32][NACC];
     double res[NACC];
     int is_last, abort;
+    Trig trig;
 };
 
 // LOOP = false: one evaluation per launch (the host enqueues launches back to back; batched alignments, single derivative
@@ -676,6 +685,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
         sctl.step_cycles += clock64() - t0;
     }
     __syncthreads();
+    if (sctl.req) {  // block-uniform
+        if (tid < 6) trig_of_angle(sctl.x_t, tid, sm.trig);
+        __syncthreads();
+        if (tid == 0) fulfil_request(sctl, sm.trig);
+        __syncthreads();
+    }
     for (int i = tid; i < (int)(sizeof(Ctl) / 4); i += EVAL_THREADS) __stcg((int*)ctl + i, ((const int*)&sctl)[i]);
     if (!LOOP) return;
     __threadfence();
@@ -693,7 +708,7 @@ __global__ void k_ndt_init(Ctl* ctls, int h, const float* __restrict__ guesses /
     Ctl& c = ctls[a];
     c.done = 0; c.ticket = 0; c.phase = phase;
     c.nr_iterations = 0; c.converged = 0; c.evals = 0; c.hess_evals = 0;
-    c.trans_probability = 0; c.score = 0; c.solve_cycles = 0; c.step_cycles = 0;
+    c.trans_probability = 0; c.score = 0; c.solve_cycles = 0; c.step_cycles = 0; c.req = 0;
     c.step_iterations = 0; c.a_t = 0;
     for (int i = 0; i < 6; ++i) { c.g[i] = 0; c.dir[i] = 0; c.x_t[i] = 0; }
     for (int i = 0; i < 36; ++i) c.H[i] = 0;

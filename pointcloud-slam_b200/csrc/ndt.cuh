@@ -104,10 +104,32 @@ __device__ __forceinline__ void xform(const float* M, float x, float y, float z,
 
 // Translation * AngleAxis(x) * AngleAxis(y) * AngleAxis(z) in float (ndt_omp_impl.hpp:129,749-753); float sin/cos
 // evaluated as the correctly rounded value (double evaluation, narrowed)
+// The sines / cosines of a requested pose: cf / sf = correctly rounded floats of the float-narrowed angles (pose_matrix),
+// cd / sd = doubles with computeAngleDerivatives' small-angle snap (angle_tables).  Six independent evaluations: the
+// evaluation kernel computes them on six lanes instead of one after the other.
+struct Trig {
+    double cd[3], sd[3];
+    float cf[3], sf[3];
+};
+__device__ inline void trig_of_angle(const double* p, int which /*0..5*/, Trig& t) {
+    const int a = which % 3;
+    if (which < 3) {
+        if (fabs(p[3 + a]) < 10e-5) { t.cd[a] = 1.0; t.sd[a] = 0.0; }
+        else { t.cd[a] = cos(p[3 + a]); t.sd[a] = sin(p[3 + a]); }
+    } else {
+        const float r = (float)p[3 + a];
+        t.cf[a] = (float)cos((double)r);
+        t.sf[a] = (float)sin((double)r);
+    }
+}
+__device__ inline void pose_matrix_core(const double* p, float cx, float sx, float cy, float sy, float cz, float sz, float* M);
 __device__ inline void pose_matrix(const double* p, float* M /*row-major 4x4*/) {
     const float rx = (float)p[3], ry = (float)p[4], rz = (float)p[5];
     const float cx = (float)cos((double)rx), sx = (float)sin((double)rx), cy = (float)cos((double)ry), sy = (float)sin((double)ry),
                 cz = (float)cos((double)rz), sz = (float)sin((double)rz);
+    pose_matrix_core(p, cx, sx, cy, sy, cz, sz, M);
+}
+__device__ inline void pose_matrix_core(const double* p, float cx, float sx, float cy, float sy, float cz, float sz, float* M) {
     const float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
     const float Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
     const float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
@@ -146,11 +168,15 @@ __device__ inline void euler_012(const float* R, float* res) {
 
 // computeAngleDerivatives (ndt_omp_impl.hpp:271-366), including the small-angle snap and the float
 // table's +sy entry in row d1 (:354) where the double table has -sy (:332).
+__device__ inline void angle_tables_core(double cx, double sx, double cy, double sy, double cz, double sz, AngleTables& t);
 __device__ inline void angle_tables(const double* p, AngleTables& t) {
     double cx, cy, cz, sx, sy, sz;
     if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
     if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
     if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
+    angle_tables_core(cx, sx, cy, sy, cz, sz, t);
+}
+__device__ inline void angle_tables_core(double cx, double sx, double cy, double sy, double cz, double sz, AngleTables& t) {
     const double J[8][3] = {{(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
                             {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
                             {(-sy * cz), sy * sz, cy},
