@@ -1271,6 +1271,9 @@ int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
     cudaEventElapsedTime(&last_ms, ev0, ev1);
     LAUNCH_COUNT(launches);
     last_launches = launches;
+    if (!single)
+        for (int a = 0; a < h; ++a)
+            if (!h_ctl.p[a].done) B200_FAIL(B200_ERR_CUDA, "NDT alignment did not run to completion (evaluation bound or barrier watchdog)");
     return B200_OK;
 }
 
