@@ -514,6 +514,25 @@ __device__ void advance(Ctl& c, const AlignConsts& k, const double* res) {
     }
 }
 
+// One level of the recursive-halving warp reduction of an N-vector held in v[0..N): lanes with bit MASK set keep the upper
+// half [H, N) (moved to the front), the others the lower half [0, H); each adds what its partner hands over.  `base` is the
+// original index of v[0], `len` how many entries of this lane's vector are real (the upper half is shorter when N is odd).
+template <int N, int MASK>
+__device__ __forceinline__ void halve_level(double (&v)[NACC], int lane, int& base, int& len) {
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double lo = v[i];
+        const double hi = (i + H < N) ? v[i + H] : 0.0;
+        const double keep = up ? hi : lo;
+        const double send = up ? lo : hi;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+    base += up ? H : 0;
+    len = up ? max(len - H, 0) : min(len, H);
+}
+
 // ------------------------------------------------------------------ evaluation kernel
 constexpr int kPairCap = 2048;  // (point, leaf) pairs a block can queue
 struct EvalSmem {
@@ -618,13 +637,20 @@ __global__ void __launch_bounds__(EVAL_THREADS, 1) k_ndt_eval(View v, Ctl* ctls,
             if (lf >= 0) evaluate(i, lf);
         }
     }
-    // block reduction in a fixed order: xor-tree inside the warp, warps in index order
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) {
-        double a = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if ((tid & 31) == 0) sm.red[tid >> 5][i] = a;
+    // block reduction in a fixed order.  Inside the warp: recursive halving - at every level a lane keeps one half of its
+    // vector and hands the other half to its partner, so the 43 sums cost 22 + 11 + 6 + 3 + 2 = 44 exchanges instead of
+    // 43 x 5, and end up spread over the lanes (two per lane); then the warps in index order.
+    {
+        const int lane = tid & 31;
+        int base = 0, len = NACC;
+        halve_level<NACC, 16>(acc, lane, base, len);
+        halve_level<(NACC + 1) / 2, 8>(acc, lane, base, len);
+        halve_level<((NACC + 1) / 2 + 1) / 2, 4>(acc, lane, base, len);
+        halve_level<(((NACC + 1) / 2 + 1) / 2 + 1) / 2, 2>(acc, lane, base, len);
+        halve_level<((((NACC + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2, 1>(acc, lane, base, len);
+        static_assert((((((NACC + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 == 2, "two sums per lane after five levels");
+        if (len > 0) sm.red[tid >> 5][base] = acc[0];
+        if (len > 1) sm.red[tid >> 5][base + 1] = acc[1];
     }
     __syncthreads();
     if (tid < NACC) {
