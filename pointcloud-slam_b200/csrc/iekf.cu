@@ -42,6 +42,7 @@ struct PointState {  // per-point arrays that persist across passes and scans (l
 // hdr: the {x, P, n, prev_n} header as it arrived from the host (either inside the staged scan block or
 // already in the control block itself)
 __global__ void k_iekf_init(Ctl* ctl, const Ctl* hdr, PointState ps, int force_converge) {
+    pdl_trigger();  // the first search may be scheduled while this kernel runs (it waits in griddepcontrol.wait)
     const int tid = threadIdx.x + blockIdx.x * blockDim.x;
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < NS * NS; i += blockDim.x) {
@@ -65,8 +66,8 @@ __global__ void k_iekf_init(Ctl* ctl, const Ctl* hdr, PointState ps, int force_c
             ctl->ticket = 0;
             ctl->passes = ctl->knn_passes = ctl->any_valid = ctl->converged = 0;
             for (int i = 0; i < B200_MAX_PASSES; ++i) { ctl->n_eff[i] = 0; ctl->knn[i] = 0; }
-            make_pass_consts(ctl->x, ctl->pc);
         }
+        make_pass_consts_par(hdr->x, ctl->pc);  // four independent pieces on four warps
     }
     // vector::resize(cur_pts, default) semantics: slots at or beyond the previous scan's size are fresh
     const int n = hdr->n, prev = hdr->prev_n;
