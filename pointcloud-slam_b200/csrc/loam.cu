@@ -490,7 +490,7 @@ int32_t b200_loam_optimize(b200_loam* h, const float* corner_xyz, int64_t n_corn
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     int launches = 0, it = 0;
     while (it < iter_num) {
-        const int batch = std::min(4, iter_num - it);
+        const int batch = std::min(it == 0 ? 6 : 4, iter_num - it);  // typical scans converge in 5-6 iterations: one poll
         for (int b = 0; b < batch; ++b) {
             loam_search(h, n_corner, n_surf);
             loam::k_loam_accum<<<nbx, loam::ACC_THREADS, 0, h->stream>>>(h->d_pts.p, h->d_nb.p, h->d_cnt.p, (int)n_corner, (int)n, h->d_ctl, h->d_partials.p, 0,
