@@ -203,7 +203,7 @@ class PinnedCloud:
             self.array = None
             try:
                 lib().b200_host_free(self.ptr)
-            except TypeError:
+            except Exception:  # interpreter shutdown: module globals may already be torn down
                 pass
             self.ptr = C.c_void_p()
 
