@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <cub/cub.cuh>
+#include <chrono>
 
 #include <algorithm>
 #include <cmath>
@@ -334,19 +335,27 @@ __global__ void k_extract(Table t, const uint32_t* __restrict__ slots, int64_t m
 // exchange: owner rank of a voxel, records grouped by owner
 __device__ __forceinline__ int owner_of(unsigned long long key, int nranks) { return (int)((mix64(key ^ 0x9E3779B97F4A7C15ULL) >> 8) % (uint32_t)nranks); }
 
+// Both kernels hand out positions per owner with ONE atomic per (warp, owner): a plain atomicAdd per voxel is millions of
+// atomics on nranks addresses (2.3 ms for 4.4 M voxels on two ranks).
 __global__ void k_owner_count(Table t, int nranks, unsigned long long* __restrict__ counts) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > t.mask) return;
-    const unsigned long long k = t.keys[s];
-    if (k == kEmptyKey) return;
-    atomicAdd(counts + owner_of(k, nranks), 1ull);
+    const unsigned long long k = s <= t.mask ? t.keys[s] : kEmptyKey;
+    const int owner = k == kEmptyKey ? -1 : owner_of(k, nranks);
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    if (owner >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
 }
 __global__ void k_owner_scatter(Table t, int nranks, unsigned long long* __restrict__ cursor /*starts at the owner offsets*/, Xfer* __restrict__ out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > t.mask) return;
-    const unsigned long long k = t.keys[s];
-    if (k == kEmptyKey) return;
-    const unsigned long long i = atomicAdd(cursor + owner_of(k, nranks), 1ull);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long k = s <= t.mask ? t.keys[s] : kEmptyKey;
+    const int owner = k == kEmptyKey ? -1 : owner_of(k, nranks);
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (owner >= 0 && lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (owner < 0) return;
+    const unsigned long long i = base + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
     const Acc a = t.acc[s];
     out[i] = Xfer{k, t.cnt[s], 0u, a.sx, a.sy, a.sz, a.si};
 }
@@ -809,6 +818,7 @@ int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h) {
     const int R = comm->nranks;
     const uint32_t T = b.tab.mask + 1;
     const int64_t m = b.h_ctr.p[0];
+    const auto t_merge0 = std::chrono::steady_clock::now();
     CUDA_TRY(b.d_counts.reserve(2 * (size_t)R + (size_t)R * R));
     CUDA_TRY(b.h_counts.reserve((size_t)R * R + 2 * R));
     unsigned long long* d_cnt = b.d_counts.p;           // [R] my records per owner
@@ -819,37 +829,68 @@ int32_t b200_mapbuild_merge(b200_comm* comm, b200_mapbuild* h) {
     NCCL_TRY(comm, comm->AllGather(d_cnt, d_all, R, ncclUint64, comm->comm, b.stream));
     CUDA_TRY(cudaMemcpyAsync(b.h_counts.p, d_all, (size_t)R * R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b.stream));
     CUDA_TRY(cudaStreamSynchronize(b.stream));
+    const double t_count = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_merge0).count();
+    const bool timing = getenv("B200_TIMING") != nullptr;
+    double t_alloc = 0, t_scatter = 0, t_xchg = 0, t_clear = 0;
+    auto lap = [&](double& dst) {  // profiling only: drains the stream
+        if (!timing) return;
+        cudaStreamSynchronize(b.stream);
+        dst = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_merge0).count();
+    };
     const unsigned long long* all = b.h_counts.p;  // all[src * R + dst]
     std::vector<unsigned long long> send_off(R + 1, 0), recv_off(R + 1, 0);
     for (int r = 0; r < R; ++r) {
         send_off[r + 1] = send_off[r] + all[(size_t)comm->rank * R + r];
         recv_off[r + 1] = recv_off[r] + all[(size_t)r * R + comm->rank];
     }
-    CUDA_TRY(b.d_send.reserve(std::max<size_t>(send_off[R], 1)));
-    CUDA_TRY(b.d_recv.reserve(std::max<size_t>(recv_off[R], 1)));
+    // exchange buffers from the stream-ordered pool (kept by the pool between merges: a cudaMalloc of 2 x 200 MB here cost
+    // 3.5 - 36 ms and a device-wide synchronisation)
+    {
+        static bool pool_set[64] = {};
+        if (b.device < 64 && !pool_set[b.device]) {
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, b.device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_set[b.device] = true;
+        }
+    }
+    Xfer *d_send = nullptr, *d_recv = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_send, std::max<size_t>(send_off[R], 1) * sizeof(Xfer), b.stream));
+    CUDA_TRY(cudaMallocAsync((void**)&d_recv, std::max<size_t>(recv_off[R], 1) * sizeof(Xfer), b.stream));
+    lap(t_alloc);
     unsigned long long* h_cur = b.h_counts.p + (size_t)R * R;
     for (int r = 0; r < R; ++r) h_cur[r] = send_off[r];
     CUDA_TRY(cudaMemcpyAsync(d_cursor, h_cur, R * sizeof(unsigned long long), cudaMemcpyHostToDevice, b.stream));
-    k_owner_scatter<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab, R, d_cursor, b.d_send.p);
+    k_owner_scatter<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab, R, d_cursor, d_send);
+    lap(t_scatter);
     CUDA_TRY(cudaEventRecord(b.ev0, b.stream));
     NCCL_TRY(comm, comm->GroupStart());
     for (int r = 0; r < R; ++r) {
         const size_t ns = (size_t)(send_off[r + 1] - send_off[r]) * sizeof(Xfer), nr = (size_t)(recv_off[r + 1] - recv_off[r]) * sizeof(Xfer);
-        if (ns) NCCL_TRY(comm, comm->Send(b.d_send.p + send_off[r], ns, ncclChar, r, comm->comm, b.stream));
-        if (nr) NCCL_TRY(comm, comm->Recv(b.d_recv.p + recv_off[r], nr, ncclChar, r, comm->comm, b.stream));
+        if (ns) NCCL_TRY(comm, comm->Send(d_send + send_off[r], ns, ncclChar, r, comm->comm, b.stream));
+        if (nr) NCCL_TRY(comm, comm->Recv(d_recv + recv_off[r], nr, ncclChar, r, comm->comm, b.stream));
     }
     NCCL_TRY(comm, comm->GroupEnd());
     CUDA_TRY(cudaEventRecord(b.ev1, b.stream));
+    lap(t_xchg);
     // rebuild the table from what this rank owns
     k_table_clear<<<(T + 255) / 256, 256, 0, b.stream>>>(b.tab);
+    lap(t_clear);
     CUDA_TRY(cudaMemsetAsync(b.d_ctr, 0, 8 * sizeof(unsigned int), b.stream));
     const int64_t mr = (int64_t)recv_off[R];
-    if (mr) k_merge_records<<<(unsigned)((mr + 255) / 256), 256, 0, b.stream>>>(b.d_recv.p, mr, b.tab, b.d_ctr, (unsigned int)b.capacity, b.d_ctr + 1);
+    if (mr) k_merge_records<<<(unsigned)((mr + 255) / 256), 256, 0, b.stream>>>(d_recv, mr, b.tab, b.d_ctr, (unsigned int)b.capacity, b.d_ctr + 1);
+    cudaFreeAsync(d_send, b.stream);
+    cudaFreeAsync(d_recv, b.stream);
     LAUNCH_COUNT(4);
     b.n_sorted = -1;
     rc = b.check();
     cudaEventElapsedTime(&b.last_ms, b.ev0, b.ev1);
-    (void)m;
+    if (getenv("B200_TIMING")) {
+        const double t_end = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_merge0).count();
+        fprintf(stderr, "[b200_mapbuild_merge] rank %d: %lld voxels, table %u slots, %llu out / %llu in; cumulative ms: count+allgather %.3f, buffers %.3f, "
+                        "scatter %.3f, exchange %.3f, clear %.3f, rebuild+check %.3f (NCCL events %.3f)\n", comm->rank, (long long)m, T,
+                (unsigned long long)send_off[R], (unsigned long long)recv_off[R], t_count, t_alloc, t_scatter, t_xchg, t_clear, t_end, b.last_ms);
+    }
     return rc;
 }
 float b200_mapbuild_last_exchange_ms(b200_mapbuild* h) { return h ? h->b.last_ms : 0.f; }
