@@ -144,10 +144,17 @@ __global__ void k_lookup_runs(const uint64_t* __restrict__ uniq, const int32_t* 
 __global__ void k_collect_live(const MapEntry* __restrict__ ent, const int2* __restrict__ aux, uint32_t tsize, uint64_t* __restrict__ out,
                                unsigned int* __restrict__ n_out) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= tsize) return;
-    const uint64_t k = ent[s].key;
-    if (k == kEmptyKey || k == kTombKey) return;
-    const unsigned int i = atomicAdd(n_out, 1u);
+    const int lane = threadIdx.x & 31;
+    const uint64_t k = s < tsize ? ent[s].key : kEmptyKey;
+    const bool is_live = k != kEmptyKey && k != kTombKey;
+    const unsigned live = __ballot_sync(0xffffffffu, is_live);  // one atomic per warp, not per voxel
+    if (!live) return;
+    const int leader = __ffs(live) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(live));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!is_live) return;
+    const unsigned int i = base + (unsigned int)__popc(live & ((1u << lane) - 1u));
     out[i] = ((uint64_t)(uint32_t)aux[s].y << 32) | (uint64_t)s;
 }
 __global__ void k_evict(const int32_t* __restrict__ victims, int nv, MapEntry* ent, int2* aux, MapCounters* ctr) {

@@ -314,10 +314,16 @@ __global__ void k_table_clear(Table t) {
 // occupied slots -> (key, slot) pairs
 __global__ void k_table_list(Table t, unsigned long long* __restrict__ keys, uint32_t* __restrict__ slots, unsigned int* n_out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > t.mask) return;
-    const unsigned long long k = t.keys[s];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long k = s <= t.mask ? t.keys[s] : kEmptyKey;
+    const unsigned live = __ballot_sync(0xffffffffu, k != kEmptyKey);  // one atomic per warp, not per voxel
+    if (!live) return;
+    const int leader = __ffs(live) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(live));
+    base = __shfl_sync(0xffffffffu, base, leader);
     if (k == kEmptyKey) return;
-    const unsigned int i = atomicAdd(n_out, 1u);
+    const unsigned int i = base + (unsigned int)__popc(live & ((1u << lane) - 1u));
     keys[i] = k;
     slots[i] = s;
 }
