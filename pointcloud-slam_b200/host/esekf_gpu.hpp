@@ -27,6 +27,34 @@ struct EsekfOptions {
     double filter_size_map = 0.5;     // filter_size_map_min_
 };
 
+/// A scan buffer in page-locked memory (b200_host_alloc): update_iterated_dyn_share_modified then ships the records as they
+/// are and unpacks them on the device instead of packing them on the host first.  data() / size() like std::vector, so it
+/// can be handed to the update directly; fill it where the downsampled scan is produced.
+template <typename PointT>
+class PinnedScan {
+   public:
+    using value_type = PointT;
+    explicit PinnedScan(size_t capacity) : cap_(capacity) {
+        void* p = nullptr;
+        check(b200_host_alloc(capacity * sizeof(PointT), &p), "b200_host_alloc");
+        data_ = static_cast<PointT*>(p);
+    }
+    ~PinnedScan() { b200_host_free(data_); }
+    PinnedScan(const PinnedScan&) = delete;
+    PinnedScan& operator=(const PinnedScan&) = delete;
+    PointT* data() { return data_; }
+    const PointT* data() const { return data_; }
+    size_t size() const { return n_; }
+    size_t capacity() const { return cap_; }
+    void resize(size_t n) { n_ = n <= cap_ ? n : cap_; }
+    PointT& operator[](size_t i) { return data_[i]; }
+    const PointT& operator[](size_t i) const { return data_[i]; }
+
+   private:
+    PointT* data_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
 template <typename MapT>
 class Esekf {
    public:

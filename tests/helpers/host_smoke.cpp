@@ -51,6 +51,21 @@ int main() {
         const StateVec& xo = kf.get_x();
         std::printf("iekf valid %d passes %d n_eff %d gpu_ms %.3f pos %.4f %.4f %.4f\n", (int)valid, kf.stats().passes, kf.stats().n_eff[0], ms, xo[0], xo[1], xo[2]);
         if (!valid || std::fabs(xo[0] - 0.03) > 0.01 || std::fabs(xo[1] + 0.02) > 0.01 || std::fabs(xo[2] - 0.01) > 0.01) return 3;
+        {   // the same scan from a page-locked buffer (unpacked on the device): same posterior on a fresh filter
+            PinnedScan<PointXYZINormal> pinned(scan.size());
+            pinned.resize(scan.size());
+            for (size_t i = 0; i < scan.size(); ++i) pinned[i] = scan[i];
+            Esekf<decltype(ivox)> kf_pin(ivox);
+            kf_pin.change_x(x);
+            kf_pin.change_P(P);
+            double ms2 = 0;
+            Esekf<decltype(ivox)> kf_ref(ivox);
+            kf_ref.change_x(x);
+            kf_ref.change_P(P);
+            if (!kf_pin.update_iterated_dyn_share_modified(pinned, ms2) || !kf_ref.update_iterated_dyn_share_modified(scan, ms2)) return 31;
+            for (int i = 0; i < 26; ++i)
+                if (kf_pin.get_x()[i] != kf_ref.get_x()[i]) return 32;
+        }
         auto target = std::make_shared<Cloud>();
         target->points = map;
         auto source = std::make_shared<Cloud>();
