@@ -219,7 +219,9 @@ struct Table {
     uint32_t mask;
 };
 
-__device__ __forceinline__ int table_slot(const Table& t, unsigned long long key, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
+// `created` counts the voxels this thread created; the caller adds the warp's total to the voxel counter with ONE atomic at
+// the end of the kernel (count_created) - an atomicAdd per new voxel is millions of atomics on a single address.
+__device__ __forceinline__ int table_slot(const Table& t, unsigned long long key, unsigned int& created, unsigned int* err) {
     uint32_t slot = mix64(key) & t.mask;
     for (uint32_t probes = 0; probes <= t.mask; ++probes) {
         const unsigned long long k = t.keys[slot];
@@ -227,7 +229,7 @@ __device__ __forceinline__ int table_slot(const Table& t, unsigned long long key
         if (k == kEmptyKey) {
             const unsigned long long old = atomicCAS(t.keys + slot, kEmptyKey, key);
             if (old == kEmptyKey) {
-                if (atomicAdd(n_voxels, 1u) + 1u > capacity) atomicAdd(err, 1u);
+                ++created;
                 return (int)slot;
             }
             if (old == key) return (int)slot;
@@ -236,6 +238,13 @@ __device__ __forceinline__ int table_slot(const Table& t, unsigned long long key
     }
     atomicAdd(err, 1u);
     return -1;
+}
+// every thread of the block calls this once, converged, at the end of the kernel
+__device__ __forceinline__ void count_created(unsigned int created, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
+    for (int o = 16; o > 0; o >>= 1) created += __shfl_xor_sync(0xffffffffu, created, o);
+    if ((threadIdx.x & 31) == 0 && created) {
+        if (atomicAdd(n_voxels, created) + created > capacity) atomicAdd(err, 1u);  // the table has >= 2 x capacity slots: flagged, not overrun
+    }
 }
 
 // One keyframe (or several: `frame_of` maps a point to its pose) through pcl::transformPointCloud and into the table.
@@ -247,6 +256,7 @@ struct PoseM {
 __global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM pose, float inv_leaf, Table t, unsigned int* n_voxels,
                              unsigned int capacity, unsigned int* err) {
     const float* M = pose.m;
+    unsigned int created = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 p = __ldg(pts + i);
         const float x = ((M[0] * p.x + M[1] * p.y) + M[2] * p.z) + M[3];
@@ -256,7 +266,7 @@ __global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM po
         const int cx = (int)floorf(x * inv_leaf), cy = (int)floorf(y * inv_leaf), cz = (int)floorf(z * inv_leaf);
         if (!cell_in_range(cx, cy, cz)) { atomicAdd(err + 1, 1u); continue; }
         const unsigned long long key = pack_key(cz, cy, cx);
-        const int s = table_slot(t, key, n_voxels, capacity, err);
+        const int s = table_slot(t, key, created, err);
         if (s < 0) continue;
         atomicAdd(&t.acc[s].sx, (double)x);
         atomicAdd(&t.acc[s].sy, (double)y);
@@ -264,6 +274,7 @@ __global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM po
         atomicAdd(&t.acc[s].si, (double)p.w);
         atomicAdd(t.cnt + s, 1u);
     }
+    count_created(created, n_voxels, capacity, err);
 }
 
 // Several keyframes per launch (blockIdx.y = keyframe): one 100k-point keyframe is 391 blocks, less than three per SM, and
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float i
     const float* M = d.m;
     const float4* __restrict__ pts = d.pts;
     const int64_t n = d.n;
+    unsigned int created = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 p = __ldg(pts + i);
         const float x = ((M[0] * p.x + M[1] * p.y) + M[2] * p.z) + M[3];
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float i
         const int cx = (int)floorf(x * inv_leaf), cy = (int)floorf(y * inv_leaf), cz = (int)floorf(z * inv_leaf);
         if (!cell_in_range(cx, cy, cz)) { atomicAdd(err + 1, 1u); continue; }
         const unsigned long long key = pack_key(cz, cy, cx);
-        const int s = table_slot(t, key, n_voxels, capacity, err);
+        const int s = table_slot(t, key, created, err);
         if (s < 0) continue;
         atomicAdd(&t.acc[s].sx, (double)x);
         atomicAdd(&t.acc[s].sy, (double)y);
@@ -301,6 +313,7 @@ __global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float i
         atomicAdd(&t.acc[s].si, (double)p.w);
         atomicAdd(t.cnt + s, 1u);
     }
+    count_created(created, n_voxels, capacity, err);
 }
 
 __global__ void k_table_clear(Table t) {
@@ -367,15 +380,19 @@ __global__ void k_owner_scatter(Table t, int nranks, unsigned long long* __restr
 }
 __global__ void k_merge_records(const Xfer* __restrict__ rec, int64_t m, Table t, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const Xfer r = rec[i];
-    const int s = table_slot(t, r.key, n_voxels, capacity, err);
-    if (s < 0) return;
-    atomicAdd(&t.acc[s].sx, r.sx);
-    atomicAdd(&t.acc[s].sy, r.sy);
-    atomicAdd(&t.acc[s].sz, r.sz);
-    atomicAdd(&t.acc[s].si, r.si);
-    atomicAdd(t.cnt + s, r.n);
+    unsigned int created = 0;
+    if (i < m) {
+        const Xfer r = rec[i];
+        const int s = table_slot(t, r.key, created, err);
+        if (s >= 0) {
+            atomicAdd(&t.acc[s].sx, r.sx);
+            atomicAdd(&t.acc[s].sy, r.sy);
+            atomicAdd(&t.acc[s].sz, r.sz);
+            atomicAdd(&t.acc[s].si, r.si);
+            atomicAdd(t.cnt + s, r.n);
+        }
+    }
+    count_created(created, n_voxels, capacity, err);
 }
 
 static uint32_t next_pow2(uint64_t v) {
