@@ -418,7 +418,6 @@ struct Builder {
     DevBuf<uint32_t> d_slots, d_slots2;
     DevBuf<int32_t> d_cnt;
     DevBuf<uint8_t> cub_tmp;
-    DevBuf<Xfer> d_send, d_recv;
     PinnedBuf<unsigned long long> h_counts;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t frames = 0, points = 0;
@@ -468,7 +467,7 @@ struct Builder {
         if (have_tab2) free_table(tab2);
         cudaFree(d_ctr);
         h_ctr.release(); d_pts.release(); d_out.release(); d_M.release(); h_M.release(); h_stage.release(); d_keys.release(); d_keys2.release();
-        d_counts.release(); d_slots.release(); d_slots2.release(); d_cnt.release(); cub_tmp.release(); d_send.release(); d_recv.release();
+        d_counts.release(); d_slots.release(); d_slots2.release(); d_cnt.release(); cub_tmp.release();
         h_counts.release();
         for (int i = 0; i < NSTAGE; ++i) { stage_h[i].release(); stage_d[i].release(); if (stage_ev[i]) cudaEventDestroy(stage_ev[i]); }
         if (ev0) cudaEventDestroy(ev0);
