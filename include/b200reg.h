@@ -65,6 +65,11 @@ int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t 
 /* IVox::NumValidGrids() (ivox3d.h:88) / NumPoints() (ivox3d.h:85) */
 int64_t b200_map_num_voxels(b200_map* map);
 int64_t b200_map_num_points(b200_map* map);
+/* Non-finite points and points outside the +-2^20-cell key range are NOT inserted (the reference's (int)round(NaN) is
+ * undefined behaviour; ivox3d.h:284-286): the rest of the batch goes in, the call returns B200_OK, and this reports how
+ * many points were dropped so far (return value) and by the last insert (*last_batch, may be NULL).  Dropped points
+ * still consume insertion ordinals. */
+int64_t b200_map_dropped(b200_map* map, int64_t* last_batch);
 
 /* ------------------------------------------------------------------------- *
  * B2 — IEKF measurement update.  Replaces

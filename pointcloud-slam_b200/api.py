@@ -109,6 +109,8 @@ def lib():
     L.b200_map_last_knn_ms.argtypes = [vp]
     L.b200_map_evicted.restype = i64
     L.b200_map_evicted.argtypes = [vp]
+    L.b200_map_dropped.restype = i64
+    L.b200_map_dropped.argtypes = [vp, vp]
     L.b200_flush_l2.argtypes = [i32]
     L.b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.b200_host_free.argtypes = [vp]
@@ -262,6 +264,12 @@ class IVox:
 
     def evicted(self) -> int:
         return int(lib().b200_map_evicted(self.h))
+
+    def dropped(self):
+        """(points dropped so far, by the last AddPoints) - non-finite or out-of-range points are skipped, not inserted."""
+        last = C.c_int64(0)
+        tot = lib().b200_map_dropped(self.h, C.byref(last))
+        return int(tot), int(last.value)
 
     def NumValidGrids(self) -> int:
         return int(lib().b200_map_num_voxels(self.h))

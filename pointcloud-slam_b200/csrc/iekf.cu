@@ -366,11 +366,11 @@ struct Iekf {
     // the kernel sequence of one update is captured once into a CUDA graph and replayed (the control flow
     // lives on the device, so the sequence never changes); re-captured only when a buffer moves
     struct GraphKey {
-        const void *pts, *hdr, *ent, *pool, *plane, *nb;
+        const void *pts, *hdr, *ent, *pool, *plane, *nb, *nbc;   // every pointer baked into the captured launches
         unsigned search_grid;
         int single, force, knn_mode;
         bool operator==(const GraphKey& o) const {
-            return pts == o.pts && hdr == o.hdr && ent == o.ent && pool == o.pool && plane == o.plane && nb == o.nb &&
+            return pts == o.pts && hdr == o.hdr && ent == o.ent && pool == o.pool && plane == o.plane && nb == o.nb && nbc == o.nbc &&
                    search_grid == o.search_grid && single == o.single && force == o.force && knn_mode == o.knn_mode;
         }
     };
@@ -537,7 +537,7 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
         if (rc) return rc;
     } else {
         const MapView mv0 = map->view();
-        GraphKey key{d_pts, d_hdr, mv0.ent, mv0.pool, ps.plane, d_nb.p, search_grid, single_pass, force_converge, map->knn_mode()};
+        GraphKey key{d_pts, d_hdr, mv0.ent, mv0.pool, ps.plane, d_nb.p, d_nbc.p, search_grid, single_pass, force_converge, map->knn_mode()};
         if (gexec && key == gkey) {
             CUDA_TRY(cudaGraphLaunch(gexec, stream));
             ++graph_replays;

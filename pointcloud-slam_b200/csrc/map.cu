@@ -21,11 +21,11 @@ __global__ void k_point_keys(const float4* __restrict__ pts, int n, float inv_re
     if (i >= n) return;
     float4 p = pts[i];
     int cx = pos2cell(p.x, inv_res), cy = pos2cell(p.y, inv_res), cz = pos2cell(p.z, inv_res);
-    if (!cell_in_range(cx, cy, cz) || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
-        atomicAdd(&ctr->err_range, 1u);
-        cx = cy = cz = 0;
-    }
-    keys[i] = pack_key(cx, cy, cz);
+    // a non-finite or out-of-range point is dropped, not inserted: its key sorts behind every voxel key and the run of
+    // such keys is skipped by the upsert; the count is reported as a non-fatal status (b200_map_dropped)
+    const bool bad = !cell_in_range(cx, cy, cz) || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+    if (bad) atomicAdd(&ctr->err_range, 1u);
+    keys[i] = bad ? kDropKey : pack_key(cx, cy, cz);
     vals[i] = i;
 }
 
@@ -41,6 +41,12 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     if (r >= *nruns) return;
     const uint64_t key = uniq[r];
     const int c = cnt[r];
+    if (key == kDropKey) {  // the dropped points of this batch
+        run_dst[r] = -1;
+        run_reloc[r] = -1;
+        run_oldcnt[r] = 0;
+        return;
+    }
     // LRU recency = ordinal of the last point that touched the voxel (the sort is stable: last element of the run)
     const int stamp = base_ord + sorted_vals[run_off[r] + c - 1];
     uint32_t slot = hash_key(key) & tmask;
@@ -131,6 +137,11 @@ __global__ void k_lookup_runs(const uint64_t* __restrict__ uniq, const int32_t* 
     const uint64_t key = uniq[r];
     uint32_t slot = hash_key(key) & tmask;
     int found = -1;
+    if (key == kDropKey) {  // dropped points create nothing and touch nothing
+        run_slot[r] = -2;
+        run_first[r] = 0;
+        return;
+    }
     while (true) {
         const uint64_t k = ent[slot].key;
         if (k == key) { found = (int)slot; break; }
@@ -384,7 +395,7 @@ int32_t Map::evict_for_batch(int64_t n) {
     CUDA_TRY(cudaStreamSynchronize(stream));
     const int32_t *slot = h_runs.p, *first = h_runs.p + nruns;
     int64_t n_new = 0;
-    for (int r = 0; r < nruns; ++r) n_new += slot[r] < 0;
+    for (int r = 0; r < nruns; ++r) n_new += slot[r] == -1;
     const int64_t capacity = (int64_t)prm.capacity_voxels;
     if ((int64_t)h_ctr.num_voxels + n_new < capacity) return B200_OK;
     // LRU order of the live voxels
@@ -406,8 +417,8 @@ int32_t Map::evict_for_batch(int64_t n) {
     using Ev = std::pair<int64_t, int>;                            // (time, run)
     std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> heap;
     for (int r = 0; r < nruns; ++r) {
-        if (slot[r] < 0) heap.push({(int64_t)first[r], r});
-        else touched[slot[r]] = {r, (int64_t)first[r]};
+        if (slot[r] == -1) heap.push({(int64_t)first[r], r});
+        else if (slot[r] >= 0) touched[slot[r]] = {r, (int64_t)first[r]};
     }
     std::vector<int32_t> victims;
     int64_t size = (int64_t)h_ctr.num_voxels;
@@ -457,15 +468,17 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     CUDA_TRY(v_in.reserve(n)); CUDA_TRY(v_out.reserve(n));
     CUDA_TRY(run_cnt.reserve(n)); CUDA_TRY(run_off.reserve(n)); CUDA_TRY(run_dst.reserve(n)); CUDA_TRY(run_reloc.reserve(2 * n));
     const int nb = (int)((n + 255) / 256);
+    // the three error counters describe ONE batch (they used to be cumulative: one bad point failed every later insert)
+    CUDA_TRY(cudaMemsetAsync(&d_ctr->err_range, 0, 3 * sizeof(unsigned int), stream));
     k_point_keys<<<nb, 256, 0, stream>>>(d_pts, (int)n, inv_res, k_in.p, v_in.p, d_ctr);
     size_t t1 = 0, t2 = 0, t3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 64, stream);
     cub::DeviceRunLengthEncode::Encode(nullptr, t2, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream);
     cub::DeviceScan::ExclusiveSum(nullptr, t3, run_cnt.p, run_off.p, (int)n, stream);
     size_t tmp = t1 > t2 ? t1 : t2;
     tmp = tmp > t3 ? tmp : t3;
     CUDA_TRY(cub_tmp.reserve(tmp));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 63, stream));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 64, stream));
     CUDA_TRY(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, tmp, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream));
     // exclusive scan over all n slots (entries past nruns are garbage and never read)
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, run_cnt.p, run_off.p, (int)n, stream));
@@ -489,7 +502,8 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     h_ctr = *h_ctr_pin.p;
     next_ord += n;
     h_ctr.num_points = (unsigned long long)next_ord;
-    if (h_ctr.err_range) B200_FAIL(B200_ERR_RANGE, "point outside the voxel key range or non-finite");
+    dropped_last = h_ctr.err_range;  // non-fatal: the rest of the batch is in the map
+    dropped_total += h_ctr.err_range;
     if (h_ctr.err_pool) B200_FAIL(B200_ERR_NOMEM, "point pool exhausted");
     if (h_ctr.err_capacity) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity exceeded (internal: eviction pre-pass missed a batch)");
     return B200_OK;
@@ -620,6 +634,11 @@ int32_t b200_flush_l2(int32_t device) {
 /* device time (CUDA events) of the search kernel of the last b200_map_knn5 call */
 float b200_map_last_knn_ms(b200_map* map) { return map ? map->m.last_knn_ms : 0.f; }
 int64_t b200_map_evicted(b200_map* map) { return map ? (int64_t)map->m.evicted_total : 0; }
+int64_t b200_map_dropped(b200_map* map, int64_t* last_batch) {
+    if (!map) return 0;
+    if (last_batch) *last_batch = (int64_t)map->m.dropped_last;
+    return (int64_t)map->m.dropped_total;
+}
 int64_t b200_map_num_voxels(b200_map* map) { return map ? (int64_t)map->m.h_ctr.num_voxels : 0; }
 int64_t b200_map_num_points(b200_map* map) { return map ? (int64_t)map->m.h_ctr.live_points : 0; }
 

@@ -65,6 +65,7 @@ __device__ __forceinline__ MapEntry ld_entry(const MapEntry* e) {
 
 constexpr uint64_t kInfKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;  // evicted voxel: keeps probe chains intact until the next rehash
+constexpr uint64_t kDropKey = 0x8000000000000000ull;  // insert: key of a non-finite / out-of-range point (sorts behind every voxel key)
 constexpr int kRankBits = 26;  // in-voxel index bits inside the tie-break rank
 
 // sorted insert of k into ascending t[0..4]
@@ -328,6 +329,7 @@ struct Map {
     MapCounters h_ctr{};   // mirror after the last insert
     int64_t next_ord = 0;
     uint64_t tombstones = 0, evicted_total = 0;
+    uint64_t dropped_last = 0, dropped_total = 0;  // non-finite / out-of-range points skipped by the last insert / so far
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_knn_ms = 0.f;
     // scratch

@@ -92,13 +92,33 @@ def test_knn_edge_cases(oracle, api, small_cfg):
     assert g.GetClosestPoint(np.zeros((0, 3), np.float32))[0].shape == (0, 5)
 
 
-def test_out_of_range_point_is_an_error(api):
-    g = api.IVox(resolution=0.2, nearby=6)
-    with pytest.raises(api.B200Error):
-        g.AddPoints(np.array([[1e9, 0, 0]], np.float32))
-    g2 = api.IVox(resolution=0.2, nearby=6)
-    with pytest.raises(api.B200Error):
-        g2.AddPoints(np.array([[np.nan, 0, 0]], np.float32))
+def test_bad_points_are_dropped_not_fatal(oracle, api, small_cfg):
+    """One NaN / Inf / out-of-range lidar return must not poison the map or fail every later insert: such points
+    are skipped (they still take an ordinal), reported through b200_map_dropped, and the rest of the batch goes in."""
+    mp = small_cfg["map"][:30_000].copy()
+    bad_at = [5, 77, 20_000]
+    dirty = mp.copy()
+    dirty[bad_at[0]] = [np.nan, 0, 0]
+    dirty[bad_at[1]] = [1e9, 0, 0]
+    dirty[bad_at[2]] = [0, np.inf, 1]
+    g = api.IVox(resolution=0.5, nearby=18)
+    g.AddPoints(dirty)                       # no exception
+    assert g.dropped() == (3, 3)
+    g.AddPoints(small_cfg["map"][30_000:40_000])   # a clean batch after a dirty one is clean
+    assert g.dropped() == (3, 0)
+    # oracle: the same cloud with the bad points moved far away into voxels no query reaches is equivalent for every query
+    o = oracle.OracleLio(resolution=0.5, nearby=18)
+    clean = mp.copy()
+    clean[bad_at] = [[9e3, 9e3, 9e3], [9.1e3, 9e3, 9e3], [9.2e3, 9e3, 9e3]]
+    o.insert(clean)
+    o.insert(small_cfg["map"][30_000:40_000])
+    assert g.NumPoints() == o.num_points - 3 and g.NumValidGrids() == o.num_voxels - 3
+    q = small_cfg["map"][:3000] + np.float32(0.01)
+    i0, d0, c0 = o.knn5(q)
+    i1, d1, c1 = g.GetClosestPoint(q)
+    np.testing.assert_array_equal(i1, i0)
+    np.testing.assert_array_equal(d1, d0)
+    np.testing.assert_array_equal(c1, c0)
 
 
 @pytest.mark.parametrize("pname", ["livox", "horizon"])
