@@ -1,36 +1,38 @@
 #!/usr/bin/env python
 """bench.py — scan-to-map registration hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--params livox|horizon]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[0] — a synthetic Livox Mid-360-shaped scan (20k points)
-against a 2M-point local map, one jueying_lio point-to-plane IEKF update per step
-(esekf::update_iterated_dyn_share_modified: k-NN + plane fit + residual/Jacobian + reduction + solve,
-<= max_iter+1 passes).  It is the configuration the metric "registered points/sec and ms per IEKF update"
-is quoted on, and it fits one GPU.  The single-scan update does not shard: with --gpus N every
-rank runs an independent replica (one robot / sequence per GPU, no data-path collective), scaling "weak".
+Headline (every N, so that the driver's 1 -> 8 scaling is computed on ONE metric): BASELINE.json's sharded metric,
+"reloc hypotheses/sec at 1/2/4/8 B200" = configs[3]: 4096 initial-pose hypotheses (32 x 32 xy grid at 1 m, 4 yaws) scored
+with pclomp's calculateScore against a 10M-point prior map (1.0 m voxels, DIRECT7).  The map is replicated on every rank
+(rank 0 uploads it once, ncclBroadcast over NVLink), hypothesis h lives on rank h mod N, every rank scores its slice and
+ONE ncclAllGather of 16 bytes per rank carries the local winners (allreduce-argmin).  Strong scaling: 4096 hypotheses in
+total at every N.  A step = one such batch.
 
-value      registered points/s, inputs resident in HBM, timed with CUDA events on the engine's stream (sum over
-           the K timed steps; L2 is flushed, untimed, between steps), max over ranks.
-e2e        same metric through the C-ABI call a ROS node makes (b200_iekf_update) with HOST buffers: host pack +
-           H2D + kernels + D2H inside the timed region (wall clock around the synchronous call).
-roofline   dominant kernel by bytes = the stencil k-NN search (k_search): algorithmic bytes / CUDA-event duration.
+value      hypotheses/s = 4096 / (device time per step, CUDA events on the engine's stream around score kernels + local
+           argmin + collective, L2 flushed (untimed) and the ranks aligned by a device-side rendezvous before each step;
+           mean over the K timed steps, MAX over ranks).
+e2e        same metric through the C-ABI call (b200_reloc_argmin_strided) with the slice's poses in HOST memory: H2D of
+           the poses + kernels + collective + D2H of the winners, wall clock per call, max over ranks.
+roofline   dominant kernel k_ndt_score_batch: algorithmic bytes per launch / its CUDA-event duration.
 cpu_baseline / --impl reference
-           the CPU oracle port of the reference path (oracle/), OpenMP on the box's host cores.
+           the CPU oracle port of calculateScore (oracle/), all host threads, on a bounded sample of the 4096 hypotheses.
+parity     argmin index and score equal to the single-GPU result over all 4096 hypotheses and to the oracle's on a sample.
 
-Two more objects ride on the same JSON line (the other workloads BASELINE.json's metric names):
-ndt        configs[1]: pclomp NDT of the 20k-point scan against a 10M-point prior map (1 m voxels): setInputTarget
-           (voxel-Gaussian build), one computeDerivatives, one full align(); device ms by CUDA events, e2e = wall clock
-           of the C-ABI call with host buffers, and the roofline of the derivative kernel.
-reloc      configs[3]: 4096 initial-pose hypotheses scored against the replicated 10M-point map, hypotheses sharded
-           over the N ranks (strong scaling: 4096 in total), NCCL allreduce-argmin; hypotheses/s = 4096 / max-over-ranks
-           device time, the winner checked against the oracle's argmax at N=1.
-fullmap    configs[4]: construct_full_map - keyframes x 100k points merged into a 0.1 m voxel map, keyframes split over the
-           ranks, partial voxel sums exchanged over NCCL; keyframes/s (--fullmap-frames, default 1600; 10000 = full).
-scan2map   jueying_slam's LOAM-style scan2MapOptimization for one scan: set_map + optimise times.
-sequence   configs[2]: sliding-map odometry (update + MapIncremental per scan) over --seq-scans scans (default 120;
-           1000 is the full configuration and takes ~1 min of host-side ray casting).
-Skip them with --no-ndt / --seq-scans 0 (they add ~40 s of synthetic-data generation).
+Objects that ride on the same JSON line (the other workloads BASELINE.json's metric and configs name):
+iekf       configs[0] ("registered points/sec and ms per IEKF update"): one jueying_lio point-to-plane IEKF update of a
+           20k-point Mid-360-shaped scan against a 2M-point local map: device value, e2e through b200_iekf_update with
+           host buffers, roofline of the k-NN gather (k_search), k_obs latency line, cpu_baseline, parity.  The single-scan
+           update does not shard: at N > 1 every rank runs a replica ("iekf_replicas", no collective).
+ndt        configs[1] (N = 1): setInputTarget / computeDerivatives / align of the scan against the 10M-point map.
+sequence   configs[2] (N = 1): sliding-map odometry over --seq-scans scans (default 1000 = full size), update +
+           MapIncremental per scan, oracle parity over the first --seq-parity scans.
+fullmap    configs[4]: construct_full_map over --fullmap-frames keyframes x 100k points (default 10000 = full size), keyframes
+           cut into one block per rank, partial voxel sums exchanged over NCCL (strong scaling).
+scan2map   jueying_slam's LOAM-style scan2MapOptimization for one scan (N = 1).
+summary    the headline numbers of every leg once more, last on the line.
 """
 from __future__ import annotations
 
@@ -53,6 +55,24 @@ PARAMS = {
     "horizon": dict(resolution=0.5, nearby=18, ext=True, stencil=19),
 }
 N_MAP, N_SCAN = 2_000_000, 20_000
+N_PRIOR, N_HYP = 10_000_000, 4096
+NDT_KW = dict(resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=35, search=7)
+L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB streaming write, untimed); CPU arm: not applicable"
+
+
+def headline_config():
+    """The `config` object - identical in the GPU arm and in --impl reference."""
+    return {"workload": "configs[3]: global relocalization - 4096 initial-pose hypotheses (32x32 xy grid at 1 m x 4 yaws) scored with "
+                        "calculateScore against a 10M-point prior map (1.0 m voxels, DIRECT7), 20k-point scan; hypotheses sharded over "
+                        "the ranks (h mod N), map replicated, NCCL argmin",
+            "hypotheses": N_HYP, "n_map": N_PRIOR, "n_scan": N_SCAN, "resolution": NDT_KW["resolution"], "search": "DIRECT7", "l2": L2_NOTE}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler(threading.Thread):
@@ -120,15 +140,39 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_oracle_run(data, prm, steps, warmup, budget_s=25.0):
-    """The reference path's CPU port (oracle/), all host threads.  Returns (ms list, threads, oracle handle, x, P, stats)."""
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py with the commit it was taken at); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))
+        e = t["kernels"].get(kernel)
+        return (int(e["dram_bytes_per_launch"]), f"profiles/traffic.json ({e.get('capture', '?')}, commit {t.get('commit', '?')})") if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def mean(v):
+    return float(np.mean(v)) if len(v) else float("nan")
+
+
+# =============================================================================================== CPU oracle legs
+def cpu_reloc_sample(o, poses, n_s):
+    """calculateScore on every (4096 / n_s)-th hypothesis, one hypothesis per thread (all host threads)."""
+    sel = np.arange(0, len(poses), max(1, len(poses) // n_s))[:n_s]
+    t0 = time.perf_counter()
+    sc = o.score_batch(poses[sel])
+    return sel, sc, time.perf_counter() - t0
+
+
+def cpu_oracle_iekf(data, prm, steps, warmup, budget_s=25.0):
+    """The reference IEKF path's CPU port (oracle/), all host threads."""
     from oracle import binding as ob
-    lio = ob.OracleLio(resolution=prm["resolution"], nearby=prm["nearby"], extrinsic_est_en=prm["ext"])
+    lio = ob.OracleLio(resolution=prm["resolution"], nearby=prm["nearby"], extrinsic_est_en=prm["ext"], num_threads=host_threads())
     t0 = time.perf_counter()
     lio.insert(data["map"])
     t_insert = time.perf_counter() - t0
-    ms = []
-    out = None
+    ms, out = [], None
     t_start = time.perf_counter()
     for k in range(warmup + steps):
         t0 = time.perf_counter()
@@ -138,54 +182,37 @@ def cpu_oracle_run(data, prm, steps, warmup, budget_s=25.0):
             ms.append(dt)
         if time.perf_counter() - t_start > budget_s and len(ms) >= 3:
             break
-    return ms, os.cpu_count(), t_insert, out
+    return ms, t_insert, out
 
 
-N_PRIOR, N_HYP = 10_000_000, 4096
-NDT_KW = dict(resolution=1.0, step_size=0.1, outlier_ratio=0.55, trans_eps=0.01, max_iter=35, search=7)
-
-
-def ndt_cpu(cfg, poses, budget_s=20.0, want_build=True):
+def ndt_cpu(cfg, want_align=True):
     """NDT legs on the CPU oracle (OpenMP derivatives as pclomp does; serial voxel build as the reference)."""
     from oracle import binding as ob
-    o = ob.OracleNdt(**NDT_KW)
+    o = ob.OracleNdt(**NDT_KW, num_threads=host_threads())
     t0 = time.perf_counter()
     o.set_target(cfg["map"])
     t_build = time.perf_counter() - t0
     o.set_source(cfg["scan"])
-    t0 = time.perf_counter()
-    for _ in range(3):
-        s, g, H = o.derivatives(cfg["p_guess"])
-    t_der = (time.perf_counter() - t0) / 3
-    t0 = time.perf_counter()
-    rc, T, r = o.align(cfg["guess"])
-    t_align = time.perf_counter() - t0
-    # reloc: a bounded sample of the hypothesis grid (every k-th hypothesis), all threads
-    n_s = 256
-    sel = np.arange(0, len(poses), max(1, len(poses) // n_s))[:n_s]
-    t0 = time.perf_counter()
-    sc = o.score_batch(poses[sel])
-    t_sc = time.perf_counter() - t0
-    return dict(oracle=o, build_s=t_build, deriv_ms=t_der * 1e3, align_ms=t_align * 1e3, align=(rc, T, r),
-                score_s=t_sc, score_n=len(sel), score_sel=sel, scores=sc, deriv=(s, g, H))
+    out = dict(oracle=o, build_s=t_build)
+    if want_align:
+        t0 = time.perf_counter()
+        for _ in range(3):
+            s, g, H = o.derivatives(cfg["p_guess"])
+        out["deriv_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        t0 = time.perf_counter()
+        out["align"] = o.align(cfg["guess"])
+        out["align_ms"] = (time.perf_counter() - t0) * 1e3
+        out["deriv"] = (s, g, H)
+    return out
 
 
-def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
-    """configs[1] (single-GPU NDT) on rank 0 and configs[3] (sharded relocalization) on all ranks."""
-    import ctypes
+# =============================================================================================== headline: relocalization
+def reloc_leg(args, rank, local_rank, world, api, synth, torch, comm, cfg):
     dist = torch.distributed if world > 1 else None
-    cfg = synth.config2(N_PRIOR, N_SCAN) if rank == 0 else None
-    if world > 1:
-        small = [dict(scan=cfg["scan"], p_true=cfg["p_true"], p_guess=cfg["p_guess"], guess=cfg["guess"]) if rank == 0 else None]
-        dist.broadcast_object_list(small, src=0)
-        if rank != 0:
-            cfg = small[0]
     g = api.NormalDistributionsTransform(device=local_rank)
     g.setTransformationEpsilon(NDT_KW["trans_eps"])
-    out = {}
-    # ---- setInputTarget: rank 0 holds the cloud; replicas receive the packed points over NVLink
     build_wall, build_dev = [], []
-    for k in range(3):
+    for k in range(3 if world == 1 else 1):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if world > 1:
@@ -198,110 +225,299 @@ def ndt_legs(args, rank, local_rank, world, api, synth, torch, comm):
     g.setInputSource(cfg["scan"])
     g._handle()
     poses = synth.hypothesis_grid(cfg["p_true"], 32, 32, 4, 1.0)
-    n_vox = g.numVoxels()
-    launches0 = api.kernel_launches()
+    assert len(poses) == N_HYP
+    mine = np.ascontiguousarray(poses[rank::world])   # interleaved slices: neighbouring, similarly expensive hypotheses spread over the ranks
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    # ---- reloc: strong scaling over ranks
-    # interleaved slices (hypothesis h on rank h mod N): neighbouring, similarly expensive hypotheses land on different ranks
-    mine = np.ascontiguousarray(poses[rank::world])
-    b, e = rank, rank + len(mine)
-    for _ in range(3):
-        best, score, ms = api.relocalize(g, mine, comm, h_begin=rank, h_stride=world)
-    dev, wall = [], []
-    if world > 1:
-        dist.barrier()
-    for _ in range(args.steps):
-        api.flush_l2(local_rank)
+    def step(aligned):
+        api.flush_l2(local_rank)                      # untimed: evict the 126 MB L2
         if world > 1:
-            dist.barrier()
+            if aligned:
+                g.stream_barrier(comm)                # device-side rendezvous on the engine's stream, before its start event
+            else:
+                dist.barrier()
         t0 = time.perf_counter()
         best, score, ms = api.relocalize(g, mine, comm, h_begin=rank, h_stride=world)
-        wall.append((time.perf_counter() - t0) * 1e3)
+        return best, score, ms, (time.perf_counter() - t0) * 1e3, g.last_score_kernel_ms()
+
+    for _ in range(warmup):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.sm and time.perf_counter() - t_wait < 3.0:   # NVML start-up must not eat the (short) timed region
+        step(True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = api.kernel_launches()
+    t_wall0 = time.perf_counter()
+    dev, kern = [], []
+    for _ in range(steps):
+        best, score, ms, _, kms = step(True)
         dev.append(ms)
-    t = torch.tensor([float(np.mean(dev)), float(np.mean(wall))], device="cuda", dtype=torch.float64)
+        kern.append(kms)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_s = time.perf_counter() - t_wall0
+    launches = api.kernel_launches() - launches0
+    clocks = sampler.summary()
+    wall = []
+    for _ in range(steps):                            # e2e: host poses in, winners out, wall clock around the C-ABI call
+        wall.append(step(False)[3])
+    t = torch.tensor([mean(dev), mean(wall), mean(kern)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    reloc_dev_ms, reloc_wall_ms = float(t[0]), float(t[1])
-    reloc_launches = (api.kernel_launches() - launches0) // (args.steps + 3)
-    out["reloc"] = {
-        "metric": "relocalization hypotheses/sec", "value": len(poses) / (reloc_dev_ms * 1e-3), "unit": "hypotheses/s",
-        "n_gpus": world, "scaling": "strong", "hypotheses": len(poses), "per_rank": e - b, "ms_per_batch": reloc_dev_ms,
-        "e2e": {"value": len(poses) / (reloc_wall_ms * 1e-3), "unit": "hypotheses/s", "ms_per_batch": reloc_wall_ms,
-                "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": 32},
-        "best": int(best), "best_score": float(score), "true_index": (16 * 32 + 16) * 4, "gpu_launches_per_batch": int(reloc_launches),
-        "collective": "one ncclAllGather of 16 B per rank ((score key, index) winners), reduced identically on every rank" if world > 1 else "none (single GPU)",
-        "workload": "configs[3]: 32x32x4 pose grid (1 m, 90 deg) vs 10M-pt prior map, calculateScore per hypothesis, map replicated per GPU",
-        "l2": "flushed between timed batches"}
+    dev_ms, wall_ms, kern_ms = float(t[0]), float(t[1]), float(t[2])
 
+    # roofline of the score kernel on this rank's launch: per hypothesis N*16 (scan point) + N*32 (one nbr7 record: the seven
+    # DIRECT7 leaf slots of the point's cell + count) + 96 B per (point, occupied voxel) pair (fp64 mean + inverse covariance)
+    pairs = g.score_pairs(mine)
+    algo = len(mine) * (N_SCAN * 16 + N_SCAN * 32) + 96 * pairs
+    peak, peak_src = measured_peak()
+    traffic, traffic_src = ncu_traffic("k_ndt_score_batch")
+    roofline = {"bound": "hbm", "kernel": "k_ndt_score_batch<7> (one launch per step and rank)", "achieved": algo / (kern_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": algo / (kern_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": int(algo), "kernel_ms": kern_ms,
+                "pairs_per_hypothesis": pairs / max(len(mine), 1), "hypotheses_per_launch": len(mine), "share_of_step": kern_ms / dev_ms,
+                "note": "every hypothesis re-reads the same few MB of voxel Gaussians, so the algorithmic bytes are served by L1/L2, not "
+                        "by DRAM (compare traffic): the kernel is bound by the L1 data pipe (96-byte fp64 leaf per pair) and fp64 exp, "
+                        "which is why achieved can exceed the DRAM peak"}
+
+    out = {"value": N_HYP / (dev_ms * 1e-3), "ms_per_step": dev_ms, "per_rank": len(mine),
+           "e2e": {"value": N_HYP / (wall_ms * 1e-3), "unit": "hypotheses/s", "ms_per_step": wall_ms,
+                   "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": 16 * world},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region_incl_flush": wall_s,
+           "best": int(best), "best_score": float(score), "true_index": (16 * 32 + 16) * 4,
+           "collective": "one ncclAllGather of 16 B per rank ((score key, index) winners), reduced identically on every rank" if world > 1 else "none (single GPU)",
+           "set_target_ms": {"device": float(np.min(build_dev)), "e2e_wall": float(np.min(build_wall)), "voxels": int(g.numVoxels()),
+                             "how": "rank 0 uploads, ncclBroadcast of the packed points, every rank builds identical leaves" if world > 1 else "host cloud -> device build"}}
+    # parity: the sharded winner against the single-GPU result over all 4096 hypotheses (rank 0), and against the oracle on a sample
     if rank == 0:
-        # ---- configs[1]: derivatives and full align on one GPU
-        der_dev, der_wall = [], []
-        for k in range(args.steps + 3):
-            api.flush_l2(local_rank)
-            t0 = time.perf_counter()
-            s, gr, H = g.computeDerivatives(cfg["p_guess"])
-            if k >= 3:
-                der_wall.append((time.perf_counter() - t0) * 1e3)
-                der_dev.append(g.last_ms())
-        al_dev, al_wall = [], []
-        for k in range(args.steps + 3):
-            api.flush_l2(local_rank)
-            t0 = time.perf_counter()
-            rc = g.align(cfg["guess"])
-            if k >= 3:
-                al_wall.append((time.perf_counter() - t0) * 1e3)
-                al_dev.append(g.result.gpu_ms)
-        r = g.result
-        pairs = g.nbhd_total(cfg["p_guess"])
-        peak, peak_src = measured_peak()
-        # algorithmic bytes of one derivative evaluation: N*16 (source point) + N*7*4 (one cell-table probe per
-        # neighbourhood cell; the dense table stores 4-byte slots) + 64 B per (point, voxel) pair (float-path leaf record)
-        der_bytes = N_SCAN * 16 + N_SCAN * 7 * 4 + 64 * pairs
-        der_ms = float(np.mean(der_dev))
-        out["ndt"] = {
-            "workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
-            "voxels": int(n_vox),
-            "set_target_ms": {"device": float(np.min(build_dev)), "e2e_wall": float(np.min(build_wall)),
-                              "points_per_s_device": N_PRIOR / (float(np.min(build_dev)) * 1e-3),
-                              "note": "device = min/max + key + radix sort + segmented fp64 sums + per-leaf eigen/inverse; e2e adds host pack + 160 MB H2D"
-                                      + (" + ncclBroadcast to the replicas" if world > 1 else "")},
-            "derivatives_ms": {"device": der_ms, "e2e_wall": float(np.mean(der_wall)), "pairs": int(pairs)},
-            "align_ms": {"device": float(np.mean(al_dev)), "e2e_wall": float(np.mean(al_wall)), "iters": r.iters, "evals": r.evals,
-                         "hess_evals": r.hess_evals, "launches": g.last_launches(), "converged": bool(r.converged),
-                         "points_per_s": N_SCAN / (float(np.mean(al_dev)) * 1e-3)},
-            "roofline": {"bound": "hbm", "kernel": "k_ndt_eval (one init + one evaluation launch, CUDA events around both)",
-                         "achieved": der_bytes / (der_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": der_bytes / (der_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(der_bytes),
-                         # ncu dram bytes of one k_ndt_eval launch (profiles/r01_ndt_ncu_full_summary.md): leaves and cell table are L2-resident
-                         "traffic": 1546240 + 1024,
-                         "note": "20k points x <=7 voxels is ~9 MB per evaluation: the kernel is latency/launch bound, not bandwidth bound"},
-        }
-        if world == 1 and not args.no_cpu:
-            c = ndt_cpu(cfg, poses)
-            rc0, T0, r0 = c["align"]
-            s0, g0, H0 = c["deriv"]
-            s1 = g.calculateScore(poses[c["score_sel"]])
-            out["ndt"]["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(), "set_target_s": c["build_s"], "derivatives_ms": c["deriv_ms"],
-                                          "align_ms": c["align_ms"], "sample": "full size: 10M-pt voxel build (serial, as the reference), "
-                                          "3 derivative evaluations and 1 align on all threads"}
-            out["ndt"]["parity"] = {"align_dpos_m": float(np.abs(np.array(r.p_final)[:3] - np.array(r0.p_final)[:3]).max()),
-                                    "align_drot_rad": float(np.abs(np.array(r.p_final)[3:] - np.array(r0.p_final)[3:]).max()),
-                                    "iters_equal": bool(r.iters == r0.iters and r.evals == r0.evals),
-                                    "score_rel": float(abs(s - s0) / abs(s0)),
-                                    "g_rel": float(np.abs(gr - g0).max() / np.abs(g0).max()),
-                                    "H_rel": float(np.abs(H - H0).max() / np.abs(H0).max())}
-            out["reloc"]["cpu_baseline"] = {"value": c["score_n"] / c["score_s"], "unit": "hypotheses/s", "cores": os.cpu_count(), "kind": "port",
-                                            "sample": f"{c['score_n']} of the 4096 hypotheses (every 16th), one hypothesis per thread"}
-            out["reloc"]["parity"] = {"scores_rel": float(np.abs(s1 - c["scores"]).max() / np.abs(c["scores"]).max()),
-                                      "argmax_equal_on_sample": bool(int(np.argmax(s1)) == int(np.argmax(c["scores"])))}
-    g.close()
+        s_all = g.calculateScore(poses)
+        b1 = int(np.argmax(s_all))
+        out["parity"] = {"argmin_equal_single_gpu": bool(b1 == best), "score_equal_single_gpu": bool(s_all[b1] == score),
+                         "winner_is_true_pose_cell": bool(best == out["true_index"])}
+        if not args.no_cpu:
+            c = ndt_cpu(cfg, want_align=False)
+            n_s = 256 if world == 1 else 64
+            sel, sc, t_sc = cpu_reloc_sample(c["oracle"], poses, n_s)
+            if best not in sel:
+                sel = np.concatenate([sel, [best]])
+                sc = np.concatenate([sc, c["oracle"].score_batch(poses[[best]])])
+            out["parity"].update({"oracle_sample": len(sel), "scores_rel_vs_oracle": float(np.abs(s_all[sel] - sc).max() / np.abs(sc).max()),
+                                  "argmin_equal_oracle_on_sample": bool(int(sel[np.argmax(sc)]) == int(sel[np.argmax(s_all[sel])])),
+                                  "oracle_argmin_on_sample": int(sel[np.argmax(sc)])})
+            if world == 1:
+                out["cpu_baseline"] = {"value": n_s / t_sc, "unit": "hypotheses/s", "cores": host_threads(), "kind": "port",
+                                       "sample": f"{n_s} of the 4096 hypotheses (every {N_HYP // n_s}th), one hypothesis per thread, {t_sc:.2f} s; "
+                                                 f"serial 10M-pt voxel build {c['build_s']:.1f} s not included"}
+            out["_oracle_ndt"] = c
+    return g, poses, out
+
+
+# =============================================================================================== configs[1]: NDT align (N = 1)
+def ndt_leg(args, local_rank, api, g, cfg, c):
+    der_dev, der_wall = [], []
+    for k in range(args.steps + 3):
+        api.flush_l2(local_rank)
+        t0 = time.perf_counter()
+        s, gr, H = g.computeDerivatives(cfg["p_guess"])
+        if k >= 3:
+            der_wall.append((time.perf_counter() - t0) * 1e3)
+            der_dev.append(g.last_ms())
+    al_dev, al_wall = [], []
+    for k in range(args.steps + 3):
+        api.flush_l2(local_rank)
+        t0 = time.perf_counter()
+        g.align(cfg["guess"])
+        if k >= 3:
+            al_wall.append((time.perf_counter() - t0) * 1e3)
+            al_dev.append(g.result.gpu_ms)
+    r = g.result
+    pairs = g.nbhd_total(cfg["p_guess"])
+    peak, _ = measured_peak()
+    # algorithmic bytes of one derivative evaluation: N*16 (source point) + N*7*4 (one 4-byte cell-table probe per neighbourhood
+    # cell) + 64 B per (point, voxel) pair (float-path leaf record)
+    der_bytes = N_SCAN * 16 + N_SCAN * 7 * 4 + 64 * pairs
+    der_ms = mean(der_dev)
+    traffic, traffic_src = ncu_traffic("k_ndt_eval")
+    out = {"workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
+           "derivatives_ms": {"device": der_ms, "e2e_wall": mean(der_wall), "pairs": int(pairs)},
+           "align_ms": {"device": mean(al_dev), "e2e_wall": mean(al_wall), "iters": r.iters, "evals": r.evals,
+                        "hess_evals": r.hess_evals, "launches": g.last_launches(), "converged": bool(r.converged),
+                        "points_per_s": N_SCAN / (mean(al_dev) * 1e-3)},
+           "roofline": {"bound": "hbm", "kernel": "k_ndt_eval (one init + one evaluation launch, CUDA events around both)",
+                        "achieved": der_bytes / (der_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": der_bytes / (der_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": int(der_bytes),
+                        "traffic": traffic, "traffic_source": traffic_src}}
+    if c is not None:
+        rc0, T0, r0 = c["align"]
+        s0, g0, H0 = c["deriv"]
+        out["cpu_baseline"] = {"kind": "port", "cores": host_threads(), "set_target_s": c["build_s"], "derivatives_ms": c["deriv_ms"],
+                               "align_ms": c["align_ms"], "sample": "full size: 10M-pt voxel build (serial, as the reference), "
+                               "3 derivative evaluations and 1 align on all threads"}
+        out["parity"] = {"align_dpos_m": float(np.abs(np.array(r.p_final)[:3] - np.array(r0.p_final)[:3]).max()),
+                         "align_drot_rad": float(np.abs(np.array(r.p_final)[3:] - np.array(r0.p_final)[3:]).max()),
+                         "iters_equal": bool(r.iters == r0.iters and r.evals == r0.evals),
+                         "score_rel": float(abs(s - s0) / abs(s0)),
+                         "g_rel": float(np.abs(gr - g0).max() / np.abs(g0).max()),
+                         "H_rel": float(np.abs(H - H0).max() / np.abs(H0).max())}
     return out
 
 
-def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
+# =============================================================================================== configs[0]: IEKF update
+def iekf_leg(args, rank, local_rank, world, api, synth, torch, full):
+    """One IEKF update per step on configs[0].  full = all the trimmings (N = 1); otherwise the replica figure only."""
+    prm = PARAMS[args.params]
+    data = synth.config1(N_MAP, N_SCAN)
+    scan = data["scan"]
+    n = len(scan)
+    ivox = api.IVox(resolution=prm["resolution"], nearby=prm["nearby"], device=local_rank)
+    ivox.AddPoints(data["map"])
+    kf = api.Esekf(ivox, extrinsic_est_en=prm["ext"])
+    scan4 = np.zeros((n, 4), np.float32)
+    scan4[:, :3] = scan
+    d_scan = torch.from_numpy(scan4).cuda()
+    torch.cuda.synchronize()
+    steps = args.steps
+
+    def step_device():
+        kf.change_x(data["x_prop"])
+        kf.change_P(data["P"])
+        kf.update_device(d_scan.data_ptr(), n)
+        return kf.stats.gpu_ms
+
+    for _ in range(max(args.warmup, 3)):
+        api.flush_l2(local_rank)
+        step_device()
+    launches0 = api.kernel_launches()
+    dev_ms = []
+    for _ in range(steps):
+        api.flush_l2(local_rank)          # untimed: evict the 126 MB L2 between steps
+        dev_ms.append(step_device())      # timed on the device: CUDA events on the engine's stream
+    launches = api.kernel_launches() - launches0
+    passes, knn_passes = kf.stats.passes, kf.stats.knn_passes
+    n_eff = list(kf.stats.n_eff)[:passes]
+    ms_step = mean(dev_ms)
+    if world > 1:
+        t = torch.tensor([ms_step], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_step = float(t[0])
+    out = {"workload": "configs[0]: 20k-pt Mid-360-shaped scan vs 2M-pt local map, one IEKF update per step",
+           "metric": "registered points/sec (IEKF update)", "value": world * n / (ms_step * 1e-3), "unit": "points/s", "ms_per_update": ms_step,
+           "params": args.params, "passes": passes, "knn_passes": knn_passes, "n_eff": n_eff, "gpu_launches": int(launches),
+           "parallelism": f"{world} independent replicas, no collective" if world > 1 else "single GPU"}
+    if not full:
+        return out
+    warm_ms = [step_device() for _ in range(steps)]   # warm-L2 variant (the map stays L2-resident between scans in real operation)
+    out["ms_per_update_warm_l2"] = mean(warm_ms)
+    # e2e: the C-ABI call with host buffers (H2D + kernels + D2H), wall clock per call.  Headline: the scan sits in page-locked
+    # host memory (b200_host_alloc); second figure: a pageable buffer (what a PCL cloud is), packed through the handle's pinned stage
+    pinned = api.PinnedCloud(n, 3)
+    pinned.array[:] = scan
+    e2e_ms, e2e_pageable_ms = [], []
+    for src, dst in ((pinned.array, e2e_ms), (scan, e2e_pageable_ms)):
+        for k in range(steps + 3):
+            api.flush_l2(local_rank)
+            kf.change_x(data["x_prop"])
+            kf.change_P(data["P"])
+            t0 = time.perf_counter()
+            kf.update_iterated_dyn_share_modified(src)
+            dt = (time.perf_counter() - t0) * 1e3
+            if k >= 3:
+                dst.append(dt)
+    h2d, d2h = kf.io_bytes(n)
+    h2d = h2d - n * 16 + n * 12   # the pinned path ships the caller's 12-byte records
+    out["e2e"] = {"value": n / (mean(e2e_ms) * 1e-3), "unit": "points/s", "ms_per_update": mean(e2e_ms),
+                  "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                  "input": "scan in page-locked host memory (b200_host_alloc), unpacked on the device",
+                  "pageable_input_ms_per_update": mean(e2e_pageable_ms)}
+    # per-kernel durations by CUDA events (profiling mode launches kernel by kernel)
+    kf.set_profiling(True)
+    search_ms, obs_s_ms, obs_n_ms, init_ms, prof_totals = [], [], [], [], []
+    for k in range(steps + 2):
+        api.flush_l2(local_rank)
+        step_device()
+        if k >= 2:
+            t = kf.kernel_times_ms()
+            prof_totals.append(sum(t[:1 + 2 * passes]))
+            init_ms.append(t[0])
+            for p in range(passes):
+                if kf.stats.knn[p]:
+                    search_ms.append(t[1 + 2 * p])
+                    obs_s_ms.append(t[2 + 2 * p])
+                else:
+                    obs_n_ms.append(t[2 + 2 * p])
+    kf.set_profiling(False)
+    # roofline of the k-NN search kernel: algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md):
+    #   N*16 (scan point) + N*S*8 (one table probe per stencil cell) + 16*sum(C_i) (gathered map points) + N*20 (5 indices out)
+    o_l, Rl = synth.lidar_pose(data["x_prop"])
+    qw = (scan.astype(np.float64) @ Rl.T + o_l).astype(np.float32)
+    sum_c, cells = ivox.stencil_points(qw)
+    algo_bytes = n * 16 + n * prm["stencil"] * 8 + 16 * sum_c + n * 20
+    peak, peak_src = measured_peak()
+    k_ms = mean(search_ms)
+    tot = mean(prof_totals)
+    traffic, traffic_src = ncu_traffic("k_search")
+    out["roofline"] = {"bound": "hbm", "kernel": "k_search (stencil k-NN gather)", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": traffic,
+                       "traffic_source": traffic_src, "algorithmic_bytes": int(algo_bytes), "kernel_ms": k_ms,
+                       "candidates_per_query": sum_c / n, "occupied_cells_per_query": cells / n, "share_of_step": knn_passes * k_ms / tot}
+    # the same search body with enough parallelism to leave the launch-latency regime: 50 scans' worth of queries in one call
+    rng = np.random.default_rng(1)
+    qbig = np.ascontiguousarray(np.concatenate([qw + rng.normal(0, 0.05, qw.shape).astype(np.float32) for _ in range(50)], 0))
+    ivox.GetClosestPoint(qbig)
+    big_ms = []
+    for _ in range(5):
+        api.flush_l2(local_rank)
+        ivox.GetClosestPoint(qbig)
+        big_ms.append(ivox.last_knn_ms())
+    sum_cb, _ = ivox.stencil_points(qbig)
+    nb_ = len(qbig)
+    big_bytes = nb_ * 16 + nb_ * prm["stencil"] * 8 + 16 * sum_cb + nb_ * 20 + nb_ * 24   # + sqdist (20 B) and count (4 B) out
+    out["roofline"]["batched"] = {"queries": nb_, "kernel": "k_knn5 (same search body, 1M queries per launch)", "kernel_ms": mean(big_ms),
+                                  "algorithmic_bytes": int(big_bytes), "achieved": big_bytes / (mean(big_ms) * 1e-3) / 1e9,
+                                  "frac": big_bytes / (mean(big_ms) * 1e-3) / 1e9 / peak, "queries_per_s": nb_ / (mean(big_ms) * 1e-3)}
+    # k_obs: latency line + bytes (SURVEY 8d: N*41 B on a pass that reuses the planes, N*126 B on a search pass = + N*85 B hand-off)
+    obs_ms = obs_s_ms + obs_n_ms
+    obs_bytes_s, obs_bytes_n = n * 126, n * 41
+    out["kernels"] = {
+        "k_iekf_init_ms": mean(init_ms), "k_search_ms": k_ms, "k_obs_ms": mean(obs_ms),
+        "per_update": f"1 init + {passes} x (k_search, k_obs); k_search is a no-op on non-search passes",
+        "share_of_step": {"k_search": knn_passes * k_ms / tot, "k_obs": passes * mean(obs_ms) / tot},
+        "k_obs": {"bound": "latency (serial fp64 filter chain + per-point QR), not bytes",
+                  "search_pass": {"ms": mean(obs_s_ms), "algorithmic_bytes": obs_bytes_s,
+                                  "achieved_gbs": obs_bytes_s / (mean(obs_s_ms) * 1e-3) / 1e9 if obs_s_ms else None,
+                                  "frac": obs_bytes_s / (mean(obs_s_ms) * 1e-3) / 1e9 / peak if obs_s_ms else None},
+                  "reuse_pass": {"ms": mean(obs_n_ms), "algorithmic_bytes": obs_bytes_n,
+                                 "achieved_gbs": obs_bytes_n / (mean(obs_n_ms) * 1e-3) / 1e9 if obs_n_ms else None,
+                                 "frac": obs_bytes_n / (mean(obs_n_ms) * 1e-3) / 1e9 / peak if obs_n_ms else None}},
+        "note": "event-to-event per kernel with plain launches (each interval carries ~3-4 us of launch / event gap that the graph replay of the timed steps does not pay)"}
+    if not args.no_cpu:
+        ms, t_insert, res = cpu_oracle_iekf(data, prm, 20, 3, budget_s=25.0)
+        cpu_ms = float(np.median(ms))
+        out["cpu_baseline"] = {"value": n / (cpu_ms * 1e-3), "unit": "points/s", "cores": host_threads(), "kind": "port", "ms_per_update": cpu_ms,
+                               "sample": f"{len(ms)} full-size updates on the same inputs (median); map insert {t_insert:.2f} s excluded"}
+        rc, x_o, P_o, st_o = res
+        step_device()
+        from oracle import binding as ob
+        d = ob.boxminus(kf.get_x(), x_o)
+        out["parity"] = {"pos_m": float(np.abs(d[:3]).max()), "rot_rad": float(np.abs(d[3:6]).max()),
+                         "passes_equal": bool(st_o.passes == kf.stats.passes),
+                         "n_eff_equal": bool(list(st_o.n_eff)[:passes] == list(kf.stats.n_eff)[:passes])}
+    kf.close()
+    ivox.close()
+    return out
+
+
+# =============================================================================================== configs[2]: sliding-map sequence
+def sequence_leg(args, local_rank, api, synth, n_scans, n_parity):
     """configs[2]: sliding-map odometry over a synthetic scan sequence.  The map starts from the first scan and grows by
     MapIncremental (downsample-on-insert); the prior of scan k is the posterior of scan k-1 moved by the true relative
-    motion plus a seeded perturbation (stand-in for the IMU propagation, which is out of scope)."""
+    motion plus a seeded perturbation (stand-in for the IMU propagation)."""
+    from concurrent.futures import ThreadPoolExecutor
     prm = PARAMS["horizon"]
     world = synth.make_world(synth.SEED)
     rng = np.random.default_rng(synth.SEED + 31)
@@ -328,28 +544,32 @@ def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
         x[3:7] = q / np.linalg.norm(q)
         return x
 
+    t_gen = time.perf_counter()
+    with ThreadPoolExecutor(min(16, host_threads())) as ex:   # host-side ray casting of the whole sequence (synthetic data, untimed)
+        scans = list(ex.map(scan_of, range(n_scans)))
+    t_gen = time.perf_counter() - t_gen
     ivox = api.IVox(resolution=prm["resolution"], nearby=prm["nearby"], device=local_rank)
     kf = api.Esekf(ivox, extrinsic_est_en=False, filter_size_map=0.5)
     oracle_on = n_parity > 0 and not args.no_cpu
     if oracle_on:
         from oracle import binding as ob
-        orc = ob.OracleLio(resolution=prm["resolution"], nearby=prm["nearby"], extrinsic_est_en=False, filter_size_map=0.5)
+        orc = ob.OracleLio(resolution=prm["resolution"], nearby=prm["nearby"], extrinsic_est_en=False, filter_size_map=0.5, num_threads=host_threads())
     P0 = synth.init_cov() * 0.01
     x_g = true_state(0)
-    first = scan_of(0)
     ol, Rl = synth.lidar_pose(x_g)
-    w0 = (first.astype(np.float64) @ Rl.T + ol).astype(np.float32)
+    w0 = (scans[0].astype(np.float64) @ Rl.T + ol).astype(np.float32)
     ivox.AddPoints(w0)                      # first frame: every point goes in (laser_mapping.cc:314-319)
     if oracle_on:
         orc.insert(w0)
-    ms_update, ms_incr, ms_wall, voxels, points, par, passes, knn_passes, neff = [], [], [], [], [], [], [], [], []
+    ms_update, ms_incr, ms_wall, voxels, points, par, passes, knn_passes, neff, add_par = [], [], [], [], [], [], [], [], [], []
+    cpu_ms = []
     for k in range(1, n_scans):
-        scan = scan_of(k)
+        scan = scans[k]
         prior = move(x_g, k)
         kf.change_x(prior)
         kf.change_P(P0)
         t0 = time.perf_counter()
-        rc = kf.update_iterated_dyn_share_modified(scan)
+        kf.update_iterated_dyn_share_modified(scan)
         t1 = time.perf_counter()
         na, nd = kf.MapIncremental(kf.get_x(), True)
         t2 = time.perf_counter()
@@ -360,36 +580,45 @@ def sequence_leg(args, local_rank, api, synth, n_scans, n_parity=12):
         neff.append(kf.stats.n_eff[max(kf.stats.passes - 1, 0)])
         ms_wall.append((t2 - t0) * 1e3)
         ms_incr.append((t2 - t1) * 1e3)
-        if k % 50 == 0 or k == n_scans - 1:
+        if k % 100 == 0 or k == n_scans - 1:
             voxels.append(ivox.NumValidGrids())
             points.append(ivox.NumPoints())
         if oracle_on and k <= n_parity:      # the oracle is fed the same prior and grows its own map from its own posterior
+            t0 = time.perf_counter()
             rco, x_o, P_o, st_o = orc.update(scan, prior, P0)
-            orc.map_incremental(scan, x_o, True)
+            _, na_o, nd_o = orc.map_incremental(scan, x_o, True)
+            cpu_ms.append((time.perf_counter() - t0) * 1e3)
             d = ob.boxminus(x_g, x_o)
             par.append(float(np.abs(d[:6]).max()))
+            add_par.append((na, nd) == (na_o, nd_o))
     xt = true_state(n_scans - 1)
     drift = float(np.linalg.norm(x_g[0:3] - xt[0:3]))
-    return {"workload": f"configs[2]: {n_scans}-scan closed-loop sequence (0.5 m / 1.2 deg steps), 20k-pt scans, P-horizon map "
-                        "(0.5 m voxels, NEARBY18), update + MapIncremental (filter_size_map 0.5) per scan",
-            "scans": n_scans, "ms_update_device": {"mean": float(np.mean(ms_update)), "p95": float(np.percentile(ms_update, 95))},
-            "ms_per_scan_e2e": {"mean": float(np.mean(ms_wall)), "p95": float(np.percentile(ms_wall, 95)),
-                                "map_incremental_mean": float(np.mean(ms_incr))},
-            "scans_per_s_e2e": 1e3 / float(np.mean(ms_wall)), "points_per_s_e2e": N_SCAN * 1e3 / float(np.mean(ms_wall)),
-            "passes_mean": float(np.mean(passes)), "knn_passes_mean": float(np.mean(knn_passes)), "n_eff_mean": float(np.mean(neff)),
-            "launch_modes": dict(zip(("graph_captures", "graph_replays", "plain"), kf.launch_modes())),
-            "ms_update_device_median": float(np.median(ms_update)),
-            "map_voxels": voxels, "map_points": points, "final_position_error_m": drift,
-            "parity_vs_oracle": {"scans": len(par), "max_state_diff": max(par) if par else None,
-                                 "note": "both filters fed the same priors; posterior and inserted points compared per scan"},
-            **({"trace_ms_update_device": [round(v, 4) for v in ms_update]} if os.environ.get("B200_SEQ_TRACE") else {})}
+    out = {"workload": f"configs[2]: {n_scans}-scan closed-loop sequence (0.5 m / 1.2 deg steps), 20k-pt scans, P-horizon map "
+                       "(0.5 m voxels, NEARBY18), update + MapIncremental (filter_size_map 0.5) per scan",
+           "scans": n_scans, "ms_update_device": {"mean": mean(ms_update), "median": float(np.median(ms_update)), "p95": float(np.percentile(ms_update, 95))},
+           "ms_per_scan_e2e": {"mean": mean(ms_wall), "p95": float(np.percentile(ms_wall, 95)), "map_incremental_mean": mean(ms_incr)},
+           "scans_per_s_e2e": 1e3 / mean(ms_wall), "points_per_s_e2e": N_SCAN * 1e3 / mean(ms_wall),
+           "passes_mean": mean(passes), "knn_passes_mean": mean(knn_passes), "n_eff_mean": mean(neff),
+           "launch_modes": dict(zip(("graph_captures", "graph_replays", "plain"), kf.launch_modes())),
+           "map_voxels": voxels, "map_points": points, "final_position_error_m": drift, "scan_generation_s_untimed": t_gen,
+           "parity_vs_oracle": {"scans": len(par), "max_state_diff": max(par) if par else None, "map_incremental_counts_equal": bool(all(add_par)) if add_par else None,
+                                "note": "both filters fed the same priors; each grows its own map from its own posterior"}}
+    if cpu_ms:
+        out["cpu_baseline"] = {"value": 1e3 / mean(cpu_ms), "unit": "scans/s", "ms_per_scan": mean(cpu_ms), "cores": host_threads(), "kind": "port",
+                               "sample": f"the first {len(cpu_ms)} scans of the sequence (update on all threads + serial MapIncremental)"}
+    if os.environ.get("B200_SEQ_TRACE"):
+        out["trace_ms_update_device"] = [round(v, 4) for v in ms_update]
+    kf.close()
+    ivox.close()
+    return out
 
 
+# =============================================================================================== configs[4]: construct_full_map
 def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
     """configs[4]: construct_full_map - keyframes (Avia-shaped, 100k points) moved by their poses and merged into a 0.1 m
     voxel-grid map.  A pool of ray-cast keyframes along a loop in the synthetic hall is replayed on a grid of tiles
     (copies of the hall side by side), so the map keeps growing; the keyframe list is cut into contiguous blocks, one per
-    rank (weak scaling would need N x frames: here the total is fixed = strong scaling)."""
+    rank; the total is fixed = strong scaling."""
     n_frames, n_pool, n_pts = args.fullmap_frames, args.fullmap_pool, 100_000
     world_geo = synth.make_world(synth.SEED, beams=True)
     pool, pool_pose = [], []
@@ -401,7 +630,6 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
         inten = np.full((len(pts), 1), float(k), np.float32)
         pool.append(np.ascontiguousarray(np.concatenate([pts, inten], 1)))
         pool_pose.append(np.array([pos[0], pos[1], pos[2], q[3], q[0], q[1], q[2]]))
-
     reuse = args.fullmap_reuse   # keyframes per tile = pool x reuse: ~20 points per voxel, the density BASELINE.json quotes (1e9 pts -> 50M)
 
     def pose_of(i):
@@ -414,8 +642,10 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
     fb, fe = api.shard_range(n_frames, world, rank)
     frame_poses = np.stack([pose_of(i) for i in range(n_frames)])   # poses.txt of the job, read once
     d_pool = [torch.from_numpy(f).cuda() for f in pool]
-    cap = int(min(1 << 29, max(4_000_000, 1.6e6 * (-(-n_frames // (n_pool * reuse)) // world + 2))))
-    times, times_e2e, vox_total, exch = [], [], 0, []
+    tiles = -(-n_frames // (n_pool * reuse))
+    cap = int(min(1 << 29, max(4_000_000, 1.6e6 * (-(-tiles // world) + 2))))
+    times, times_e2e, exch, vox_local = [], [], [], 0
+    n_host = min(fe - fb, max(1, args.fullmap_host_frames // world))   # e2e (host buffers) on a bounded block of this rank's keyframes
     for rep in range(3):
         for mode in ("device", "host"):
             if mode == "host" and rep > 0:
@@ -432,8 +662,8 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
                     b.add_keyframes_device([d_pool[i % n_pool].data_ptr() for i in idx], [len(pool[i % n_pool]) for i in idx],
                                            frame_poses[i0:idx[-1] + 1])
             else:
-                for i in range(fb, fe):
-                    b.add_keyframe(pool[i % n_pool], pose_of(i))
+                for i in range(fb, fb + n_host):
+                    b.add_keyframe(pool[i % n_pool], frame_poses[i])
             b.merge(comm)
             nv = b.num_voxels()
             dt = time.perf_counter() - t0
@@ -451,25 +681,25 @@ def fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm):
         t_dev, t_e2e, vox_total = float(tm[0]), float(tm[1]), int(ts[2])
     else:
         t_dev, t_e2e, vox_total = float(t[0]), float(t[1]), int(t[2])
-    out = {"workload": f"configs[4] scaled: {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes, {reuse} passes per tile, tiles side by side), leaf 0.1 m; "
-                       "10000 keyframes = full size (--fullmap-frames)",
+    out = {"workload": f"configs[4]: construct_full_map, {n_frames} keyframes x {n_pts} pts (pool of {n_pool} ray-cast Avia keyframes replayed {reuse}x per "
+                       f"tile, {tiles} tiles side by side), leaf 0.1 m" + ("" if n_frames >= 10000 else " - REDUCED SIZE (10000 keyframes = full)"),
            "metric": "keyframes/s", "value": n_frames / t_dev, "unit": "keyframes/s", "points_per_s": n_frames * n_pts / t_dev, "n_gpus": world,
-           "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.min(exch)) if exch else 0.0,  # best of the repetitions, like `seconds` (the first one sets up the NCCL channels)
-           "timing": "wall clock around b200_mapbuild_add_keyframes_device (batches of 96 keyframes, 24 per kernel launch) + merge (NCCL exchange) + final sync, keyframes resident in HBM; max over ranks, best of 3",
-           "e2e": {"value": n_frames / t_e2e, "unit": "keyframes/s", "seconds": t_e2e, "h2d_bytes_per_keyframe": n_pts * 16,
-                   "note": "b200_mapbuild_add_keyframe with host buffers: pack + H2D per keyframe"}}
-    if rank == 0 and world == 1 and not args.no_cpu:
+           "scaling": "strong", "seconds": t_dev, "map_voxels": vox_total, "exchange_ms": float(np.min(exch)) if exch else 0.0,
+           "timing": "wall clock around b200_mapbuild_add_keyframes_device (batches of 96 keyframes) + merge (NCCL exchange) + final sync, keyframes resident in HBM; max over ranks, best of 3",
+           "e2e": {"value": n_host * world / t_e2e, "unit": "keyframes/s", "seconds": t_e2e, "keyframes": n_host * world, "h2d_bytes_per_keyframe": n_pts * 16,
+                   "note": "b200_mapbuild_add_keyframe with host buffers (pack + H2D per keyframe) on a bounded block of keyframes + merge"}}
+    if rank == 0 and not args.no_cpu:
         from oracle import binding as ob
-        ns = min(8, n_frames)
+        ns = min(64, n_frames)
         t0 = time.perf_counter()
         c0, n0 = ob.full_map([pool[i % n_pool] for i in range(ns)], np.array([pose_of(i) for i in range(ns)]), 0.1)
         dt = time.perf_counter() - t0
-        b = api.FullMapBuilder(leaf=0.1, capacity_voxels=4_000_000, device=local_rank)
+        b = api.FullMapBuilder(leaf=0.1, capacity_voxels=8_000_000, device=local_rank)
         for i in range(ns):
             b.add_keyframe(pool[i % n_pool], pose_of(i))
         c1, n1 = b.extract()
         out["cpu_baseline"] = {"value": ns / dt, "unit": "keyframes/s", "cores": 1, "kind": "port", "sample": f"first {ns} keyframes (single thread, as pcl::VoxelGrid)"}
-        out["parity"] = {"voxels_equal": bool(len(c0) == len(c1) and np.array_equal(n0, n1)),
+        out["parity"] = {"keyframes": ns, "voxels_equal": bool(len(c0) == len(c1) and np.array_equal(n0, n1)),
                          "max_centroid_diff_m": float(np.abs(c0 - c1).max()) if len(c0) == len(c1) else None}
         b.close()
     return out
@@ -495,58 +725,68 @@ def loam_leg(args, local_rank, api, synth):
             dev.append(g.stats.gpu_ms)
     out = {"workload": f"jueying_slam scan2MapOptimization: {len(sc['corner'])} corner + {len(sc['surf'])} surf features vs "
                        f"{len(sc['corner_map'])} / {len(sc['surf_map'])}-point feature maps, 0.18 m / 1 deg initial error",
-           "set_map_ms_e2e": float(np.min(t_set)), "optimize_ms": {"device": float(np.mean(dev)), "e2e_wall": float(np.mean(wall))},
+           "set_map_ms_e2e": float(np.min(t_set)), "optimize_ms": {"device": mean(dev), "e2e_wall": mean(wall)},
            "iters": g.stats.iters, "n_sel": g.stats.n_sel, "converged": bool(g.stats.converged),
            "pose_error": {"trans_m": float(np.abs(t[3:] - sc["t_true"][3:]).max()), "rot_rad": float(np.abs(t[:3] - sc["t_true"][:3]).max())}}
     if not args.no_cpu:
         from oracle import binding as ob
-        o = ob.OracleLoam()
+        o = ob.OracleLoam(num_threads=host_threads())
         o.set_map(sc["corner_map"], sc["surf_map"])
         t0 = time.perf_counter()
         t_o, st = o.optimize(sc["corner"], sc["surf"], guess)
-        out["cpu_baseline"] = {"optimize_ms": (time.perf_counter() - t0) * 1e3, "cores": os.cpu_count(), "kind": "port",
+        out["cpu_baseline"] = {"optimize_ms": (time.perf_counter() - t0) * 1e3, "cores": host_threads(), "kind": "port",
                                "sample": "one full optimisation; the port finds neighbours by brute force (exact, like the kd-tree, but slower than one)"}
         out["parity"] = {"iters_equal": bool(st["iters"] == g.stats.iters), "max_transform_diff": float(np.abs(t_o - t).max())}
     g.close()
     return out
 
 
+# =============================================================================================== arms
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = its restatement in oracle/
-    (the reference cannot be compiled here: no PCL/Eigen/Boost/TBB), all host threads."""
+    (the reference cannot be compiled here: no PCL/Eigen-Core/Boost/TBB), all host threads (set explicitly:
+    torchrun exports OMP_NUM_THREADS=1).  A step = calculateScore on a bounded sample of the 4096 hypotheses."""
     if rank != 0:
         return
     from pointcloud_slam_b200 import synth
-    prm = PARAMS[args.params]
-    data = synth.config1(N_MAP, N_SCAN)
-    n = len(data["scan"])
-    ms, cores, t_insert, out = cpu_oracle_run(data, prm, args.steps, args.warmup, budget_s=120.0)
-    ms_step = float(np.mean(ms))
-    value = n / (ms_step * 1e-3)
+    threads = host_threads()
+    cfg = synth.config2(N_PRIOR, N_SCAN)
+    poses = synth.hypothesis_grid(cfg["p_true"], 32, 32, 4, 1.0)
+    c = ndt_cpu(cfg, want_align=(world == 1 and not args.no_ndt))
+    n_s = args.ref_sample
+    steps, warmup = args.steps, args.warmup
+    ms = []
+    t_start = time.perf_counter()
+    for k in range(warmup + steps):
+        sel, sc, t_sc = cpu_reloc_sample(c["oracle"], poses, n_s)
+        if k >= warmup:
+            ms.append(t_sc * 1e3)
+        if time.perf_counter() - t_start > 150.0 and len(ms) >= 3:
+            break
+    ms_step = mean(ms)
+    value = n_s / (ms_step * 1e-3)
+    sample = f"each step scores {n_s} of the 4096 hypotheses (every {N_HYP // n_s}th), one hypothesis per thread; serial 10M-pt voxel build {c['build_s']:.1f} s not included"
     line = {
-        "impl": "reference", "metric": "registered points/sec (IEKF update)", "value": value, "unit": "points/s",
-        "n_gpus": args.gpus, "steps": len(ms), "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 per-point math, f64 accumulation and filter", "data": "synthetic",
-        "config": {"workload": "configs[0]: 20k-pt Mid-360-shaped scan vs 2M-pt local map, one IEKF update per step",
-                   "params": args.params, "n_scan": n, "n_map": N_MAP, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(ms)} full-size updates (20k-pt scan, 2M-pt map); map insert {t_insert:.2f} s not included"},
-        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "relocalization hypotheses/sec", "value": value, "unit": "hypotheses/s",
+        "n_gpus": args.gpus, "steps": len(ms), "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": headline_config(),
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if not args.no_ndt:
-        cfg = synth.config2(N_PRIOR, N_SCAN)
-        poses = synth.hypothesis_grid(cfg["p_true"], 32, 32, 4, 1.0)
-        c = ndt_cpu(cfg, poses)
-        rc0, T0, r0 = c["align"]
-        line["ndt"] = {"workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
-                       "set_target_ms": {"e2e_wall": c["build_s"] * 1e3}, "derivatives_ms": {"e2e_wall": c["deriv_ms"]},
-                       "align_ms": {"e2e_wall": c["align_ms"], "iters": r0.iters, "evals": r0.evals, "hess_evals": r0.hess_evals,
-                                    "points_per_s": N_SCAN / (c["align_ms"] * 1e-3)},
-                       "cpu_baseline": {"kind": "port", "cores": cores, "sample": "full size; voxel build serial as in the reference"}}
-        line["reloc"] = {"metric": "relocalization hypotheses/sec", "value": c["score_n"] / c["score_s"], "unit": "hypotheses/s",
-                         "hypotheses": len(poses), "cpu_baseline": {"kind": "port", "cores": cores,
-                                                                     "sample": f"{c['score_n']} of the 4096 hypotheses, one per thread"}}
+    if world == 1:
+        if not args.no_ndt:
+            rc0, T0, r0 = c["align"]
+            line["ndt"] = {"workload": "configs[1]: 20k-pt scan vs 10M-pt prior map, 1.0 m voxels, DIRECT7, eps 0.01, step 0.1",
+                           "set_target_ms": {"e2e_wall": c["build_s"] * 1e3}, "derivatives_ms": {"e2e_wall": c["deriv_ms"]},
+                           "align_ms": {"e2e_wall": c["align_ms"], "iters": r0.iters, "evals": r0.evals, "hess_evals": r0.hess_evals,
+                                        "points_per_s": N_SCAN / (c["align_ms"] * 1e-3)}}
+        if not args.no_iekf:
+            data = synth.config1(N_MAP, N_SCAN)
+            ims, t_insert, _ = cpu_oracle_iekf(data, PARAMS[args.params], 20, 3, budget_s=30.0)
+            line["iekf"] = {"workload": "configs[0]: 20k-pt Mid-360-shaped scan vs 2M-pt local map, one IEKF update per step",
+                            "metric": "registered points/sec (IEKF update)", "value": N_SCAN / (float(np.median(ims)) * 1e-3), "unit": "points/s",
+                            "ms_per_update": float(np.median(ims)), "cores": threads, "sample": f"{len(ims)} full-size updates (median)"}
     print(json.dumps(line), flush=True)
 
 
@@ -554,209 +794,96 @@ def run_b200(args, rank, local_rank, world):
     import torch
     from pointcloud_slam_b200 import api, synth
 
-    prm = PARAMS[args.params]
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    data = synth.config1(N_MAP, N_SCAN)
-    scan = data["scan"]
-    n = len(scan)
-
-    ivox = api.IVox(resolution=prm["resolution"], nearby=prm["nearby"], device=local_rank)
-    ivox.AddPoints(data["map"])
-    kf = api.Esekf(ivox, extrinsic_est_en=prm["ext"])
-    scan4 = np.zeros((n, 4), np.float32)
-    scan4[:, :3] = scan
-    d_scan = torch.from_numpy(scan4).cuda()
-    torch.cuda.synchronize()
-
-    def step_device():
-        kf.change_x(data["x_prop"])
-        kf.change_P(data["P"])
-        kf.update_device(d_scan.data_ptr(), n)
-        return kf.stats.gpu_ms
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        api.flush_l2(local_rank)
-        step_device()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_wait = time.perf_counter()
-    while not sampler.sm and time.perf_counter() - t_wait < 3.0:   # NVML start-up must not eat the (short) timed region
-        step_device()
-    barrier()
-    launches0 = api.kernel_launches()
-    t_wall0 = time.perf_counter()
-    dev_ms = []
-    for _ in range(args.steps):
-        api.flush_l2(local_rank)          # untimed: evict the 126 MB L2 between steps
-        dev_ms.append(step_device())      # timed on the device: CUDA events on the engine's stream
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    launches = api.kernel_launches() - launches0  # the engine's own kernels (the L2-flush helper is not counted)
-    passes, knn_passes = kf.stats.passes, kf.stats.knn_passes
-    n_eff = list(kf.stats.n_eff)[:passes]
-
-    # warm-L2 variant (the map stays L2-resident between scans in real operation)
-    warm_ms = [step_device() for _ in range(args.steps)]
-
-    # e2e: the C-ABI call with host buffers (H2D + kernels + D2H), wall clock per call.  Headline: the scan sits in page-locked
-    # host memory (b200_host_alloc), so it crosses PCIe as it is and is unpacked on the device; second figure: a pageable
-    # buffer (what a PCL cloud is), packed through the handle's pinned stage first.
-    pinned = api.PinnedCloud(n, 3)
-    pinned.array[:] = scan
-    e2e_ms, e2e_pageable_ms = [], []
-    for src, out in ((pinned.array, e2e_ms), (scan, e2e_pageable_ms)):
-        for k in range(args.steps + 3):
-            api.flush_l2(local_rank)
-            kf.change_x(data["x_prop"])
-            kf.change_P(data["P"])
-            t0 = time.perf_counter()
-            kf.update_iterated_dyn_share_modified(src)
-            dt = (time.perf_counter() - t0) * 1e3
-            if k >= 3:
-                out.append(dt)
-    h2d, d2h = kf.io_bytes(n)
-    h2d = h2d - n * 16 + n * 12   # the pinned path ships the caller's 12-byte records
-    clocks = sampler.summary()
-
-    # per-kernel durations by CUDA events (profiling mode launches kernel by kernel)
-    kf.set_profiling(True)
-    search_ms, obs_ms, init_ms, prof_totals = [], [], [], []
-    for k in range(args.steps + 2):
-        api.flush_l2(local_rank)
-        step_device()
-        if k >= 2:
-            t = kf.kernel_times_ms()
-            prof_totals.append(list(t[:1 + 2 * passes]))
-            init_ms.append(t[0])
-            for p in range(passes):
-                if kf.stats.knn[p]:
-                    search_ms.append(t[1 + 2 * p])
-                obs_ms.append(t[2 + 2 * p])
-    kf.set_profiling(False)
-
-    extra = {}
-    comm = None
-    if world > 1 and not (args.no_ndt and args.fullmap_frames <= 0):
         ident = [api.Communicator.unique_id() if rank == 0 else None]
-        torch.distributed.broadcast_object_list(ident, src=0)
+        dist.broadcast_object_list(ident, src=0)
         comm = api.Communicator(world, rank, ident[0], device=local_rank)
-    if not args.no_ndt:
-        extra = ndt_legs(args, rank, local_rank, world, api, synth, torch, comm)
+
+    # ---- headline: configs[3] on all ranks
+    cfg = synth.config2(N_PRIOR, N_SCAN) if rank == 0 else None
+    if world > 1:
+        small = [dict(scan=cfg["scan"], p_true=cfg["p_true"], p_guess=cfg["p_guess"], guess=cfg["guess"]) if rank == 0 else None]
+        torch.distributed.broadcast_object_list(small, src=0)
+        if rank != 0:
+            cfg = small[0]
+    g, poses, rel = reloc_leg(args, rank, local_rank, world, api, synth, torch, comm, cfg)
+    oracle_ndt = rel.pop("_oracle_ndt", None)
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_ndt:
+        c = None
+        if oracle_ndt is not None:
+            o = oracle_ndt["oracle"]
+            t0 = time.perf_counter()
+            for _ in range(3):
+                s, gg, H = o.derivatives(cfg["p_guess"])
+            oracle_ndt["deriv_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+            t0 = time.perf_counter()
+            oracle_ndt["align"] = o.align(cfg["guess"])
+            oracle_ndt["align_ms"] = (time.perf_counter() - t0) * 1e3
+            oracle_ndt["deriv"] = (s, gg, H)
+            c = oracle_ndt
+        extra["ndt"] = ndt_leg(args, local_rank, api, g, cfg, c)
+        extra["ndt"]["set_target_ms"] = rel["set_target_ms"]
+    g.close()
+    del oracle_ndt
+    if cfg is not None:
+        cfg.pop("map", None)
+
+    # ---- the other workloads
+    if not args.no_iekf:
+        extra["iekf" if world == 1 else "iekf_replicas"] = iekf_leg(args, rank, local_rank, world, api, synth, torch, full=(world == 1))
     if args.fullmap_frames > 0:
         extra["fullmap"] = fullmap_leg(args, rank, local_rank, world, api, synth, torch, comm)
     if comm is not None:
         comm.close()
-
-    if args.seq_scans > 1 and rank == 0:
-        extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans)
-    if not args.no_ndt and rank == 0:
-        extra["scan2map"] = loam_leg(args, local_rank, api, synth)
-
-    ms_step = float(np.mean(dev_ms))
-    ms_e2e = float(np.mean(e2e_ms))
-    if world > 1:
-        t = torch.tensor([ms_step, ms_e2e], device="cuda", dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_step, ms_e2e = float(t[0]), float(t[1])
+    if world == 1:
+        if args.seq_scans > 1:
+            extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans, args.seq_parity)
+        if not args.no_ndt:
+            extra["scan2map"] = loam_leg(args, local_rank, api, synth)
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
             torch.distributed.destroy_process_group()
         return
 
-    # roofline of the k-NN search kernel: algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md):
-    #   N*16 (scan point) + N*S*8 (one table probe per stencil cell) + 16*sum(C_i) (gathered map points) + N*20 (5 indices out)
-    o_l, Rl = synth.lidar_pose(data["x_prop"])
-    qw = (scan.astype(np.float64) @ Rl.T + o_l).astype(np.float32)
-    sum_c, cells = ivox.stencil_points(qw)
-    algo_bytes = n * 16 + n * prm["stencil"] * 8 + 16 * sum_c + n * 20
-    peak, peak_src = measured_peak()
-    k_ms = float(np.mean(search_ms)) if search_ms else float("nan")
-    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_search (stencil k-NN, 8 lanes/query)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch at this workload (P-livox, cold L2),
-                # ncu --set full capture summarised in profiles/r01_iekf_ncu_full_summary.md (prof_iekf_r1c, launch id 0)
-                "traffic": 29512704 + 2816000 if args.params == "livox" else None, "algorithmic_bytes": int(algo_bytes),
-                "kernel_ms": k_ms, "candidates_per_query": sum_c / n, "occupied_cells_per_query": cells / n,
-                "share_of_step": (knn_passes * k_ms) / float(np.mean([sum(x) for x in prof_totals])) if prof_totals else None,
-                "note": "kernel_ms is event-to-event inside the update's stream (includes ~4 us of launch/event gap); traffic = ncu dram bytes "
-                        "per launch with a cold L2 (2.3x the algorithmic bytes: 32-byte sectors around 16-byte table entries and short runs); "
-                        "one scan is a single wave of 625 blocks: the kernel is bound by instruction issue (425 warp instructions per query, "
-                        "half of them the 64-bit top-5 insertion, 15 of 32 lanes active) and by the latency of two dependent gathers, not by "
-                        "DRAM (profiles/README.md, r02 source-level counters)"}
-    # the same search kernel with enough parallelism to leave the launch-latency regime: 50 scans' worth of queries in one call
-    rng = np.random.default_rng(1)
-    qbig = np.ascontiguousarray(np.concatenate([qw + rng.normal(0, 0.05, qw.shape).astype(np.float32) for _ in range(50)], 0))
-    ivox.GetClosestPoint(qbig)
-    big_ms = []
-    for _ in range(5):
-        api.flush_l2(local_rank)
-        ivox.GetClosestPoint(qbig)
-        big_ms.append(ivox.last_knn_ms())
-    sum_cb, _ = ivox.stencil_points(qbig)
-    nb_ = len(qbig)
-    big_bytes = nb_ * 16 + nb_ * prm["stencil"] * 8 + 16 * sum_cb + nb_ * 20 + nb_ * 24   # + sqdist (20 B) and count (4 B) out
-    roofline["batched"] = {"queries": nb_, "kernel": "k_knn5 (same knn5_group<8> body, 1M queries per launch)", "kernel_ms": float(np.mean(big_ms)),
-                           "algorithmic_bytes": int(big_bytes), "achieved": big_bytes / (float(np.mean(big_ms)) * 1e-3) / 1e9,
-                           "frac": big_bytes / (float(np.mean(big_ms)) * 1e-3) / 1e9 / peak, "queries_per_s": nb_ / (float(np.mean(big_ms)) * 1e-3),
-                           "note": "L2 flushed before each launch; the 32 MB map becomes L2-resident during the launch"}
-    kernels = {"k_iekf_init_ms": float(np.mean(init_ms)), "k_search_ms": k_ms, "k_obs_ms": float(np.mean(obs_ms)),
-               "per_update": f"1 init + {passes} x (k_search, k_obs); k_search is a no-op on non-search passes",
-               "share_of_step": {"k_search": (knn_passes * k_ms) / float(np.mean([sum(x) for x in prof_totals])),
-                                 "k_obs": (passes * float(np.mean(obs_ms))) / float(np.mean([sum(x) for x in prof_totals]))},
-               "note": "event-to-event per kernel with plain launches (each interval carries ~3-4 us of launch / event gap that the graph "
-                       "replay of the timed steps does not pay); k_obs is bound by the latency of its serial parts - the per-point 5x3 QR "
-                       "on 137 threads per SM and the filter block's fp64 chain - not by bytes (profiles/README.md)"}
-
     line = {
-        "metric": "registered points/sec (IEKF update)", "value": world * n / (ms_step * 1e-3), "unit": "points/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 per-point math, f64 accumulation and filter", "data": "synthetic",
-        "config": {"workload": "configs[0]: 20k-pt Mid-360-shaped scan vs 2M-pt local map, one IEKF update per step",
-                   "params": args.params, "n_scan": n, "n_map": N_MAP, "passes": passes, "knn_passes": knn_passes, "n_eff": n_eff,
-                   "l2": "flushed between timed steps (256 MiB streaming write, untimed)",
-                   "parallelism": "replicas" if world > 1 else "single GPU"},
-        "ms_per_update_warm_l2": float(np.mean(warm_ms)),
-        "wall_s_timed_region_incl_flush": wall_s,
-        "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_update": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "input": "scan in page-locked host memory (b200_host_alloc), unpacked on the device",
-                "pageable_input_ms_per_update": float(np.mean(e2e_pageable_ms))},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "kernels": kernels,
+        "metric": "relocalization hypotheses/sec", "value": rel["value"], "unit": "hypotheses/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rel["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": headline_config(),
+        "e2e": rel["e2e"], "gpu_launches": rel["gpu_launches"], "clocks": rel["clocks"], "roofline": rel["roofline"],
+        "cpu_baseline": rel.get("cpu_baseline"), "parity": rel.get("parity"),
+        "reloc": {k: rel[k] for k in ("per_rank", "best", "best_score", "true_index", "collective", "set_target_ms", "wall_s_timed_region_incl_flush")},
     }
     line.update(extra)
-    if world == 1 and not args.no_cpu:
-        ms, cores, t_insert, out = cpu_oracle_run(data, prm, 20, 3, budget_s=25.0)
-        cpu_ms = float(np.median(ms))
-        line["cpu_baseline"] = {"value": n / (cpu_ms * 1e-3), "unit": "points/s", "cores": cores, "kind": "port",
-                                "ms_per_update": cpu_ms,
-                                "sample": f"{len(ms)} full-size updates on the same inputs (median); map insert {t_insert:.2f} s excluded"}
-        # parity gate printed with the timing: the GPU posterior against the oracle's on the same inputs
-        rc, x_o, P_o, st_o = out
-        step_device()
-        from oracle import binding as ob
-        d = ob.boxminus(kf.get_x(), x_o)
-        line["parity"] = {"pos_m": float(np.abs(d[:3]).max()), "rot_rad": float(np.abs(d[3:6]).max()),
-                          "passes_equal": bool(st_o.passes == kf.stats.passes),
-                          "n_eff_equal": bool(list(st_o.n_eff)[:passes] == list(kf.stats.n_eff)[:passes])}
-    else:
-        line["cpu_baseline"] = None
+    # the headline numbers of every leg once more, last on the line (stored tails keep the end of the line)
+    summ = {"reloc_hyp_per_s": rel["value"], "reloc_ms_per_4096": rel["ms_per_step"], "reloc_e2e_hyp_per_s": rel["e2e"]["value"], "n_gpus": world,
+            "reloc_parity": rel.get("parity"), "reloc_roofline_frac": rel["roofline"]["frac"]}
+    ie = extra.get("iekf") or extra.get("iekf_replicas")
+    if ie:
+        summ.update({"iekf_points_per_s": ie["value"], "iekf_ms_per_update": ie["ms_per_update"]})
+        if "e2e" in ie:
+            summ.update({"iekf_e2e_ms_per_update": ie["e2e"]["ms_per_update"], "knn_roofline_frac": ie["roofline"]["frac"],
+                         "knn_roofline_frac_1M_queries": ie["roofline"]["batched"]["frac"], "iekf_cpu_ms_per_update": (ie.get("cpu_baseline") or {}).get("ms_per_update"),
+                         "iekf_parity": ie.get("parity")})
+    if "ndt" in extra:
+        summ.update({"ndt_align_ms": extra["ndt"]["align_ms"]["device"], "ndt_set_target_ms_device": extra["ndt"]["set_target_ms"]["device"],
+                     "ndt_set_target_ms_e2e": extra["ndt"]["set_target_ms"]["e2e_wall"], "ndt_parity": extra["ndt"].get("parity")})
+    if "sequence" in extra:
+        sq = extra["sequence"]
+        summ.update({"seq_scans": sq["scans"], "seq_ms_per_scan_e2e": sq["ms_per_scan_e2e"]["mean"], "seq_map_incremental_ms": sq["ms_per_scan_e2e"]["map_incremental_mean"],
+                     "seq_ms_update_device": sq["ms_update_device"]["mean"], "seq_parity": sq["parity_vs_oracle"]})
+    if "fullmap" in extra:
+        fm = extra["fullmap"]
+        summ.update({"fullmap_keyframes": args.fullmap_frames, "fullmap_keyframes_per_s": fm["value"], "fullmap_seconds": fm["seconds"],
+                     "fullmap_exchange_ms": fm["exchange_ms"], "fullmap_parity": fm.get("parity")})
+    line["summary"] = summ
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -769,13 +896,17 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--params", default="livox", choices=list(PARAMS))
-    ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] / configs[3] legs")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
-    ap.add_argument("--seq-scans", type=int, default=120, help="configs[2] leg: scans in the sliding-map sequence (1000 = full; 0 = skip)")
-    ap.add_argument("--fullmap-frames", type=int, default=1600, help="configs[4] leg: keyframes to merge (10000 = full; 0 = skip)")
+    ap.add_argument("--params", default="livox", choices=list(PARAMS), help="configs[0] parameter set (livox.yaml / horizon.yaml)")
+    ap.add_argument("--no-ndt", action="store_true", help="skip the configs[1] and scan2map legs")
+    ap.add_argument("--no-iekf", action="store_true", help="skip the configs[0] leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / oracle parity legs")
+    ap.add_argument("--seq-scans", type=int, default=1000, help="configs[2] leg: scans in the sliding-map sequence (1000 = full size; 0 = skip)")
+    ap.add_argument("--seq-parity", type=int, default=120, help="configs[2] leg: scans checked against the CPU oracle")
+    ap.add_argument("--fullmap-frames", type=int, default=10000, help="configs[4] leg: keyframes to merge (10000 = full size; 0 = skip)")
     ap.add_argument("--fullmap-pool", type=int, default=32, help="distinct ray-cast keyframes in the replay pool")
     ap.add_argument("--fullmap-reuse", type=int, default=5, help="times the pool is replayed on one tile before moving to the next")
+    ap.add_argument("--fullmap-host-frames", type=int, default=800, help="keyframes of the host-buffer (e2e) pass of the configs[4] leg")
+    ap.add_argument("--ref-sample", type=int, default=256, help="--impl reference: hypotheses scored per step")
     ap.add_argument("--small", action="store_true", help="DEV ONLY: shrink the maps 10x (not a valid bench number)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()

@@ -206,6 +206,13 @@ int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* ndt, const float* poses16, 
 int32_t b200_reloc_argmin_strided(b200_comm* comm, b200_ndt* ndt, const float* poses16, int64_t h, int64_t h_begin, int64_t h_stride,
                                   int64_t* best, double* best_score, float* gpu_ms);
 
+/* measurement aids (bench.py): device time of the score kernel of the last score / relocalization call; the number of
+ * (source point, occupied neighbourhood voxel) pairs over h poses (algorithmic bytes of the roofline); a device-side
+ * rendezvous of the ranks on the handle's stream, so that a timed step starts on all ranks together */
+float b200_ndt_last_score_kernel_ms(b200_ndt* ndt);
+int32_t b200_ndt_score_pairs(b200_ndt* ndt, const float* poses16, int64_t h, int64_t* pairs);
+int32_t b200_ndt_stream_barrier(b200_comm* comm, b200_ndt* ndt);
+
 /* ------------------------------------------------------------------------- *
  * Voxel-grid reductions.
  *   b200_voxel_downsample replaces pcl::VoxelGrid<PointType>::filter as jueying_lio runs it on every scan

@@ -1,16 +1,23 @@
 // TEST INFRASTRUCTURE ONLY — part of the CPU oracle (see oracle/README.md).
 // Nothing under pointcloud-slam_b200/ may include this file.
 //
-// Tiny dense linear algebra used by the oracle restatements.  The reference
-// uses Eigen (not vendored in a usable form); the routines here
-// restate the *published* Eigen 3.3 algorithms the reference call sites pick:
-//   - ColPivHouseholderQR::solve   (common_lib.h:208,223)
-//   - Matrix::inverse() via PartialPivLU for n>4 (esekfom.hpp:1685,1706)
-//   - 3x3 inverse by cofactors      (voxel_grid_covariance_omp_impl.hpp:355,359)
-//   - SelfAdjointEigenSolver 3x3    (voxel_grid_covariance_omp_impl.hpp:333)
-//   - JacobiSVD(6x6).solve          (ndt_omp_impl.hpp:112-114)
-// Summation orders that Eigen's SIMD kernels would pick are unknowable here;
-// every reduction below is a plain left-to-right loop (documented contract).
+// Tiny dense linear algebra used by the oracle restatements.  The reference uses Eigen.  The copy vendored in the
+// reference (src/pointcloud_match/fast_gicp/thirdparty/Eigen) cannot be compiled - Eigen/Core and Eigen/src/Core are
+// missing from the snapshot - but the decomposition sources ARE there, and every routine below restates
+// the file it cites line by line (E/ = that directory's Eigen/src/):
+//   - ColPivHouseholderQR::computeInPlace / _solve_impl   E/QR/ColPivHouseholderQR.h:480-586, 595-620 + E/Householder/Householder.h:67-108,
+//                                                          116-172                                        (call sites common_lib.h:208,223)
+//   - Matrix::inverse() for n > 4 = partialPivLu().inverse()   E/LU/InverseImpl.h:22-31, E/LU/PartialPivLU.h:340-420 (unblocked kernel),
+//                                                          :504-529 (compute), :225-245 (_solve_impl)     (esekfom.hpp:1685,1706)
+//   - 3x3 inverse by cofactors                             E/LU/InverseImpl.h:125-176                      (vgc_impl:355,359)
+//   - SelfAdjointEigenSolver<Matrix3d>::compute            E/Eigenvalues/SelfAdjointEigenSolver.h:414-461, 498-569, 823-893,
+//                                                          E/Eigenvalues/Tridiagonalization.h:459-503, E/Jacobi/Jacobi.h:231-267,331-332
+//                                                                                                         (vgc_impl:333)
+//   - JacobiSVD<Matrix6d>(H, FullU|FullV).solve            E/SVD/JacobiSVD.h:666-796, E/misc/RealSvd2x2.h:18-51, E/Jacobi/Jacobi.h:83-113,
+//                                                          E/SVD/SVDBase.h:149-157,198-205,308-318        (ndt_omp_impl.hpp:112-114)
+// What stays unknowable without Eigen/src/Core: the order in which Eigen's SSE2 packet kernels add the terms of a
+// reduction (dot products, products of small matrices) and numext::hypot (restated from Eigen 3.4's published
+// MathFunctionsImpl.h).  Every reduction below is a plain left-to-right loop (documented contract).
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -273,6 +280,304 @@ inline void svd_solve_sym6(const double H[36], const double rhs[6], double x[6])
         for (int i = 0; i < 6; ++i) d += V[i * 6 + k] * rhs[i];
         d /= w[k];
         for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + k] * d;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Givens rotation, real case: JacobiRotation<double>::makeGivens (E/Jacobi/Jacobi.h:231-267)
+// ---------------------------------------------------------------------------
+inline void make_givens(double p, double q, double& c, double& s) {
+    if (q == 0.0) {
+        c = p < 0.0 ? -1.0 : 1.0;
+        s = 0.0;
+    } else if (p == 0.0) {
+        c = 0.0;
+        s = q < 0.0 ? 1.0 : -1.0;
+    } else if (std::fabs(p) > std::fabs(q)) {
+        double t = q / p;
+        double u = std::sqrt(1.0 + t * t);
+        if (p < 0.0) u = -u;
+        c = 1.0 / u;
+        s = -t * c;
+    } else {
+        double t = p / q;
+        double u = std::sqrt(1.0 + t * t);
+        if (q < 0.0) u = -u;
+        s = -1.0 / u;
+        c = -t * s;
+    }
+}
+// numext::hypot for reals (Eigen 3.4 Core/MathFunctionsImpl.h positive_real_hypot - not in the snapshot, published form)
+inline double eigen_hypot(double x, double y) {
+    x = std::fabs(x);
+    y = std::fabs(y);
+    if (std::isinf(x) || std::isinf(y)) return std::numeric_limits<double>::infinity();
+    if (std::isnan(x) || std::isnan(y)) return std::numeric_limits<double>::quiet_NaN();
+    double p = x > y ? x : y;
+    if (p == 0.0) return 0.0;
+    double qp = (y < x ? y : x) / p;
+    return p * std::sqrt(1.0 + qp * qp);
+}
+
+// ---------------------------------------------------------------------------
+// SelfAdjointEigenSolver<Matrix3d>::compute(A, ComputeEigenvectors): eigenvalues ascending in w, eigenvectors in
+// the columns of V (row-major storage here).  Only the lower triangle of A (row-major) is read.
+//   scaling                   SelfAdjointEigenSolver.h:445-449
+//   3x3 tridiagonalisation    Tridiagonalization.h:459-503
+//   deflation / iteration     SelfAdjointEigenSolver.h:498-550 (m_maxIterations = 30, :375)
+//   implicit QR step          SelfAdjointEigenSolver.h:823-893
+//   ascending sort            SelfAdjointEigenSolver.h:551-567
+// Returns false on NoConvergence (the eigenvalues are then left unsorted, as in Eigen).
+// ---------------------------------------------------------------------------
+inline bool eigen_selfadjoint3(const double* A, double w[3], double V[9]) {
+    const double dmin = std::numeric_limits<double>::min();
+    double m00 = A[0], m10 = A[3], m11 = A[4], m20 = A[6], m21 = A[7], m22 = A[8];
+    double scale = 0.0;
+    {
+        const double l[6] = {m00, m10, m11, m20, m21, m22};
+        for (int i = 0; i < 6; ++i) scale = std::fabs(l[i]) > scale ? std::fabs(l[i]) : scale;  // the strict upper part is zero
+    }
+    if (scale == 0.0) scale = 1.0;
+    m00 /= scale; m10 /= scale; m11 /= scale; m20 /= scale; m21 /= scale; m22 /= scale;
+    double diag[3], sub[2];
+    double Q[3][3];  // Q[row][col]
+    diag[0] = m00;
+    const double v1norm2 = m20 * m20;
+    if (v1norm2 <= dmin) {
+        diag[1] = m11; diag[2] = m22; sub[0] = m10; sub[1] = m21;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Q[i][j] = i == j ? 1.0 : 0.0;
+    } else {
+        const double beta = std::sqrt(m10 * m10 + v1norm2);
+        const double invBeta = 1.0 / beta;
+        const double m01 = m10 * invBeta, m02 = m20 * invBeta;
+        const double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
+        diag[1] = m11 + m02 * q;
+        diag[2] = m22 - m02 * q;
+        sub[0] = beta;
+        sub[1] = m21 - m01 * q;
+        Q[0][0] = 1; Q[0][1] = 0; Q[0][2] = 0;
+        Q[1][0] = 0; Q[1][1] = m01; Q[1][2] = m02;
+        Q[2][0] = 0; Q[2][1] = m02; Q[2][2] = -m01;
+    }
+    const int n = 3, maxIterations = 30;
+    int end = n - 1, start = 0, iter = 0;
+    const double precision_inv = 1.0 / std::numeric_limits<double>::epsilon();
+    while (end > 0) {
+        for (int i = start; i < end; ++i) {
+            if (std::fabs(sub[i]) < dmin) {
+                sub[i] = 0.0;
+            } else {
+                const double scaled = precision_inv * sub[i];
+                if (scaled * scaled <= (std::fabs(diag[i]) + std::fabs(diag[i + 1]))) sub[i] = 0.0;
+            }
+        }
+        while (end > 0 && sub[end - 1] == 0.0) end--;
+        if (end <= 0) break;
+        iter++;
+        if (iter > maxIterations * n) break;
+        start = end - 1;
+        while (start > 0 && sub[start - 1] != 0.0) start--;
+        // tridiagonal_qr_step
+        double td = (diag[end - 1] - diag[end]) * 0.5;
+        double e = sub[end - 1];
+        double mu = diag[end];
+        if (td == 0.0) {
+            mu -= std::fabs(e);
+        } else if (e != 0.0) {
+            const double e2 = e * e;
+            const double h = eigen_hypot(td, e);
+            if (e2 == 0.0) mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+            else mu -= e2 / (td + (td > 0.0 ? h : -h));
+        }
+        double x = diag[start] - mu;
+        double z = sub[start];
+        for (int k = start; k < end && z != 0.0; ++k) {
+            double c, s;
+            make_givens(x, z, c, s);
+            const double sdk = s * diag[k] + c * sub[k];
+            const double dkp1 = s * sub[k] + c * diag[k + 1];
+            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+            diag[k + 1] = s * sdk + c * dkp1;
+            sub[k] = c * sdk - s * dkp1;
+            if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+            x = sub[k];
+            if (k < end - 1) {
+                z = -s * sub[k + 1];
+                sub[k + 1] = c * sub[k + 1];
+            }
+            // Q = Q * G: q.applyOnTheRight(k, k+1, rot) = apply_rotation_in_the_plane(col k, col k+1, rot.transpose())
+            if (!(c == 1.0 && s == 0.0)) {
+                for (int i = 0; i < 3; ++i) {
+                    const double xi = Q[i][k], yi = Q[i][k + 1];
+                    Q[i][k] = c * xi - s * yi;
+                    Q[i][k + 1] = s * xi + c * yi;
+                }
+            }
+        }
+    }
+    const bool ok = iter <= maxIterations * n;
+    if (ok) {
+        for (int i = 0; i < n - 1; ++i) {
+            int k = 0;
+            for (int j = 1; j < n - i; ++j)
+                if (diag[i + j] < diag[i + k]) k = j;
+            if (k > 0) {
+                std::swap(diag[i], diag[k + i]);
+                for (int r = 0; r < 3; ++r) std::swap(Q[r][i], Q[r][k + i]);
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i * 3 + j] = Q[i][j];
+    return ok;
+}
+
+// ---------------------------------------------------------------------------
+// JacobiSVD<Matrix<double,6,6>> sv(H, ComputeFullU | ComputeFullV); x = sv.solve(rhs)   (ndt_omp_impl.hpp:112-114)
+//   two-sided Jacobi sweeps        JacobiSVD.h:666-745
+//   2x2 real SVD                   misc/RealSvd2x2.h:18-51, makeJacobi Jacobi.h:83-113, rotation product Jacobi.h:53-59
+//   signs / scale / sort           JacobiSVD.h:747-792
+//   rank (threshold 6 eps) + solve SVDBase.h:149-157, 198-205, 308-318
+// H row-major.  The dot products of solve are plain left-to-right loops.
+// ---------------------------------------------------------------------------
+inline void jacobi_svd_solve6(const double H[36], const double rhs[6], double x[6], double* sv_out = nullptr) {
+    const int n = 6;
+    const double eps = std::numeric_limits<double>::epsilon(), dmin = std::numeric_limits<double>::min();
+    const double precision = 2.0 * eps;
+    double scale = 0.0;
+    bool nan = false;
+    for (int i = 0; i < 36; ++i) {
+        const double a = std::fabs(H[i]);
+        if (a != a) nan = true;
+        if (a > scale) scale = a;
+    }
+    if (nan || !std::isfinite(scale)) {  // InvalidInput: Eigen returns without a decomposition
+        for (int i = 0; i < 6; ++i) x[i] = std::numeric_limits<double>::quiet_NaN();
+        return;
+    }
+    if (scale == 0.0) scale = 1.0;
+    double W[6][6], U[6][6], V[6][6];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            W[i][j] = H[i * 6 + j] / scale;
+            U[i][j] = V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    double maxDiag = 0.0;
+    for (int i = 0; i < n; ++i) maxDiag = std::fabs(W[i][i]) > maxDiag ? std::fabs(W[i][i]) : maxDiag;
+    bool finished = false;
+    while (!finished) {
+        finished = true;
+        for (int p = 1; p < n; ++p) {
+            for (int q = 0; q < p; ++q) {
+                const double thr = std::max(dmin, precision * maxDiag);
+                if (std::fabs(W[p][q]) > thr || std::fabs(W[q][p]) > thr) {
+                    finished = false;
+                    // real_2x2_jacobi_svd
+                    double m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+                    double c1, s1;
+                    const double t = m00 + m11, d = m10 - m01;
+                    if (std::fabs(d) < dmin) {
+                        s1 = 0.0; c1 = 1.0;
+                    } else {
+                        const double u = t / d;
+                        const double tmp = std::sqrt(1.0 + u * u);
+                        s1 = 1.0 / tmp;
+                        c1 = u / tmp;
+                    }
+                    if (!(c1 == 1.0 && s1 == 0.0)) {  // m.applyOnTheLeft(0,1,rot1)
+                        const double a0 = m00, a1 = m01, b0 = m10, b1 = m11;
+                        m00 = c1 * a0 + s1 * b0; m01 = c1 * a1 + s1 * b1;
+                        m10 = -s1 * a0 + c1 * b0; m11 = -s1 * a1 + c1 * b1;
+                    }
+                    double cr, sr;  // j_right.makeJacobi(m00, m01, m11)
+                    {
+                        const double deno = 2.0 * std::fabs(m01);
+                        if (deno < dmin) {
+                            cr = 1.0; sr = 0.0;
+                        } else {
+                            const double tau = (m00 - m11) / deno;
+                            const double w = std::sqrt(tau * tau + 1.0);
+                            const double tt = tau > 0.0 ? 1.0 / (tau + w) : 1.0 / (tau - w);
+                            const double sign_t = tt > 0.0 ? 1.0 : -1.0;
+                            const double nn = 1.0 / std::sqrt(tt * tt + 1.0);
+                            sr = -sign_t * (m01 / std::fabs(m01)) * std::fabs(tt) * nn;
+                            cr = nn;
+                        }
+                    }
+                    // j_left = rot1 * j_right.transpose()
+                    const double c2 = cr, s2 = -sr;
+                    const double cl = c1 * c2 - s1 * s2, sl = c1 * s2 + s1 * c2;
+                    // m_workMatrix.applyOnTheLeft(p,q,j_left): rows p, q
+                    if (!(cl == 1.0 && sl == 0.0)) {
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = W[p][k], yi = W[q][k];
+                            W[p][k] = cl * xi + sl * yi;
+                            W[q][k] = -sl * xi + cl * yi;
+                        }
+                        // m_matrixU.applyOnTheRight(p,q,j_left.transpose()): columns p, q with (cl, sl)
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = U[k][p], yi = U[k][q];
+                            U[k][p] = cl * xi + sl * yi;
+                            U[k][q] = -sl * xi + cl * yi;
+                        }
+                    }
+                    // m_workMatrix.applyOnTheRight(p,q,j_right); m_matrixV.applyOnTheRight(p,q,j_right): columns with (cr, -sr)
+                    if (!(cr == 1.0 && -sr == 0.0)) {
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = W[k][p], yi = W[k][q];
+                            W[k][p] = cr * xi - sr * yi;
+                            W[k][q] = sr * xi + cr * yi;
+                        }
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = V[k][p], yi = V[k][q];
+                            V[k][p] = cr * xi - sr * yi;
+                            V[k][q] = sr * xi + cr * yi;
+                        }
+                    }
+                    maxDiag = std::max(maxDiag, std::max(std::fabs(W[p][p]), std::fabs(W[q][q])));
+                }
+            }
+        }
+    }
+    double sv[6];
+    for (int i = 0; i < n; ++i) {
+        const double a = W[i][i];
+        sv[i] = std::fabs(a);
+        if (a < 0.0)
+            for (int k = 0; k < n; ++k) U[k][i] = -U[k][i];
+    }
+    for (int i = 0; i < n; ++i) sv[i] *= scale;
+    int nonzero = n;
+    for (int i = 0; i < n; ++i) {
+        int pos = 0;
+        double mx = sv[i];
+        for (int j = 1; j < n - i; ++j)
+            if (sv[i + j] > mx) { mx = sv[i + j]; pos = j; }
+        if (mx == 0.0) { nonzero = i; break; }
+        if (pos) {
+            pos += i;
+            std::swap(sv[i], sv[pos]);
+            for (int k = 0; k < n; ++k) { std::swap(U[k][pos], U[k][i]); std::swap(V[k][pos], V[k][i]); }
+        }
+    }
+    if (sv_out) for (int i = 0; i < n; ++i) sv_out[i] = sv[i];
+    // rank() and _solve_impl
+    const double pthr = std::max(sv[0] * (6.0 * eps), dmin);
+    int r = nonzero - 1;
+    while (r >= 0 && sv[r] < pthr) --r;
+    const int rank = r + 1;
+    double tmp[6];
+    for (int k = 0; k < rank; ++k) {
+        double d = 0.0;
+        for (int i = 0; i < n; ++i) d += U[i][k] * rhs[i];
+        tmp[k] = (1.0 / sv[k]) * d;
+    }
+    for (int i = 0; i < n; ++i) {
+        double d = 0.0;
+        for (int k = 0; k < rank; ++k) d += V[i][k] * tmp[k];
+        x[i] = d;
     }
 }
 

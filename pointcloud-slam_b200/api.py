@@ -141,6 +141,10 @@ def lib():
         L.b200_ndt_last_ms.argtypes = [vp]
         L.b200_ndt_last_launches.argtypes = [vp]
         L.b200_ndt_fitness_score.argtypes = [vp, vp, C.c_double, vp, vp]
+        L.b200_ndt_last_score_kernel_ms.restype = C.c_float
+        L.b200_ndt_last_score_kernel_ms.argtypes = [vp]
+        L.b200_ndt_score_pairs.argtypes = [vp, vp, i64, vp]
+        L.b200_ndt_stream_barrier.argtypes = [vp, vp]
     L.b200_downsampler_create.argtypes = [i32, C.POINTER(vp)]
     L.b200_downsampler_destroy.argtypes = [vp]
     L.b200_voxel_downsample.argtypes = [vp, vp, i64, i64, C.c_float, i32, vp, vp, i64, vp]
@@ -556,6 +560,21 @@ class NormalDistributionsTransform:
 
     def last_launches(self):
         return int(lib().b200_ndt_last_launches(self._handle()))
+
+    def last_score_kernel_ms(self):
+        """Device time of the k_ndt_score_batch launch of the last calculateScore / relocalize call."""
+        return float(lib().b200_ndt_last_score_kernel_ms(self._handle()))
+
+    def score_pairs(self, poses_cm16):
+        """(point, occupied voxel) pairs summed over the poses - roofline bookkeeping."""
+        poses = np.ascontiguousarray(poses_cm16, dtype=np.float32).reshape(-1, 16)
+        n = C.c_int64(0)
+        _check(lib().b200_ndt_score_pairs(self._handle(), _p(poses), poses.shape[0], C.byref(n)))
+        return n.value
+
+    def stream_barrier(self, comm):
+        """Device-side rendezvous of the ranks on this handle's stream (no-op without a communicator)."""
+        _check(lib().b200_ndt_stream_barrier(comm.h if comm is not None else None, self._handle()))
 
 
 class Communicator:

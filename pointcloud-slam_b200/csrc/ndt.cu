@@ -860,6 +860,23 @@ __global__ void k_ndt_nbhd_total(View v, const float* __restrict__ M16_rowmajor,
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
 }
 
+// same count for a batch of poses (col-major 4x4 each): grid = (point chunks, hypotheses)
+__global__ void k_ndt_pairs_batch(View v, const float* __restrict__ poses, unsigned long long* out) {
+    __shared__ float M[12];
+    const int h = blockIdx.y;
+    if (threadIdx.x < 12) M[threadIdx.x] = poses[(size_t)h * 16 + (threadIdx.x & 3) * 4 + (threadIdx.x >> 2)];
+    __syncthreads();
+    unsigned long long cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_src; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(v.src + i);
+        float tx, ty, tz;
+        xform(M, p.x, p.y, p.z, tx, ty, tz);
+        for (int s = 0; s < v.nst; ++s) cnt += nbr_leaf(v, tx, ty, tz, s) >= 0 ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
 // Order-preserving map double -> uint64 (NaN -> 0, below every real score)
 __device__ __forceinline__ unsigned long long dbl_key(double s) {
     if (s != s) return 0ull;
@@ -1025,9 +1042,10 @@ struct Ndt {
     PinnedBuf<Ctl> h_ctl;
     PinnedBuf<double> h_scores;
     PinnedBuf<float> h_poses;
-    DevBuf<unsigned long long> d_best;
+    DevBuf<unsigned long long> d_best, d_bar;
     PinnedBuf<unsigned long long> h_best;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;  // around the score kernel alone (roofline of k_ndt_score_batch)
     double d1 = 0, d2 = 0, d3 = 0;
     float last_ms = 0.f;
     int last_launches = 0;
@@ -1060,6 +1078,8 @@ int32_t Ndt::init(const b200_ndt_params* p, int dev) {
     coop_launch = prop.cooperativeLaunch != 0;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventCreate(&evs0));
+    CUDA_TRY(cudaEventCreate(&evs1));
     CUDA_TRY(d_small.reserve(16));
     CUDA_TRY(h_small.reserve(16));
     CUDA_TRY(d_best.reserve(4));
@@ -1076,9 +1096,11 @@ void Ndt::destroy() {
     d_npts.release(); d_vals_in.release(); d_vals_out.release(); d_run_cnt.release(); d_run_off.release(); d_small.release();
     d_keys_in.release(); d_keys_out.release(); d_uniq.release(); d_valid.release(); cub_tmp.release();
     h_stage.release(); h_small.release(); d_ctl.release(); d_partials.release(); d_p_in.release(); d_scores.release(); d_poses.release();
-    h_ctl.release(); h_scores.release(); h_poses.release(); d_best.release(); h_best.release();
+    h_ctl.release(); h_scores.release(); h_poses.release(); d_best.release(); d_bar.release(); h_best.release();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (evs0) cudaEventDestroy(evs0);
+    if (evs1) cudaEventDestroy(evs1);
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
 }
@@ -1312,9 +1334,11 @@ int32_t Ndt::score_batch_device(const float* d_poses16, int64_t h, double* d_out
     CUDA_TRY(d_partials.reserve((size_t)h * nch));
     const dim3 grid(nch, (unsigned)h);
     const View v = view();
+    CUDA_TRY(cudaEventRecord(evs0, stream));
     if (prm.search == 1) k_ndt_score_batch<1><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
     else if (prm.search == 27) k_ndt_score_batch<27><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
     else k_ndt_score_batch<7><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
+    CUDA_TRY(cudaEventRecord(evs1, stream));
     k_ndt_score_finish<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_partials.p, nch, h, n_src, d_out);
     LAUNCH_COUNT(2);
     CUDA_TRY(cudaGetLastError());
@@ -1630,11 +1654,15 @@ static int32_t reloc_argmin_impl(b200_comm* comm, b200_ndt* n, const float* pose
     }
     unsigned long long* d = k.d_best.p;  // [0..1] local (key, index), [2..2+2R) the pairs of all ranks
     CUDA_TRY(cudaEventRecord(k.ev0, k.stream));
+    // a rank whose scoring fails still takes part in the collective (with "no hypothesis"), so the healthy ranks do not
+    // block in NCCL; the error is returned after the exchange
+    int32_t rc_local = B200_OK;
+    std::string err_local;
     if (h) {
-        int32_t rc = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
-        if (rc) return rc;
+        rc_local = k.score_batch_device(k.d_poses.p, h, k.d_scores.p);
+        if (rc_local) err_local = g_last_error;
     }
-    ndt::k_local_best<<<1, 256, 0, k.stream>>>(k.d_scores.p, h, h_begin, h_stride, d);
+    ndt::k_local_best<<<1, 256, 0, k.stream>>>(k.d_scores.p, rc_local ? 0 : h, h_begin, h_stride, d);
     LAUNCH_COUNT(1);
     if (R > 1) NCCL_TRY(comm, comm->AllGather(d, d + 2, 2, ncclUint64, comm->comm, k.stream));
     else CUDA_TRY(cudaMemcpyAsync(d + 2, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, k.stream));
@@ -1644,6 +1672,7 @@ static int32_t reloc_argmin_impl(b200_comm* comm, b200_ndt* n, const float* pose
     CUDA_TRY(cudaGetLastError());
     cudaEventElapsedTime(&k.last_ms, k.ev0, k.ev1);
     if (gpu_ms) *gpu_ms = k.last_ms;
+    if (rc_local) { g_last_error = err_local; return rc_local; }
     unsigned long long key = 0, idx = ~0ull;
     for (int r = 0; r < R; ++r) {
         const unsigned long long kr = k.h_best.p[2 * r], ir = k.h_best.p[2 * r + 1];
@@ -1657,6 +1686,45 @@ static int32_t reloc_argmin_impl(b200_comm* comm, b200_ndt* n, const float* pose
     if (best_score) *best_score = sc;
     return B200_OK;
 }
+/* device time of the k_ndt_score_batch launch of the last score / relocalization call (CUDA events around that kernel alone) */
+float b200_ndt_last_score_kernel_ms(b200_ndt* n) {
+    if (!n) return 0.f;
+    float ms = 0.f;
+    cudaSetDevice(n->k.device);
+    if (cudaEventElapsedTime(&ms, n->k.evs0, n->k.evs1) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+/* roofline bookkeeping: number of (source point, occupied neighbourhood voxel) pairs summed over h poses */
+int32_t b200_ndt_score_pairs(b200_ndt* n, const float* poses16, int64_t h, int64_t* pairs) {
+    if (!n || !poses16 || h < 1 || h > 65535 || !pairs) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    if (!k.have_target || k.n_src < 1) B200_FAIL(B200_ERR_ARG, "no target / source set");
+    CUDA_SET_DEVICE(k.device);
+    CUDA_TRY(k.d_poses.reserve((size_t)h * 16)); CUDA_TRY(k.h_poses.reserve((size_t)h * 16));
+    CUDA_TRY(k.d_best.reserve(4)); CUDA_TRY(k.h_best.reserve(4));
+    memcpy(k.h_poses.p, poses16, (size_t)h * 16 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(k.d_poses.p, k.h_poses.p, (size_t)h * 16 * sizeof(float), cudaMemcpyHostToDevice, k.stream));
+    CUDA_TRY(cudaMemsetAsync(k.d_best.p, 0, sizeof(unsigned long long), k.stream));
+    ndt::k_ndt_pairs_batch<<<dim3(8, (unsigned)h), 256, 0, k.stream>>>(k.view(), k.d_poses.p, k.d_best.p);
+    CUDA_TRY(cudaMemcpyAsync(k.h_best.p, k.d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    CUDA_TRY(cudaGetLastError());
+    *pairs = (int64_t)k.h_best.p[0];
+    return B200_OK;
+}
+/* Device-side rendezvous of the ranks on this handle's stream (a one-word ncclAllReduce): work enqueued afterwards starts
+ * on all ranks together.  bench.py calls it before each timed relocalization step so that the per-step device time is
+ * not inflated by the host-side start skew of the ranks. */
+int32_t b200_ndt_stream_barrier(b200_comm* comm, b200_ndt* n) {
+    if (!n) B200_FAIL(B200_ERR_ARG, "bad argument");
+    if (!comm || comm->nranks < 2) return B200_OK;
+    Ndt& k = n->k;
+    CUDA_SET_DEVICE(k.device);
+    CUDA_TRY(k.d_bar.reserve(2));
+    NCCL_TRY(comm, comm->AllReduce(k.d_bar.p, k.d_bar.p + 1, 1, ncclUint64, ncclSum, comm->comm, k.stream));
+    return B200_OK;
+}
+
 int32_t b200_reloc_argmin(b200_comm* comm, b200_ndt* n, const float* poses16, int64_t h, int64_t h_begin, int64_t* best, double* best_score,
                           float* gpu_ms) {
     return reloc_argmin_impl(comm, n, poses16, h, h_begin, 1, best, best_score, gpu_ms);
