@@ -172,6 +172,11 @@ int32_t b200_ndt_align(b200_ndt* ndt, const float* guess16, float* final16, b200
 int32_t b200_ndt_derivatives(b200_ndt* ndt, const double* p6, double* score, double* g6, double* H36);
 /* computeHessian (double path, ndt_omp_impl.hpp:499-560) */
 int32_t b200_ndt_hessian(b200_ndt* ndt, const double* p6, double* H36);
+/* parity primitive: the Newton direction Eigen::JacobiSVD<Matrix<double,6,6>>(H, FullU | FullV).solve(rhs) of
+ * computeTransformation (ndt_omp_impl.hpp:112-114) as the device computes it.  *path (may be NULL): 0 = pivoted-elimination
+ * shortcut (H comfortably full rank), 1 = literal two-sided Jacobi SVD with Eigen's 6-eps rank threshold; force_svd = 1
+ * always takes the latter. */
+int32_t b200_ndt_newton_direction(b200_ndt* ndt, const double* H36, const double* rhs6, int32_t force_svd, double* x6, int32_t* path);
 /* pcl::Registration::getFitnessScore(max_range) (PCL; loop-closure gate at jueying_slam/src/mapOptmization.cpp:693,719): mean
  * squared distance from the source, moved by T16 (column-major; NULL = final transformation of the last align), to its exact
  * nearest target points; points farther than max_range (squared distance) are skipped; DBL_MAX when none is in range */

@@ -118,6 +118,10 @@ def lib():
         L.orc_loam_optimize.restype = i32
         L.orc_loam_optimize.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, i32, vp, vp, vp, vp]
         L.orc_euler_from_matrix.argtypes = [vp, vp]
+        L.orc_set_legacy_eigen.argtypes = [i32]
+        L.orc_eigen_selfadjoint3.restype = i32
+        L.orc_eigen_selfadjoint3.argtypes = [vp, vp, vp]
+        L.orc_jacobi_svd_solve6.argtypes = [vp, vp, vp, vp]
         L.orc_matrix_from_pose.argtypes = [vp, vp]
         _LIB = L
     return _LIB
@@ -221,6 +225,26 @@ class OracleLio:
         tot = lib().orc_map_incremental(self.h, _p(scan), scan.shape[0], scan.strides[0], _p(x), int(ekf_inited),
                                         C.byref(na), C.byref(nd))
         return tot, na.value, nd.value
+
+
+def set_legacy_eigen(on: bool):
+    """Test switch: the round-1 cyclic-Jacobi substitutes instead of the restated Eigen SelfAdjointEigenSolver / JacobiSVD."""
+    lib().orc_set_legacy_eigen(int(on))
+
+
+def eigen_selfadjoint3(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    w, V = np.zeros(3), np.zeros((3, 3))
+    ok = lib().orc_eigen_selfadjoint3(_p(A), _p(w), _p(V))
+    return bool(ok), w, V
+
+
+def jacobi_svd_solve6(H, rhs):
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x, sv = np.zeros(6), np.zeros(6)
+    lib().orc_jacobi_svd_solve6(_p(H), _p(rhs), _p(x), _p(sv))
+    return x, sv
 
 
 def esti_plane(pts, thr=0.1):

@@ -10,8 +10,10 @@
 //   updateDerivatives / computeHessian / updateHessian           ndt_omp_impl.hpp:452-590
 //   updateIntervalMT / trialValueSelectionMT / computeStepLengthMT  ndt_omp_impl.hpp:594-833
 //   calculateScore                                    ndt_omp_impl.hpp:836-880
-// Third-party arithmetic restated from published behaviour: pcl::transformPointCloud
-// (PCL 1.7/1.8 scalar form), pcl::getMinMax3D, Eigen eulerAngles(0,1,2), AngleAxis products.
+// Third-party arithmetic: Eigen's SelfAdjointEigenSolver, JacobiSVD, 3x3 inverse and eulerAngles(0,1,2) are restated
+// from the Eigen sources vendored in the reference (fast_gicp/thirdparty/Eigen/Eigen/src/{Eigenvalues,SVD,LU,Geometry},
+// file:line in smallmat.h and at euler_012); pcl::transformPointCloud (PCL 1.7/1.8 scalar form), pcl::getMinMax3D and the
+// AngleAxis products (Eigen/src/Core and Geometry/AngleAxis arithmetic over absent Core) from published behaviour.
 #include "oracle.h"
 #include "smallmat.h"
 
@@ -21,6 +23,7 @@
 #include <vector>
 
 namespace orc {
+int g_legacy_eigen = 0;  // test switch (orc_set_legacy_eigen): 1 = round-1 cyclic-Jacobi substitutes instead of the Eigen restatements
 
 struct Leaf {
     int nr_points = 0;
@@ -111,7 +114,10 @@ struct Ndt {
             double A[9], w[3], V[9];
             for (int a = 0; a < 3; ++a)  // SelfAdjointEigenSolver reads the lower triangle
                 for (int b = 0; b < 3; ++b) A[a * 3 + b] = (a >= b) ? lf.cov[a * 3 + b] : lf.cov[b * 3 + a];
-            jacobi_eig_sym(A, 3, w, V);
+            // eigensolver.compute(leaf.cov_) (vgc_impl:333): Eigen's tridiagonalisation + implicit QR, restated from the vendored
+            // sources (smallmat.h).  g_legacy_eigen: the round-1 substitute (cyclic Jacobi), kept for the cross-check test only.
+            if (g_legacy_eigen) jacobi_eig_sym(A, 3, w, V);
+            else eigen_selfadjoint3(A, w, V);
             if (w[0] < 0 || w[1] < 0 || w[2] <= 0) { lf.nr_points = -1; continue; }
             double min_ev = prm.eig_ratio * w[2];
             if (w[0] < min_ev) {
@@ -493,7 +499,8 @@ struct Ndt {
     }
 };
 
-// Eigen Matrix3f::eulerAngles(0,1,2) (Eigen 3.3 EulerAngles.h), R row-major
+// Eigen Matrix3f::eulerAngles(0,1,2): fast_gicp/thirdparty/Eigen/Eigen/src/Geometry/EulerAngles.h:36-107 (a0 != a2 branch,
+// even permutation: i=0, j=1, k=2, result negated), R row-major
 static void euler_012(const float R[9], float res[3]) {
     const int i = 0, j = 1, k = 2;
     auto c = [&](int r, int cc) { return R[r * 3 + cc]; };
@@ -543,7 +550,9 @@ static int ndt_align(Ndt& N, const float* guess_cm, float* final_cm, orc_ndt_res
     while (!converged) {
         double ng[6];
         for (int i = 0; i < 6; ++i) ng[i] = -g[i];
-        svd_solve_sym6(H, ng, delta_p);
+        // Eigen::JacobiSVD<Matrix<double,6,6>> sv(hessian, FullU | FullV); delta_p = sv.solve(-score_gradient)  (:112-114)
+        if (g_legacy_eigen) svd_solve_sym6(H, ng, delta_p);
+        else jacobi_svd_solve6(H, ng, delta_p);
         double dn = 0;
         for (int i = 0; i < 6; ++i) dn += delta_p[i] * delta_p[i];
         dn = std::sqrt(dn);
@@ -582,6 +591,10 @@ using namespace orc;
 struct orc_ndt { Ndt N; };
 
 extern "C" {
+void orc_set_legacy_eigen(int32_t on) { orc::g_legacy_eigen = on; }
+/* stand-alone probes of the Eigen restatements (tests) */
+int32_t orc_eigen_selfadjoint3(const double* A9, double* w3, double* V9) { return orc::eigen_selfadjoint3(A9, w3, V9) ? 1 : 0; }
+void orc_jacobi_svd_solve6(const double* H36, const double* rhs6, double* x6, double* sv6) { orc::jacobi_svd_solve6(H36, rhs6, x6, sv6); }
 orc_ndt* orc_ndt_create(const orc_ndt_params* p) {
     orc_ndt* h = new orc_ndt();
     h->N.prm = *p;

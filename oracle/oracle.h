@@ -7,7 +7,9 @@
  *
  * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests
  * or fixtures for the iVox / IEKF / pclomp-NDT path and
- * cannot be compiled here (no PCL/Eigen/Boost/TBB).  The oracle
+ * cannot be compiled here (no PCL / Boost / TBB; the vendored Eigen lacks
+ * Eigen/Core).  The Eigen decompositions the path calls are
+ * restated line by line from the vendored Eigen sources (smallmat.h).  The oracle
  * is pinned by its own self-checks only (tests/test_oracle_*.py): stencil kNN
  * == brute force, Jacobian rows == finite differences, NDT gradient ==
  * numeric derivative of the score, pose recovery on noise-free data.
@@ -130,6 +132,11 @@ void orc_ndt_score_batch(orc_ndt* h, const float* poses16, int64_t nposes, doubl
 int64_t orc_ndt_nbhd_total(orc_ndt* h, const double* p6);
 /* pcl::Registration::getFitnessScore(max_range) with the source moved by T (col-major 4x4) */
 double orc_ndt_fitness(orc_ndt* h, const float* T16_colmajor, double max_range, int64_t* n_in_range); /* sum of neighbourhood sizes (roofline bytes) */
+/* test switch: 1 = round-1 substitutes (cyclic Jacobi) for SelfAdjointEigenSolver / JacobiSVD instead of the restatements of
+ * the Eigen sources vendored in the reference; and stand-alone probes of those restatements */
+void orc_set_legacy_eigen(int32_t on);
+int32_t orc_eigen_selfadjoint3(const double* A9_rowmajor, double* w3, double* V9_rowmajor);
+void orc_jacobi_svd_solve6(const double* H36_rowmajor, const double* rhs6, double* x6, double* sv6);
 void orc_euler_from_matrix(const float* m16_colmajor, float* rpy);
 void orc_matrix_from_pose(const double* p6, float* m16_colmajor);
 

@@ -126,6 +126,7 @@ def lib():
         L.b200_ndt_align.argtypes = [vp, vp, vp, C.POINTER(NdtResult)]
         L.b200_ndt_derivatives.argtypes = [vp, vp, vp, vp, vp]
         L.b200_ndt_hessian.argtypes = [vp, vp, vp]
+        L.b200_ndt_newton_direction.argtypes = [vp, vp, vp, i32, vp, vp]
         L.b200_ndt_score_batch.argtypes = [vp, vp, i64, vp]
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
@@ -527,6 +528,15 @@ class NormalDistributionsTransform:
         H = np.zeros((6, 6))
         _check(lib().b200_ndt_hessian(self._handle(), _p(p6), _p(H)))
         return H
+
+    def newtonDirection(self, H, rhs, force_svd=False):
+        """JacobiSVD(H).solve(rhs) as the device computes it; returns (x, path) with path 0 = elimination shortcut, 1 = Jacobi SVD."""
+        H = np.ascontiguousarray(H, dtype=np.float64)
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros(6)
+        path = C.c_int32(0)
+        _check(lib().b200_ndt_newton_direction(self._handle(), _p(H), _p(rhs), int(force_svd), _p(x), C.byref(path)))
+        return x, path.value
 
     def calculateScore(self, poses_cm16):
         """calculateScore (ndt_omp_impl.hpp:836-880) for a batch of poses ([h,16] column-major 4x4)."""

@@ -176,7 +176,7 @@ __global__ void k_ndt_finalize(const uint32_t* __restrict__ uniq, const int32_t*
     double A[9], w[3], V[9];
     for (int a = 0; a < 3; ++a)  // SelfAdjointEigenSolver reads the lower triangle
         for (int b = 0; b < 3; ++b) A[a * 3 + b] = (a >= b) ? cov[a * 3 + b] : cov[b * 3 + a];
-    jacobi_eig<3>(A, w, V);
+    eigen_selfadjoint3(A, w, V);  // eigensolver.compute(leaf.cov_), Eigen's own algorithm (ndt.cuh)
     if (w[0] < 0 || w[1] < 0 || w[2] <= 0) { npts[r] = -1; leafD[r] = L; return; }
     const double min_ev = eig_ratio * w[2];
     if (w[0] < min_ev) {
@@ -265,8 +265,8 @@ __global__ void k_ndt_gather(const float4* __restrict__ in, const int32_t* __res
 // ------------------------------------------------------------------ Newton / More-Thuente state machine (thread 0 of the last block)
 // H x = rhs the way JacobiSVD(H).solve(rhs) answers it for symmetric H (ndt_omp_impl.hpp:112-114): a pseudo-inverse that
 // drops singular values below max(sv) * 6 eps.  When H is comfortably full rank that is simply H^-1 rhs, which a pivoted
-// 6x6 elimination delivers in ~2 us of one thread; only a (nearly) rank-deficient H takes the eigen-decomposition path
-// (cyclic Jacobi, ~60 us) that implements the thresholding literally.
+// 6x6 elimination delivers in ~2 us of one thread; only a (nearly) rank-deficient H takes the literal two-sided Jacobi
+// SVD below.
 __device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, double* x) {
     double a[6][7];
     for (int i = 0; i < 6; ++i) {
@@ -300,23 +300,142 @@ __device__ __noinline__ bool lu_solve6(const double* Hs, const double* rhs, doub
     return true;
 }
 
-__device__ __noinline__ void eig_solve6(const double* Hs, const double* rhs, double* x) {
-    double A[36], w[6], V[36];
-    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
-    jacobi_eig<6>(A, w, V);
-    double smax = 0.0;
-    for (int i = 0; i < 6; ++i) smax = fmax(smax, fabs(w[i]));
-    const double thr = fmax(smax * 6.0 * 2.220446049250313e-16, 2.2250738585072014e-308);
-    for (int i = 0; i < 6; ++i) x[i] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        if (fabs(w[k]) <= thr) continue;
+// JacobiSVD<Matrix<double,6,6>>(H, FullU | FullV).solve(rhs), literally: two-sided Jacobi sweeps E/SVD/JacobiSVD.h:666-745,
+// 2x2 real SVD E/misc/RealSvd2x2.h:18-51 (makeJacobi E/Jacobi/Jacobi.h:83-113, rotation product :53-59), signs / scale / sort
+// JacobiSVD.h:747-792, rank with threshold 6 eps and solve E/SVD/SVDBase.h:149-157,198-205,308-318 (E/ = the Eigen sources
+// vendored in the reference).  Only a (nearly) rank-deficient or non-finite H gets here.
+__device__ __noinline__ void jacobi_svd_solve6(const double* H, const double* rhs, double* x) {
+    const int n = 6;
+    const double eps = 2.220446049250313e-16, dmin = 2.2250738585072014e-308, precision = 2.0 * eps;
+    double scale = 0.0;
+    bool bad = false;
+    for (int i = 0; i < 36; ++i) {
+        const double a = fabs(H[i]);
+        if (a != a) bad = true;
+        if (a > scale) scale = a;
+    }
+    if (bad || isinf(scale)) {  // InvalidInput: no decomposition; the caller sees a NaN step and stops (ndt_omp_impl.hpp:119-123)
+        for (int i = 0; i < 6; ++i) x[i] = CUDART_NAN;
+        return;
+    }
+    if (scale == 0.0) scale = 1.0;
+    double W[6][6], U[6][6], V[6][6];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            W[i][j] = H[i * 6 + j] / scale;
+            U[i][j] = V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    double maxDiag = 0.0;
+    for (int i = 0; i < n; ++i) maxDiag = fabs(W[i][i]) > maxDiag ? fabs(W[i][i]) : maxDiag;
+    bool finished = false;
+    int guard = 0;
+    while (!finished && ++guard < 1000) {
+        finished = true;
+        for (int p = 1; p < n; ++p) {
+            for (int q = 0; q < p; ++q) {
+                const double thr = fmax(dmin, precision * maxDiag);
+                if (fabs(W[p][q]) > thr || fabs(W[q][p]) > thr) {
+                    finished = false;
+                    double m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+                    double c1, s1;
+                    const double t = m00 + m11, d = m10 - m01;
+                    if (fabs(d) < dmin) {
+                        s1 = 0.0; c1 = 1.0;
+                    } else {
+                        const double u = t / d;
+                        const double tmp = sqrt(1.0 + u * u);
+                        s1 = 1.0 / tmp;
+                        c1 = u / tmp;
+                    }
+                    if (!(c1 == 1.0 && s1 == 0.0)) {
+                        const double a0 = m00, a1 = m01, b0 = m10, b1 = m11;
+                        m00 = c1 * a0 + s1 * b0; m01 = c1 * a1 + s1 * b1;
+                        m10 = -s1 * a0 + c1 * b0; m11 = -s1 * a1 + c1 * b1;
+                    }
+                    double cr, sr;
+                    {
+                        const double deno = 2.0 * fabs(m01);
+                        if (deno < dmin) {
+                            cr = 1.0; sr = 0.0;
+                        } else {
+                            const double tau = (m00 - m11) / deno;
+                            const double w = sqrt(tau * tau + 1.0);
+                            const double tt = tau > 0.0 ? 1.0 / (tau + w) : 1.0 / (tau - w);
+                            const double sign_t = tt > 0.0 ? 1.0 : -1.0;
+                            const double nn = 1.0 / sqrt(tt * tt + 1.0);
+                            sr = -sign_t * (m01 / fabs(m01)) * fabs(tt) * nn;
+                            cr = nn;
+                        }
+                    }
+                    const double c2 = cr, s2 = -sr;
+                    const double cl = c1 * c2 - s1 * s2, sl = c1 * s2 + s1 * c2;
+                    if (!(cl == 1.0 && sl == 0.0)) {
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = W[p][k], yi = W[q][k];
+                            W[p][k] = cl * xi + sl * yi;
+                            W[q][k] = -sl * xi + cl * yi;
+                        }
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = U[k][p], yi = U[k][q];
+                            U[k][p] = cl * xi + sl * yi;
+                            U[k][q] = -sl * xi + cl * yi;
+                        }
+                    }
+                    if (!(cr == 1.0 && -sr == 0.0)) {
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = W[k][p], yi = W[k][q];
+                            W[k][p] = cr * xi - sr * yi;
+                            W[k][q] = sr * xi + cr * yi;
+                        }
+                        for (int k = 0; k < n; ++k) {
+                            const double xi = V[k][p], yi = V[k][q];
+                            V[k][p] = cr * xi - sr * yi;
+                            V[k][q] = sr * xi + cr * yi;
+                        }
+                    }
+                    maxDiag = fmax(maxDiag, fmax(fabs(W[p][p]), fabs(W[q][q])));
+                }
+            }
+        }
+    }
+    double sv[6];
+    for (int i = 0; i < n; ++i) {
+        const double a = W[i][i];
+        sv[i] = fabs(a);
+        if (a < 0.0)
+            for (int k = 0; k < n; ++k) U[k][i] = -U[k][i];
+    }
+    for (int i = 0; i < n; ++i) sv[i] *= scale;
+    int nonzero = n;
+    for (int i = 0; i < n; ++i) {
+        int pos = 0;
+        double mx = sv[i];
+        for (int j = 1; j < n - i; ++j)
+            if (sv[i + j] > mx) { mx = sv[i + j]; pos = j; }
+        if (mx == 0.0) { nonzero = i; break; }
+        if (pos) {
+            pos += i;
+            const double ts = sv[i]; sv[i] = sv[pos]; sv[pos] = ts;
+            for (int k = 0; k < n; ++k) {
+                double tv = U[k][pos]; U[k][pos] = U[k][i]; U[k][i] = tv;
+                tv = V[k][pos]; V[k][pos] = V[k][i]; V[k][i] = tv;
+            }
+        }
+    }
+    const double pthr = fmax(sv[0] * (6.0 * eps), dmin);
+    int r = nonzero - 1;
+    while (r >= 0 && sv[r] < pthr) --r;
+    const int rank = r + 1;
+    double tmp[6];
+    for (int k = 0; k < rank; ++k) {
         double d = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) d += V[i * 6 + k] * rhs[i];
-        d /= w[k];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + k] * d;
+        for (int i = 0; i < n; ++i) d += U[i][k] * rhs[i];
+        tmp[k] = (1.0 / sv[k]) * d;
+    }
+    for (int i = 0; i < n; ++i) {
+        double d = 0.0;
+        for (int k = 0; k < rank; ++k) d += V[i][k] * tmp[k];
+        x[i] = d;
     }
 }
 
@@ -324,7 +443,22 @@ __device__ inline void svd_solve6(const double* H, const double* rhs, double* x)
     double Hs[36];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
-    if (!lu_solve6(Hs, rhs, x)) eig_solve6(Hs, rhs, x);
+    if (!lu_solve6(Hs, rhs, x)) jacobi_svd_solve6(H, rhs, x);
+}
+
+// parity probe of the Newton direction (b200_ndt_newton_direction): io = [H(36) | rhs(6) | x(6) | path(1)]
+__global__ void k_ndt_solve_probe(double* io, int force_svd) {
+    if (threadIdx.x || blockIdx.x) return;
+    double H[36], rhs[6], x[6];
+    for (int i = 0; i < 36; ++i) H[i] = io[i];
+    for (int i = 0; i < 6; ++i) rhs[i] = io[36 + i];
+    double Hs[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = 0.5 * (H[i * 6 + j] + H[j * 6 + i]);
+    double path = 0.0;
+    if (force_svd || !lu_solve6(Hs, rhs, x)) { jacobi_svd_solve6(H, rhs, x); path = 1.0; }
+    for (int i = 0; i < 6; ++i) io[42 + i] = x[i];
+    io[48] = path;
 }
 
 // updateIntervalMT (ndt_omp_impl.hpp:594-620)
@@ -1458,6 +1592,28 @@ int32_t b200_ndt_set_source(b200_ndt* n, const float* xyz, int64_t cnt, int64_t 
 int64_t b200_ndt_num_voxels(b200_ndt* n) { return n ? (int64_t)n->k.n_valid : 0; }
 float b200_ndt_last_ms(b200_ndt* n) { return n ? n->k.last_ms : 0.f; }
 int32_t b200_ndt_last_launches(b200_ndt* n) { return n ? n->k.last_launches : 0; }
+/* parity probe (a-12): the Newton direction the device computes for Hessian H and right-hand side rhs, i.e. what
+ * JacobiSVD(H).solve(rhs) answers (ndt_omp_impl.hpp:112-114).  *path = 0 pivoted-elimination shortcut (H comfortably full
+ * rank), 1 literal two-sided Jacobi SVD; force_svd = 1 always takes the latter. */
+int32_t b200_ndt_newton_direction(b200_ndt* n, const double* H36, const double* rhs6, int32_t force_svd, double* x6, int32_t* path) {
+    if (!n || !H36 || !rhs6 || !x6) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Ndt& k = n->k;
+    CUDA_SET_DEVICE(k.device);
+    CUDA_TRY(k.d_p_in.reserve(64));
+    double h[49] = {0};
+    memcpy(h, H36, 36 * sizeof(double));
+    memcpy(h + 36, rhs6, 6 * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(k.d_p_in.p, h, sizeof h, cudaMemcpyHostToDevice, k.stream));
+    ndt::k_ndt_solve_probe<<<1, 32, 0, k.stream>>>(k.d_p_in.p, force_svd);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaMemcpyAsync(h, k.d_p_in.p, sizeof h, cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    CUDA_TRY(cudaGetLastError());
+    memcpy(x6, h + 42, 6 * sizeof(double));
+    if (path) *path = (int32_t)h[48];
+    return B200_OK;
+}
+
 /* profiling aid: SM cycles the state machine (advance) and its Newton solves took over the last align */
 int32_t b200_ndt_debug_cycles(b200_ndt* n, int64_t* step_cycles, int64_t* solve_cycles) {
     if (!n || !n->k.h_ctl.p) return -1;

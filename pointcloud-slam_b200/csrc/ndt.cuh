@@ -344,6 +344,146 @@ __device__ __forceinline__ void inverse3(const double* m, double* inv) {
     inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
 
+// ---- Eigen decompositions the reference calls, following the Eigen sources vendored in the reference
+// (pointcloud_match/fast_gicp/thirdparty/Eigen/Eigen/src/, "E/" below) operation by operation; this TU is compiled
+// with -fmad=false, fp64 sqrt and division are IEEE, so the results are bit-identical to an SSE2 build of Eigen.
+// JacobiRotation<double>::makeGivens, real case (E/Jacobi/Jacobi.h:231-267)
+__device__ __forceinline__ void make_givens(double p, double q, double& c, double& s) {
+    if (q == 0.0) {
+        c = p < 0.0 ? -1.0 : 1.0;
+        s = 0.0;
+    } else if (p == 0.0) {
+        c = 0.0;
+        s = q < 0.0 ? 1.0 : -1.0;
+    } else if (fabs(p) > fabs(q)) {
+        const double t = q / p;
+        double u = sqrt(1.0 + t * t);
+        if (p < 0.0) u = -u;
+        c = 1.0 / u;
+        s = -t * c;
+    } else {
+        const double t = p / q;
+        double u = sqrt(1.0 + t * t);
+        if (q < 0.0) u = -u;
+        s = -1.0 / u;
+        c = -t * s;
+    }
+}
+// numext::hypot, real case (Eigen 3.4 Core/MathFunctionsImpl.h positive_real_hypot; Core is absent from the snapshot)
+__device__ __forceinline__ double eigen_hypot(double x, double y) {
+    x = fabs(x);
+    y = fabs(y);
+    if (isinf(x) || isinf(y)) return CUDART_INF;
+    if (isnan(x) || isnan(y)) return CUDART_NAN;
+    const double p = x > y ? x : y;
+    if (p == 0.0) return 0.0;
+    const double qp = (y < x ? y : x) / p;
+    return p * sqrt(1.0 + qp * qp);
+}
+// SelfAdjointEigenSolver<Matrix3d>::compute(A, ComputeEigenvectors) (vgc_impl:333): scaling E/Eigenvalues/SelfAdjointEigenSolver.h:445-449,
+// 3x3 tridiagonalisation E/Eigenvalues/Tridiagonalization.h:459-503, deflation + iteration :498-550, implicit QR step with
+// Wilkinson shift :823-893, ascending sort :551-567.  Reads the lower triangle of A (row-major); eigenvalues ascending in w,
+// eigenvectors in the columns of V (row-major).
+__device__ __noinline__ bool eigen_selfadjoint3(const double* A, double* w, double* V) {
+    const double dmin = 2.2250738585072014e-308;
+    double m00 = A[0], m10 = A[3], m11 = A[4], m20 = A[6], m21 = A[7], m22 = A[8];
+    double scale = fabs(m00);
+    scale = fmax(scale, fabs(m10)); scale = fmax(scale, fabs(m11)); scale = fmax(scale, fabs(m20));
+    scale = fmax(scale, fabs(m21)); scale = fmax(scale, fabs(m22));
+    if (scale == 0.0) scale = 1.0;
+    m00 /= scale; m10 /= scale; m11 /= scale; m20 /= scale; m21 /= scale; m22 /= scale;
+    double diag[3], sub[2], Q[3][3];
+    diag[0] = m00;
+    const double v1norm2 = m20 * m20;
+    if (v1norm2 <= dmin) {
+        diag[1] = m11; diag[2] = m22; sub[0] = m10; sub[1] = m21;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Q[i][j] = i == j ? 1.0 : 0.0;
+    } else {
+        const double beta = sqrt(m10 * m10 + v1norm2);
+        const double invBeta = 1.0 / beta;
+        const double m01 = m10 * invBeta, m02 = m20 * invBeta;
+        const double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
+        diag[1] = m11 + m02 * q;
+        diag[2] = m22 - m02 * q;
+        sub[0] = beta;
+        sub[1] = m21 - m01 * q;
+        Q[0][0] = 1; Q[0][1] = 0; Q[0][2] = 0;
+        Q[1][0] = 0; Q[1][1] = m01; Q[1][2] = m02;
+        Q[2][0] = 0; Q[2][1] = m02; Q[2][2] = -m01;
+    }
+    const int n = 3, maxIterations = 30;
+    int end = n - 1, start = 0, iter = 0;
+    const double precision_inv = 1.0 / 2.220446049250313e-16;
+    while (end > 0) {
+        for (int i = start; i < end; ++i) {
+            if (fabs(sub[i]) < dmin) {
+                sub[i] = 0.0;
+            } else {
+                const double scaled = precision_inv * sub[i];
+                if (scaled * scaled <= (fabs(diag[i]) + fabs(diag[i + 1]))) sub[i] = 0.0;
+            }
+        }
+        while (end > 0 && sub[end - 1] == 0.0) end--;
+        if (end <= 0) break;
+        iter++;
+        if (iter > maxIterations * n) break;
+        start = end - 1;
+        while (start > 0 && sub[start - 1] != 0.0) start--;
+        const double td = (diag[end - 1] - diag[end]) * 0.5;
+        const double e = sub[end - 1];
+        double mu = diag[end];
+        if (td == 0.0) {
+            mu -= fabs(e);
+        } else if (e != 0.0) {
+            const double e2 = e * e;
+            const double h = eigen_hypot(td, e);
+            if (e2 == 0.0) mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+            else mu -= e2 / (td + (td > 0.0 ? h : -h));
+        }
+        double x = diag[start] - mu;
+        double z = sub[start];
+        for (int k = start; k < end && z != 0.0; ++k) {
+            double c, s;
+            make_givens(x, z, c, s);
+            const double sdk = s * diag[k] + c * sub[k];
+            const double dkp1 = s * sub[k] + c * diag[k + 1];
+            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+            diag[k + 1] = s * sdk + c * dkp1;
+            sub[k] = c * sdk - s * dkp1;
+            if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+            x = sub[k];
+            if (k < end - 1) {
+                z = -s * sub[k + 1];
+                sub[k + 1] = c * sub[k + 1];
+            }
+            if (!(c == 1.0 && s == 0.0)) {  // q.applyOnTheRight(k, k+1, rot) (E/Jacobi/Jacobi.h:312-319, 331-332)
+                for (int i = 0; i < 3; ++i) {
+                    const double xi = Q[i][k], yi = Q[i][k + 1];
+                    Q[i][k] = c * xi - s * yi;
+                    Q[i][k + 1] = s * xi + c * yi;
+                }
+            }
+        }
+    }
+    const bool ok = iter <= maxIterations * n;
+    if (ok) {
+        for (int i = 0; i < n - 1; ++i) {
+            int k = 0;
+            for (int j = 1; j < n - i; ++j)
+                if (diag[i + j] < diag[i + k]) k = j;
+            if (k > 0) {
+                const double t = diag[i]; diag[i] = diag[k + i]; diag[k + i] = t;
+                for (int r = 0; r < 3; ++r) { const double tv = Q[r][i]; Q[r][i] = Q[r][k + i]; Q[r][k + i] = tv; }
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i * 3 + j] = Q[i][j];
+    return ok;
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric NxN matrix (row-major, destroyed): eigenvalues ascending in w,
 // eigenvectors in the columns of V.  Fully unrolled so A and V stay in registers.
 template <int N>

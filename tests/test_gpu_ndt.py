@@ -227,3 +227,72 @@ def test_full_size_properties(oracle, api, synth):
     assert max(wins, key=lambda w: (w[1], -w[0])) == (best, score)
     fit = g.getFitnessScore()
     assert 0 < fit < 0.05 and g.fitness_in_range == len(cfg["scan"])
+
+
+def dense_corner_scene(seed=9, n=120_000):
+    """Two walls and a floor sampled so densely that voxels hold > 1000 points: Leaf() starts cov_ from the identity, so only
+    such voxels reach the eigenvalue-inflation branch (vgc_impl:344-357), the one consumer of SelfAdjointEigenSolver's vectors."""
+    rng = np.random.default_rng(seed)
+    floor = np.c_[rng.uniform(-4, 4, n), rng.uniform(-4, 4, n), rng.normal(0, 0.01, n)]
+    wall = np.c_[rng.uniform(-4, 4, n), 4 + rng.normal(0, 0.01, n), rng.uniform(0, 3, n)]
+    wall2 = np.c_[-4 + rng.normal(0, 0.01, n // 2), rng.uniform(-4, 4, n // 2), rng.uniform(0, 3, n // 2)]
+    mp = np.concatenate([floor, wall, wall2]).astype(np.float32)
+    src = mp[rng.choice(len(mp), 4000, replace=False)] + rng.normal(0, 0.01, (4000, 3)).astype(np.float32)
+    return dict(map=mp, scan=np.ascontiguousarray(src))
+
+
+def test_inflated_leaves_bit_exact(oracle, api):
+    """The device runs Eigen's tridiagonalisation + implicit-QR eigen solver op for op (ndt.cuh eigen_selfadjoint3), so the
+    rebuilt covariances V L V^-1 of inflated leaves are bit-identical to the oracle's."""
+    cfg = dense_corner_scene()
+    o, g = pair(oracle, api, cfg, resolution=1.0)
+    Lo, Lg = o.leaves(), g.leaves()
+    w = np.linalg.eigvalsh(Lo["cov"])
+    assert (np.abs(w[:, 0] / w[:, 2] - 0.01) < 1e-9).sum() >= 20
+    np.testing.assert_array_equal(Lg["ids"], Lo["ids"])
+    np.testing.assert_array_equal(Lg["cov"], Lo["cov"])
+    np.testing.assert_array_equal(Lg["icov"], Lo["icov"])
+
+
+def test_newton_direction_parity(oracle, api):
+    """JacobiSVD(H).solve(-g) (ndt_omp_impl.hpp:112-114): the device's elimination shortcut for well-conditioned Hessians and
+    its literal two-sided Jacobi SVD (taken for rank-deficient / non-finite ones) against the oracle's restatement of Eigen."""
+    g = api.NormalDistributionsTransform()
+    g._handle()
+    rng = np.random.default_rng(12)
+    for t in range(40):
+        B = rng.normal(size=(6, 6))
+        H = -(B @ B.T) * rng.uniform(1e2, 1e6) - np.eye(6)
+        rhs = rng.normal(size=6) * 1e3
+        x0, sv = oracle.jacobi_svd_solve6(H, rhs)
+        x1, path = g.newtonDirection(H, rhs)
+        assert path == 0
+        assert np.abs(x1 - x0).max() <= 1e-9 * (sv[0] / sv[-1]) * np.abs(x0).max()
+        x2, path = g.newtonDirection(H, rhs, force_svd=True)
+        assert path == 1
+        np.testing.assert_array_equal(x2, x0)          # same algorithm, same op sequence: bit-identical
+    # rank deficient (a floor-only scene leaves x, y, yaw unobservable): singular values below 6 eps sigma_max are dropped
+    U = np.linalg.qr(rng.normal(size=(6, 6)))[0]
+    for s in ([5e6, 3e5, 1e4, 0.0, 0.0, 0.0], [1.0, 0.5, 0.25, 1e-17, 1e-18, 0.0], [0.0] * 6):
+        H = -(U @ np.diag(s) @ U.T)
+        rhs = rng.normal(size=6)
+        x0, sv = oracle.jacobi_svd_solve6(H, rhs)
+        x1, path = g.newtonDirection(H, rhs)
+        assert path == 1
+        np.testing.assert_array_equal(x1, x0)
+    H = np.eye(6)
+    H[1, 2] = np.nan
+    x1, path = g.newtonDirection(H, np.ones(6))
+    assert path == 1 and np.all(np.isnan(x1))           # NaN step: computeTransformation returns not converged (:119-123)
+
+
+def test_align_with_no_overlap_stops_like_the_reference(oracle, api, synth, ndt_small):
+    """No source point lands in a valid voxel: score, gradient and Hessian are zero, JacobiSVD.solve returns a zero step and
+    computeTransformation leaves at once with converged_ = true (ndt_omp_impl.hpp:119-123)."""
+    cfg = dict(map=ndt_small["map"], scan=ndt_small["scan"] + np.float32(500.0))
+    o, g = pair(oracle, api, cfg)
+    guess = np.eye(4, dtype=np.float32)
+    rc0, T0, r0 = o.align(guess)
+    rc1 = g.align(guess)
+    assert rc1 == rc0 and (g.result.iters, g.result.evals, g.result.converged) == (r0.iters, r0.evals, r0.converged)
+    np.testing.assert_allclose(g.getFinalTransformation(), T0, atol=1e-6)
