@@ -5,10 +5,15 @@
 // reference (src/pointcloud_match/fast_gicp/thirdparty/Eigen) cannot be compiled - Eigen/Core and Eigen/src/Core are
 // missing from the snapshot - but the decomposition sources ARE there, and every routine below restates
 // the file it cites line by line (E/ = that directory's Eigen/src/):
-//   - ColPivHouseholderQR::computeInPlace / _solve_impl   E/QR/ColPivHouseholderQR.h:480-586, 595-620 + E/Householder/Householder.h:67-108,
-//                                                          116-172                                        (call sites common_lib.h:208,223)
-//   - Matrix::inverse() for n > 4 = partialPivLu().inverse()   E/LU/InverseImpl.h:22-31, E/LU/PartialPivLU.h:340-420 (unblocked kernel),
-//                                                          :504-529 (compute), :225-245 (_solve_impl)     (esekfom.hpp:1685,1706)
+//   - ColPivHouseholderQR::computeInPlace / _solve_impl   E/QR/ColPivHouseholderQR.h:482-584, 587-608 + E/Householder/Householder.h:43-103
+//                                                          (makeHouseholder), 116-137 (applyHouseholderOnTheLeft) (call sites common_lib.h:208,223)
+//   - Matrix::inverse() for n > 4 = partialPivLu().inverse()   E/LU/InverseImpl.h:22-31, E/LU/PartialPivLU.h:358-411 (unblocked_lu: pivot
+//                                                          search, row swap, column scaling, rank-1 update), :525-548 (compute),
+//                                                          :196, 225-245 (inverse = solve(Identity): P, L, U)     (esekfom.hpp:1685,1706)
+//                                                          For 23 x 23 Eigen takes blocked_lu (:430-499, panels of 8 columns) whose
+//                                                          trailing updates and triangular solves run through Core/products kernels
+//                                                          (GEBP, absent from the snapshot): same pivots and the same factors in exact
+//                                                          arithmetic, rounding order of the block updates unknowable -> unblocked form here.
 //   - 3x3 inverse by cofactors                             E/LU/InverseImpl.h:125-176                      (vgc_impl:355,359)
 //   - SelfAdjointEigenSolver<Matrix3d>::compute            E/Eigenvalues/SelfAdjointEigenSolver.h:414-461, 498-569, 823-893,
 //                                                          E/Eigenvalues/Tridiagonalization.h:459-503, E/Jacobi/Jacobi.h:231-267,331-332

@@ -135,13 +135,22 @@ __host__ __device__ inline bool cell_in_range(int x, int y, int z) {
 __host__ __device__ inline uint64_t pack_key(int x, int y, int z) {
     return ((uint64_t)(uint32_t)(x + kKeyBias) << 42) | ((uint64_t)(uint32_t)(y + kKeyBias) << 21) | (uint64_t)(uint32_t)(z + kKeyBias);
 }
-__host__ __device__ inline uint32_t hash_key(uint64_t k) {  // 32-bit multiply-xorshift mix of the two key halves
-    uint32_t h = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+// Table placement with 2 x 2 x 2-voxel locality: the eight voxels of an aligned 2x2x2 block hash to ONE 128-byte line of the
+// table (8 entries of 16 bytes, position inside the line = the low bit of each cell coordinate), so the 27 probes of a
+// stencil search touch the lines of at most 8 blocks instead of 27 scattered 32-byte sectors, and z-neighbours share a
+// sector.  A collision steps 9 slots on: to the next line and the next position inside it, so a probe sequence visits
+// every slot of the table (9 is odd) even when all voxels share coordinate parities (a flat floor fills only half of
+// the in-line positions).
+__host__ __device__ inline uint32_t hash_key(uint64_t k) {  // 32-bit multiply-xorshift mix of the block key, times 8, plus the in-block index
+    const uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+    const uint32_t idx = ((hi >> 10) & 1u) << 2 | ((lo >> 21) & 1u) << 1 | (lo & 1u);  // low bits of x (bit 42), y (bit 21), z (bit 0)
+    uint32_t h = (lo & ~0x00200001u) * 0x9E3779B1u ^ (hi & ~0x00000400u) * 0x85EBCA77u;
     h ^= h >> 15;
     h *= 0x2C1B3C6Du;
     h ^= h >> 13;
-    return h;
+    return (h << 3) | idx;
 }
+__host__ __device__ inline uint32_t next_slot(uint32_t slot, uint32_t tmask) { return (slot + 9u) & tmask; }
 
 // Pass a strided host cloud through a pinned staging buffer as packed float4 (x,y,z,0).
 inline void pack_xyz_float4(const float* xyz, int64_t n, int64_t stride, float4* dst) {

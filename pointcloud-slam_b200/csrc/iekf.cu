@@ -167,6 +167,53 @@ __global__ void __launch_bounds__(KNN_BLOCK, (MODE == 0 ? 1280 : MODE == 5 ? 115
     if (lg == 0) nbc_out[q] = (unsigned char)c;
 }
 
+// warp-per-query variant (knn5_warp, map.cuh): one warp per scan point
+__global__ void __launch_bounds__(256) k_search_w(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+                                                  float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
+    pdl_trigger();
+    pdl_wait();
+    if (ctl->done || !ctl->converge) return;
+    __shared__ PassConsts pc;
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
+    __syncthreads();
+    const int q = (blockIdx.x * blockDim.x + tid) >> 5, lane = tid & 31;
+    if (q >= ctl->n) return;
+    const float4 pbody = __ldg(scan + q);
+    const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_warp(map, pw.x, pw.y, pw.z, lane, mine, key);
+    if (lane < 5) nb_out[(size_t)q * 5 + lane] = mine;
+    if (lane == 0) nbc_out[q] = (unsigned char)c;
+}
+
+// balanced 8-lanes-per-query variant (knn5_g8p, map.cuh)
+__global__ void __launch_bounds__(256, 5) k_search_p(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+                                                  float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
+    pdl_trigger();
+    pdl_wait();
+    if (ctl->done || !ctl->converge) return;
+    __shared__ PassConsts pc;
+    __shared__ __align__(16) uint32_t s_q[(256 / 8) * kG8pWords];
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
+    __syncthreads();
+    const int q = (blockIdx.x * blockDim.x + tid) >> 3, lg = tid & 7;
+    const bool active = q < ctl->n;   // groups past the end stay with their warp (full-mask collectives inside)
+    float3 pw = make_float3(0.f, 0.f, 0.f);
+    if (active) {
+        const float4 pbody = __ldg(scan + q);
+        pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
+    }
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_g8p(map, active, pw.x, pw.y, pw.z, lg, s_q + (tid >> 3) * kG8pWords, mine, key);
+    if (!active) return;
+    if (lg < 5) nb_out[(size_t)q * 5 + lg] = mine;
+    if (lg == 0) nbc_out[q] = (unsigned char)c;
+}
+
 union ObsSolveSmem {
     ObsSmem obs;
     SolveSmem solve;
@@ -497,8 +544,14 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
     for (int it = 0; it < npass; ++it) {
         const int mode = map->knn_mode();
         const bool pdl = !events;  // kernel -> kernel edges only (an event record in between makes it a full dependency anyway)
-        auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 4 ? k_search<4> : mode == 1 ? k_search<1> : k_search<0>;
-        CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(KNN_BLOCK), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        if (mode == 8) {
+            CUDA_TRY(launch_k(k_search_p, dim3(search_grid * KNN_BLOCK / 256), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        } else if (mode == 7) {
+            CUDA_TRY(launch_k(k_search_w, dim3(search_grid * (32 / KNN_G) * KNN_BLOCK / 256), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        } else {
+            auto ks = mode == 5 ? k_search<5> : mode == 6 ? k_search<6> : mode == 4 ? k_search<4> : mode == 1 ? k_search<1> : k_search<0>;
+            CUDA_TRY(launch_k(ks, dim3(search_grid), dim3(KNN_BLOCK), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        }
         if (events) CUDA_TRY(cudaEventRecord(evk[e++], stream));
         CUDA_TRY(launch_k(k_obs, dim3(nblocks), dim3(OBS_THREADS), stream, pdl, d_pts, (const float4*)d_nb.p, (const unsigned char*)d_nbc.p, ps,
                           d_ctl, prm.plane_thr, (int)prm.extrinsic_est_en, d_partials, (int)prm.max_iter, prm.R, (const double*)d_limit,

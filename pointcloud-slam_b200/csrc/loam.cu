@@ -401,14 +401,14 @@ static void loam_search(b200_loam* h, int64_t nc, int64_t ns) {
     using namespace loam;
     if (nc) {
         const unsigned grid = (unsigned)((nc * G + 255) / 256);
-        if (h->corner.knn_mode() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
-        else if (h->corner.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
+        if (h->corner.knn_mode_g8() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
+        else if (h->corner.knn_mode_g8() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
         else k_loam_search<0><<<grid, 256, 0, h->stream>>>(h->corner.view(), h->d_pts.p, (int)nc, h->d_ctl, h->d_nb.p, h->d_cnt.p);
     }
     if (ns) {
         const unsigned grid = (unsigned)((ns * G + 255) / 256);
-        if (h->surf.knn_mode() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
-        else if (h->surf.knn_mode() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
+        if (h->surf.knn_mode_g8() >= 5) k_loam_search<5><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
+        else if (h->surf.knn_mode_g8() == 1) k_loam_search<1><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
         else k_loam_search<0><<<grid, 256, 0, h->stream>>>(h->surf.view(), h->d_pts.p + nc, (int)ns, h->d_ctl, h->d_nb.p + nc * 5, h->d_cnt.p + nc);
     }
     LAUNCH_COUNT((nc ? 1 : 0) + (ns ? 1 : 0));

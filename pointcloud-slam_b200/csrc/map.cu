@@ -59,7 +59,7 @@ __global__ void k_upsert_runs(const uint64_t* __restrict__ uniq, const int32_t* 
             if (old == kEmptyKey) { created = true; break; }
             if (old == key) break;
         }
-        slot = (slot + 1) & tmask;
+        slot = next_slot(slot, tmask);
     }
     int4 v = created ? make_int4(0, 0, 0, 0) : make_int4(ent[slot].start, ent[slot].count, aux[slot].x, aux[slot].y);
     if (created) {
@@ -146,7 +146,7 @@ __global__ void k_lookup_runs(const uint64_t* __restrict__ uniq, const int32_t* 
         const uint64_t k = ent[slot].key;
         if (k == key) { found = (int)slot; break; }
         if (k == kEmptyKey) break;
-        slot = (slot + 1) & tmask;
+        slot = next_slot(slot, tmask);
     }
     run_slot[r] = found;
     run_first[r] = sorted_vals[run_off[r]];
@@ -187,7 +187,7 @@ __global__ void k_rehash(const MapEntry* __restrict__ old_ent, const int2* __res
     if (e.key == kEmptyKey || e.key == kTombKey) return;
     uint32_t slot = hash_key(e.key) & (tsize - 1);
     while (atomicCAS((unsigned long long*)&ent[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)e.key) != kEmptyKey)
-        slot = (slot + 1) & (tsize - 1);
+        slot = next_slot(slot, tsize - 1);
     ent[slot].start = e.start;
     ent[slot].count = e.count;
     aux[slot] = old_aux[s];
@@ -241,6 +241,40 @@ __global__ void __launch_bounds__(256) k_knn5(MapView m, const float4* __restric
     if (lg == 0) cnt[gid] = c;
 }
 
+// 8 lanes per query, balanced through shared memory (knn5_g8p)
+__global__ void __launch_bounds__(256, 5) k_knn5_p(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                                float* __restrict__ d2, int32_t* __restrict__ cnt) {
+    __shared__ __align__(16) uint32_t s_q[(256 / 8) * kG8pWords];
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, lg = threadIdx.x & 7;
+    const bool active = gid < n;   // groups past the end stay with their warp (full-mask collectives inside)
+    const float4 p = active ? __ldg(q + gid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_g8p(m, active, p.x, p.y, p.z, lg, s_q + (threadIdx.x >> 3) * kG8pWords, mine, key);
+    if (!active) return;
+    if (lg < 5) {
+        idx[gid * 5 + lg] = __float_as_int(mine.w);
+        d2[gid * 5 + lg] = (key == 0xffffffffu) ? 0.0f : __uint_as_float(key);
+    }
+    if (lg == 0) cnt[gid] = c;
+}
+
+// warp-per-query variant (knn5_warp)
+__global__ void __launch_bounds__(256) k_knn5_w(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                                float* __restrict__ d2, int32_t* __restrict__ cnt) {
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi >= n) return;  // whole warps leave together
+    const float4 p = __ldg(q + qi);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_warp(m, p.x, p.y, p.z, lane, mine, key);
+    if (lane < 5) {
+        idx[qi * 5 + lane] = __float_as_int(mine.w);
+        d2[qi * 5 + lane] = (key == 0xffffffffu) ? 0.0f : __uint_as_float(key);
+    }
+    if (lane == 0) cnt[qi] = c;
+}
+
 // number of map points resident in the occupied stencil cells of every query (the sum C_i of the roofline's
 // algorithmic-byte formula), and the number of occupied cells
 __global__ void k_stencil_points(MapView m, const float4* __restrict__ q, int n, unsigned long long* __restrict__ out) {
@@ -256,7 +290,7 @@ __global__ void k_stencil_points(MapView m, const float4* __restrict__ q, int n,
             uint32_t slot = hash_key(key) & m.tmask;
             MapEntry e = ld_entry(m.ent + slot);
             while (e.key != key && e.key != kEmptyKey) {
-                slot = (slot + 1) & m.tmask;
+                slot = next_slot(slot, m.tmask);
                 e = ld_entry(m.ent + slot);
             }
             if (e.key == key) { pts += (unsigned long long)e.count; cells += 1; }
@@ -530,19 +564,22 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     pack_xyz_float4(xyz, n, stride, h_stage.p);
     CUDA_TRY(cudaMemcpyAsync(in_pts.p, h_stage.p, n * sizeof(float4), cudaMemcpyHostToDevice, stream));
     constexpr int G = 8;
-    const int64_t threads = n * G;
     if (!ev0) { CUDA_TRY(cudaEventCreate(&ev0)); CUDA_TRY(cudaEventCreate(&ev1)); }
     CUDA_TRY(cudaEventRecord(ev0, stream));
     {
-        const unsigned grid = (unsigned)((threads + 255) / 256);
-        // large batches on a sparse map: the flattened walk (27 % fewer instructions, 0.61 -> 0.54 ms per 1M queries); a single
-        // scan (one wave of blocks) is faster with the lane-owned walk, which needs no shared-memory list
         int mode = knn_mode();
-        if (mode == 0 && n >= 200000 && !getenv("B200_KNN_MODE")) mode = 5;
-        if (mode >= 5) k_knn5<G, 5><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
-        else if (mode == 4) k_knn5<G, 4><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
-        else if (mode == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
-        else k_knn5<G, 0><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        if (mode == 8) {  // 8 lanes per query, candidates balanced through shared memory
+            k_knn5_p<<<(unsigned)((n * 8 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        } else if (mode == 7) {  // one warp per query
+            k_knn5_w<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        } else {
+            const unsigned grid = (unsigned)((n * G + 255) / 256);
+            if (mode == 0 && n >= 200000 && !getenv("B200_KNN_MODE")) mode = 5;
+            if (mode >= 5) k_knn5<G, 5><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+            else if (mode == 4) k_knn5<G, 4><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+            else if (mode == 1) k_knn5<G, 1><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+            else k_knn5<G, 0><<<grid, 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        }
     }
     CUDA_TRY(cudaEventRecord(ev1, stream));
     LAUNCH_COUNT(1);

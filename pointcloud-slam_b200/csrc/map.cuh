@@ -51,6 +51,13 @@ static __constant__ signed char c_stencil[27][4] = {
     {-1, 0, -1, 0}, {0, 1, 1, 0},  {0, -1, 1, 0},  {0, 1, -1, 0},  {0, -1, -1, 0}, {1, 1, 1, 0},   {-1, 1, 1, 0},
     {1, -1, 1, 0},  {1, 1, -1, 0}, {-1, -1, 1, 0}, {-1, 1, -1, 0}, {1, -1, -1, 0}, {-1, -1, -1, 0}};
 
+// The same order packed one byte per cell, (dx+1) | (dy+1) << 2 | (dz+1) << 4, in GLOBAL memory: a lane reading ITS cell's
+// offsets is a lane-indexed access, which the constant cache serialises address by address (ncu r02: a third of the stall
+// samples of the first warp-per-query kernel sat on three 27-way divergent LDC instructions); through L1 it is one
+// coalesced 32-byte request.
+static __device__ const unsigned char g_stencil_code[32] = {
+    21, 20, 22, 25, 17, 5, 37,  26, 24, 18, 16, 38, 36, 6, 4,  41, 33, 9, 1,  42, 40, 34, 10, 32, 8, 2, 0,  255, 255, 255, 255, 255};
+
 // IVox::Pos2Grid (ivox3d.h:284-286): round(p * inv_res) with std::round semantics.
 __device__ __forceinline__ int pos2cell(float v, float inv_res) { return (int)roundf(__fmul_rn(v, inv_res)); }
 
@@ -104,7 +111,7 @@ __device__ __forceinline__ uint32_t lane_stencil(int lg, int nstencil) {
     for (int t = 0; t < (27 + G - 1) / G; ++t) {
         const int s = lg + G * t;
         uint32_t b = 0xFFu;
-        if (s < nstencil) b = (uint32_t)(c_stencil[s][0] + 1) | ((uint32_t)(c_stencil[s][1] + 1) << 2) | ((uint32_t)(c_stencil[s][2] + 1) << 4);
+        if (s < nstencil) b = (uint32_t)__ldg(g_stencil_code + s);
         r |= b << (8 * t);
     }
     return r;
@@ -154,7 +161,7 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
 #pragma unroll
         for (int t = 0; t < SLOTS; ++t) {  // collisions: keep probing linearly (rare at load factor <= 0.5)
             while (ce[t].key != ckey[t] && ce[t].key != kEmptyKey) {
-                cslot[t] = (cslot[t] + 1) & m.tmask;
+                cslot[t] = next_slot(cslot[t], m.tmask);
                 ce[t] = ld_entry(m.ent + cslot[t]);
             }
             const bool hit = ckey[t] != kEmptyKey && ce[t].key == ckey[t];
@@ -313,6 +320,282 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
     return count;
 }
 
+// ------------------------------------------------------------------ warp-per-query search ("W1")
+// The 8-lanes-per-query body above spends most of its instructions on per-lane sorted top-5 lists that see ~3.6 candidates
+// each (ncu r01: 425 warp instructions per query, 43 % of them the 64-bit insertion, 15 of 32 lanes active).  This body gives
+// one query to a whole warp and keeps every phase lane-parallel:
+//   1. lane s probes stencil cell s (all 27 table loads of the query in flight together, 8 block lines at most);
+//   2. a warp scan of the run lengths gives every candidate of the query a slot = its position in the reference's
+//      enumeration order (stencil order, then in-voxel order - the tie-break rank);
+//   3. lane i takes slot base + i: five shuffle steps find its cell, ONE 16-byte load fetches the point (consecutive lanes
+//      read consecutive points of a run), fp32 distance in the reference's operation order;
+//   4. selection on the 32-bit distance bits: five rounds of warp-min (one REDUX instruction) + ballot, ties go to the
+//      lowest lane = the lowest enumeration rank; winners move to lanes 0..4 and, when the query has more candidates than
+//      fit, ride along as lanes 0..4 of the next chunk (they precede every later candidate in enumeration order).
+// Returns the number found; lane r < count holds winner r: the point (x, y, z, ordinal bits) in `mine` and the bits of its
+// fp32 squared distance in `d2bits`.  Results are bit-identical to knn5_group (same arithmetic, same total order).
+__device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, float qz, int lane, float4& mine, uint32_t& d2bits) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t INF = 0xffffffffu;
+    // ---- 1. probe
+    int start = 0, cnt = 0;
+    {
+        const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
+        if (lane < m.nstencil) {
+            const uint32_t code = __ldg(g_stencil_code + lane);
+            const int cx = kx + (int)(code & 3u) - 1, cy = ky + (int)((code >> 2) & 3u) - 1, cz = kz + (int)((code >> 4) & 3u) - 1;
+            if (cell_in_range(cx, cy, cz)) {
+                const uint64_t key = pack_key(cx, cy, cz);
+                uint32_t slot = hash_key(key) & m.tmask;
+                MapEntry e = ld_entry(m.ent + slot);
+                while (e.key != key && e.key != kEmptyKey) {  // collisions: rare at load factor <= 0.5
+                    slot = next_slot(slot, m.tmask);
+                    e = ld_entry(m.ent + slot);
+                }
+                if (e.key == key) { start = e.start; cnt = e.count; }
+            }
+        }
+    }
+    // ---- 2. slots
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(FULL, incl, 31);
+    mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    d2bits = INF;
+    int found = 0;
+    // ---- 3 + 4. chunks: the first takes 32 candidates, later ones 27 new ones next to the 5 carried winners
+    for (int base = 0; base < total;) {
+        const int first_new = base == 0 ? 0 : 5;
+        const int i = base + lane - first_new;
+        const bool fresh = lane >= first_new && i < total;
+        int pos = 0;
+        const int ii = fresh ? i : 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {  // largest cell with excl <= slot (its run is not empty); all lanes shuffle
+            const int v = __shfl_sync(FULL, excl, pos + step);
+            if (v <= ii) pos += step;
+        }
+        const int addr = __shfl_sync(FULL, start, pos) + (ii - __shfl_sync(FULL, excl, pos));
+        float4 p = mine;              // lanes 0..4 of a later chunk keep the carried winner
+        uint32_t key = lane >= first_new ? INF : d2bits;
+        if (fresh) {
+            p = __ldg(m.pool + addr);
+            // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
+            const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < m.max_range2) key = __float_as_uint(d2);  // d2 >= +0: the unsigned order of the bits is the float order
+        }
+        base += 32 - first_new;
+        // selection: winner r = lowest lane among the smallest remaining keys
+        int src = lane;      // lane r < 5 learns which lane holds winner r
+        uint32_t k = key;
+        found = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t mn = __reduce_min_sync(FULL, k);
+            if (mn == INF) break;  // uniform
+            const int w = __ffs(__ballot_sync(FULL, k == mn)) - 1;
+            if (lane == w) k = INF;
+            if (lane == r) src = w;
+            ++found;
+        }
+        const float4 q4 = make_float4(__shfl_sync(FULL, p.x, src), __shfl_sync(FULL, p.y, src), __shfl_sync(FULL, p.z, src),
+                                      __shfl_sync(FULL, p.w, src));
+        const uint32_t kk = __shfl_sync(FULL, key, src);
+        if (lane < found) { mine = q4; d2bits = kk; }
+        else if (lane < 5) { mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); d2bits = INF; }
+    }
+    return found;
+}
+
+// ------------------------------------------------------------------ 8 lanes per query, balanced through shared memory ("G8P")
+// One wave holds a whole 20k-point scan at 8 lanes per query (a warp per query needs two), and four queries share every
+// instruction a warp issues - as long as the code does not diverge: the first version of this body lost a fifth of its
+// instructions to BSSY / BSYNC / BRA around per-lane loops (ncu r02), so everything below is straight-line and predicated.
+//   probes   lane lg probes cells lg, lg+8, lg+16, lg+24 of the stencil, four table loads in flight;
+//   slots    a 16-bit packed group scan numbers the candidates of the query in the reference's enumeration order
+//            (stencil order, then in-voxel order); a chunk is 32 consecutive slots;
+//   push     every run that overlaps the chunk sets a head bit at its first slot; the OR of the group's head bits makes
+//            "slot -> run" a popcount, and the owner stores ONE word per run (pool address minus slot) at the run's ordinal;
+//   pull     lane lg takes slots 4lg..4lg+3: address = slot + delta[popc(heads below)], four gathers in flight, fp32
+//            distance in the reference's operation order;
+//   select   on the 32-bit distance bits: five rounds of lane-min, group-min (three butterfly shuffles), ballot; the
+//            lowest hit lane wins and knocks out its first matching register - slots are in enumeration order, so ties
+//            go to the lower rank; winners' addresses are staged in shared memory and land on lanes 0..4, which carry
+//            them into the next chunk when the query has more than 32 candidates (a carried winner precedes every later one).
+// Bit-identical to knn5_group / knn5_warp.  smem: kG8pWords 32-bit words per query.
+constexpr int kG8pCap = 32;               // candidate slots per chunk and query
+constexpr int kG8pWords = kG8pCap + 16;   // run deltas + staged winners: 5 addresses (padded to 8), 5 keys (padded to 8)
+static __device__ const uint32_t g_stencil_code4[8] = {  // byte t = g_stencil_code[lg + 8 t]
+    21u | 24u << 8 | 33u << 16 | 8u << 24,    20u | 18u << 8 | 9u << 16 | 2u << 24,     22u | 16u << 8 | 1u << 16 | 0u << 24,
+    25u | 38u << 8 | 42u << 16 | 255u << 24,  17u | 36u << 8 | 40u << 16 | 255u << 24,  5u | 6u << 8 | 34u << 16 | 255u << 24,
+    37u | 4u << 8 | 10u << 16 | 255u << 24,   26u | 41u << 8 | 32u << 16 | 255u << 24};
+
+// Every lane of the warp must call this together (groups without a query pass active = false): all collectives use the
+// full mask - with per-group masks the compiler wraps each of them in WARPSYNC / ENDCOLLECTIVE / BSSY / BSYNC.
+__device__ __forceinline__ int knn5_g8p(const MapView& m, bool active, float qx, float qy, float qz, int lg, uint32_t* sq,
+                                        float4& mine, uint32_t& d2bits) {
+    constexpr int G = 8, SLOTS = 4;
+    constexpr uint32_t INF = 0xffffffffu;
+    constexpr unsigned gmask = 0xffffffffu;
+    const int lane0 = (threadIdx.x & 31) & ~(G - 1);
+    // ---- probes
+    int cstart[SLOTS], ccount[SLOTS];
+    {
+        const uint32_t codes = __ldg(g_stencil_code4 + lg);
+        const int kx = pos2cell(qx, m.inv_res), ky = pos2cell(qy, m.inv_res), kz = pos2cell(qz, m.inv_res);
+        uint32_t klo[SLOTS], khi[SLOTS], cslot[SLOTS];
+        uint4 ce[SLOTS];
+        bool pend = false;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            const uint32_t b = (codes >> (8 * t)) & 0xFFu;
+            const int cx = kx + (int)(b & 3u) - 1, cy = ky + (int)((b >> 2) & 3u) - 1, cz = kz + (int)((b >> 4) & 3u) - 1;
+            const bool ok = active && lg + G * t < m.nstencil && cell_in_range(cx, cy, cz);
+            const uint64_t key = ok ? pack_key(cx, cy, cz) : kEmptyKey;
+            klo[t] = (uint32_t)key;
+            khi[t] = (uint32_t)(key >> 32);
+            cslot[t] = hash_key(key) & m.tmask;
+            ce[t] = make_uint4(INF, INF, 0u, 0u);
+            if (ok) ce[t] = __ldg(reinterpret_cast<const uint4*>(m.ent + cslot[t]));
+        }
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) pend |= (ce[t].x != klo[t] || ce[t].y != khi[t]) && (ce[t].x & ce[t].y) != INF;
+        while (pend) {  // collisions: one shared loop for the four probes of the lane
+            pend = false;
+#pragma unroll
+            for (int t = 0; t < SLOTS; ++t) {
+                if ((ce[t].x != klo[t] || ce[t].y != khi[t]) && (ce[t].x & ce[t].y) != INF) {
+                    cslot[t] = next_slot(cslot[t], m.tmask);
+                    ce[t] = __ldg(reinterpret_cast<const uint4*>(m.ent + cslot[t]));
+                    pend |= (ce[t].x != klo[t] || ce[t].y != khi[t]) && (ce[t].x & ce[t].y) != INF;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            const bool hit = ce[t].x == klo[t] && ce[t].y == khi[t] && (klo[t] & khi[t]) != INF;
+            cstart[t] = (int)ce[t].z;
+            ccount[t] = hit ? (int)ce[t].w : 0;
+        }
+    }
+    // ---- enumeration-order slot numbers: exclusive prefix over (t, lg); two 16-bit counters per word unless a run is huge
+    int excl[SLOTS], total;
+    const bool huge = __any_sync(gmask, max(max(ccount[0], ccount[1]), max(ccount[2], ccount[3])) > 8191);  // warp-uniform
+    if (!huge) {
+        uint32_t w01 = (uint32_t)ccount[0] | ((uint32_t)ccount[1] << 16), w23 = (uint32_t)ccount[2] | ((uint32_t)ccount[3] << 16);
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(gmask, w01, o, G), b = __shfl_up_sync(gmask, w23, o, G);
+            if (lg >= o) { w01 += a; w23 += b; }
+        }
+        const uint32_t t01 = __shfl_sync(gmask, w01, G - 1, G), t23 = __shfl_sync(gmask, w23, G - 1, G);
+        const int T0 = (int)(t01 & 0xFFFFu), T1 = (int)(t01 >> 16), T2 = (int)(t23 & 0xFFFFu), T3 = (int)(t23 >> 16);
+        excl[0] = (int)(w01 & 0xFFFFu) - ccount[0];
+        excl[1] = T0 + (int)(w01 >> 16) - ccount[1];
+        excl[2] = T0 + T1 + (int)(w23 & 0xFFFFu) - ccount[2];
+        excl[3] = T0 + T1 + T2 + (int)(w23 >> 16) - ccount[3];
+        total = T0 + T1 + T2 + T3;
+    } else {
+        total = 0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            int incl = ccount[t];
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const int v = __shfl_up_sync(gmask, incl, o, G);
+                if (lg >= o) incl += v;
+            }
+            excl[t] = total + incl - ccount[t];
+            total += __shfl_sync(gmask, incl, G - 1, G);
+        }
+    }
+    uint32_t* s_delta = sq;                // [kG8pCap] pool address minus slot, one word per run of the chunk
+    uint32_t* s_waddr = sq + kG8pCap;      // [5] winners' pool addresses
+    uint32_t* s_wkey = sq + kG8pCap + 8;   // [5] and distance bits
+    uint32_t kc = INF, ac = 0;             // carried winner of lanes 0..4 (distance bits, pool address)
+    int found = 0;
+    for (int base = 0; __any_sync(gmask, base < total); base += kG8pCap) {  // warp-uniform trip count: a group that is done repeats its (idempotent) selection
+        // push: head bits and one delta per run
+        uint32_t heads = 0;
+        int s0[SLOTS];
+        bool in[SLOTS];
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            s0[t] = min(max(excl[t] - base, 0), 31);  // first slot of the run inside this chunk
+            in[t] = ccount[t] > 0 && excl[t] + ccount[t] > base && excl[t] < base + kG8pCap;
+            heads |= in[t] ? (1u << s0[t]) : 0u;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) heads |= __shfl_xor_sync(gmask, heads, o, G);
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t)
+            if (in[t]) s_delta[__popc(heads & ((1u << s0[t]) - 1u))] = (uint32_t)(cstart[t] + (base + s0[t] - excl[t]) - s0[t]);
+        __syncwarp();
+        // pull: slots 4 lg .. 4 lg + 3
+        const int navail = min(kG8pCap, total - base) - 4 * lg;  // how many of this lane's four slots hold a candidate
+        uint32_t ad[4], k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int slot = 4 * lg + u;
+            ad[u] = (uint32_t)slot + s_delta[max(__popc(heads & (0xFFFFFFFFu >> (31 - slot))) - 1, 0)];
+        }
+        {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < navail) p[u] = __ldg(m.pool + ad[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
+                const float dx = __fsub_rn(p[u].x, qx), dy = __fsub_rn(p[u].y, qy), dz = __fsub_rn(p[u].z, qz);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                k[u] = (u < navail && d2 < m.max_range2) ? __float_as_uint(d2) : INF;  // d2 >= +0: unsigned order of the bits = float order
+            }
+        }
+        int wr[4] = {7, 7, 7, 7}, wrc = 7;  // round in which the register won
+        found = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t lmk = min(min(k[0], k[1]), min(k[2], k[3]));
+            uint32_t gm = min(lmk, kc);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) gm = min(gm, __shfl_xor_sync(gmask, gm, o, G));
+            // equal distances: a carried winner first (lowest lane = best of them), then the lowest slot = lowest enumeration rank
+            const unsigned hc = (__ballot_sync(gmask, kc == gm) >> lane0) & 0xFFu;
+            const unsigned hk = (__ballot_sync(gmask, lmk == gm) >> lane0) & 0xFFu;
+            const bool alive = gm != INF;  // uniform inside the group
+            found += alive ? 1 : 0;
+            const bool me = alive && lg == __ffs(hc ? hc : hk) - 1;
+            const bool tc = me && hc != 0u, tk = me && hc == 0u;
+            const bool h0 = tk && k[0] == gm, h1 = tk && !h0 && k[1] == gm, h2 = tk && !h0 && !h1 && k[2] == gm, h3 = tk && !h0 && !h1 && !h2;
+            if (tc) { kc = INF; wrc = r; }
+            if (h0) { k[0] = INF; wr[0] = r; }
+            if (h1) { k[1] = INF; wr[1] = r; }
+            if (h2) { k[2] = INF; wr[2] = r; }
+            if (h3) { k[3] = INF; wr[3] = r; }
+            if (me) s_wkey[r] = gm;
+        }
+        if (wrc < 5) s_waddr[wrc] = ac;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (wr[u] < 5) s_waddr[wr[u]] = ad[u];
+        __syncwarp();
+        kc = INF;
+        if (lg < found) { kc = s_wkey[lg]; ac = s_waddr[lg]; }
+        __syncwarp();
+    }
+    mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    d2bits = kc;
+    if (lg < found) mine = __ldg(m.pool + ac);
+    return found;
+}
+
 // ------------------------------------------------------------------ host-side object
 struct Map {
     b200_map_params prm;
@@ -356,6 +639,11 @@ struct Map {
     int knn_mode() const {
         static const char* env = getenv("B200_KNN_MODE");
         if (env) return atoi(env);
+        return 7;  // 7 = warp per query (knn5_warp); 8 = balanced 8-lanes-per-query body (knn5_g8p); 0 / 1 / 4 / 5 = the round-1 walks (A/B timing)
+    }
+    int knn_mode_g8() const {  // density-driven choice among the 8-lanes-per-query walks (LOAM front end, A/B timing)
+        static const char* env = getenv("B200_KNN_MODE");
+        if (env && atoi(env) < 7) return atoi(env);
         if (h_ctr.num_voxels == 0) return 0;
         return (h_ctr.live_points > 6ull * h_ctr.num_voxels || h_ctr.max_count > 32u) ? 1 : 0;
     }

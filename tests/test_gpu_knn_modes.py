@@ -31,7 +31,7 @@ def test_all_walk_variants_agree_bit_for_bit():
         assert ref[regime]["oracle_equal"], regime
         assert ref[regime]["rc"] == 0
     assert ref["sparse"]["mean_candidates"] < 40 < 64 < ref["dense"]["mean_candidates"]   # both sides of the flat-list capacity
-    for mode in (0, 1, 4, 5):
+    for mode in (8, 7, 0, 1, 4, 5):
         got = run_mode(mode)
         for regime in ("sparse", "dense"):
             assert got[regime]["oracle_equal"], (mode, regime)

@@ -29,6 +29,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "worker":
         ivox.close()
     print(json.dumps(out))
 else:
-    for mode in (0, 1):   # 0 = lane-owned walk, 1 = cooperative walk (B200_KNN_MODE overrides the density heuristic)
+    for mode in (7, 0, 1, 5):   # 7 = warp per query, 0 = lane-owned walk, 1 = cooperative walk, 5 = flattened walk (8 lanes per query)
         r = subprocess.run([sys.executable, __file__, "worker"], env=dict(os.environ, B200_KNN_MODE=str(mode)), capture_output=True, text=True)
         print("mode", mode, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)
