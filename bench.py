@@ -608,6 +608,7 @@ def sequence_leg(args, local_rank, api, synth, n_scans, n_parity):
                                "sample": f"the first {len(cpu_ms)} scans of the sequence (update on all threads + serial MapIncremental)"}
     if os.environ.get("B200_SEQ_TRACE"):
         out["trace_ms_update_device"] = [round(v, 4) for v in ms_update]
+        out["trace_ms_map_incremental"] = [round(v, 4) for v in ms_incr]
     kf.close()
     ivox.close()
     return out

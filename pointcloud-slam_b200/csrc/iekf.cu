@@ -64,6 +64,7 @@ __global__ void k_iekf_init(Ctl* ctl, const Ctl* hdr, PointState ps, int force_c
             ctl->done = 0;
             ctl->t = 0;
             ctl->ticket = 0;
+            ctl->fault = 0;
             ctl->passes = ctl->knn_passes = ctl->any_valid = ctl->converged = 0;
             for (int i = 0; i < B200_MAX_PASSES; ++i) { ctl->n_eff[i] = 0; ctl->knn[i] = 0; }
         }
@@ -243,8 +244,12 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
         const long long tf1 = clock64();
 #endif
         if (threadIdx.x == 0) {
+            // wait for the workers' tickets, with a watchdog (~0.25 s): worker blocks never wait on this block, so the only way
+            // to starve here is a grid larger than the device can hold or a fault in a worker - report it instead of hanging
             volatile unsigned int* tk = &ctl->ticket;
-            while (*tk < (unsigned)nworkers) __nanosleep(40);
+            unsigned int spins = 0;
+            while (*tk < (unsigned)nworkers && ++spins < (1u << 22)) __nanosleep(40);
+            if (*tk < (unsigned)nworkers) { ctl->fault = 1; ctl->done = 1; }
             ctl->ticket = 0;
 #ifdef B200_STAMPS
             if (pass_f < B200_MAX_PASSES) {
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
             __threadfence();  // acquire: the partials are read with ld.cg after the barrier below
         }
         __syncthreads();
+        if (ctl->fault) return;
         iekf_postsolve(ctl, partials, nworkers, max_iter, limit, ext, single_pass, smu.solve);
         return;
     }
@@ -386,9 +392,47 @@ __global__ void k_map_incremental_flags(const float4* __restrict__ scan, int n, 
     }
     flag[i] = f;
 }
-__global__ void k_flag_eq(const uint8_t* __restrict__ flag, int n, uint8_t v, uint8_t* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = flag[i] == v ? 1 : 0;
+// Stable three-way partition of the scan by flag, one block: points_to_add (flag 1) first, then point_no_need_downsample
+// (flag 2), each in scan order (laser_mapping.cc:579-580) - the order the insertion ordinals follow.  counts = {na, nd, na + nd}.
+// Thread t owns the contiguous slice [t * per, (t + 1) * per) of the scan: two counts per thread, one block scan, then every
+// thread writes its slice behind its offsets - one pass, no host round trip.
+__global__ void __launch_bounds__(1024) k_partition3(const uint8_t* __restrict__ flag, const float4* __restrict__ world, int n,
+                                                     float4* __restrict__ out, int32_t* __restrict__ counts) {
+    __shared__ int s_w1[32], s_w2[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    int c1 = 0, c2 = 0;
+    for (int i = i0; i < i1; ++i) {
+        const int f = flag[i];
+        c1 += f == 1 ? 1 : 0;
+        c2 += f == 2 ? 1 : 0;
+    }
+    int x1 = c1, x2 = c2;  // inclusive scan inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, x1, o), b = __shfl_up_sync(0xffffffffu, x2, o);
+        if (lane >= o) { x1 += a; x2 += b; }
+    }
+    if (lane == 31) { s_w1[warp] = x1; s_w2[warp] = x2; }
+    __syncthreads();
+    if (warp == 0) {  // scan of the 32 warp totals
+        int a = s_w1[lane], b = s_w2[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, a, o), v = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += u; b += v; }
+        }
+        s_w1[lane] = a;
+        s_w2[lane] = b;
+    }
+    __syncthreads();
+    const int na = s_w1[31], nd = s_w2[31];
+    int p1 = x1 - c1 + (warp ? s_w1[warp - 1] : 0), p2 = na + x2 - c2 + (warp ? s_w2[warp - 1] : 0);
+    for (int i = i0; i < i1; ++i) {
+        const int f = flag[i];
+        if (f == 1) out[p1++] = world[i];
+        else if (f == 2) out[p2++] = world[i];
+    }
+    if (tid == 0) { counts[0] = na; counts[1] = nd; counts[2] = na + nd; }
 }
 
 // ------------------------------------------------------------------ host object
@@ -622,6 +666,7 @@ int32_t Iekf::run(const float4* d_pts, int n, const Ctl* d_hdr, double* x, doubl
     last_n = n;
     last_scan = d_pts;
     const Ctl& o = *h_out.p;
+    if (o.fault) B200_FAIL(B200_ERR_CUDA, "IEKF update: the measurement blocks did not report within the watchdog period");
     if (!single_pass) {
         memcpy(x, o.x, sizeof(double) * 26);
         if (P) memcpy(P, o.P, sizeof(double) * NS * NS);
@@ -849,24 +894,16 @@ int32_t b200_iekf_map_incremental(b200_iekf* ekf, const double* x26, int32_t ekf
     CUDA_TRY(cudaMemcpyAsync(k.d_x.p, k.h_x.p, sizeof(double) * 26, cudaMemcpyHostToDevice, k.stream));
     const int nb = (n + 255) / 256;
     k_map_incremental_flags<<<nb, 256, 0, k.stream>>>(k.last_scan, n, k.d_x.p, k.ps, ekf_inited, k.prm.filter_size_map, k.d_world.p, k.d_flag.p);
-    size_t tmp = 0;
-    cub::DeviceSelect::Flagged(nullptr, tmp, k.d_world.p, k.d_flag2.p, k.d_sel_pts.p, k.d_count.p, n, k.stream);
-    CUDA_TRY(k.cub_tmp.reserve(tmp));
-    // points_to_add first, then point_no_need_downsample, each in scan order (:579-580)
-    k_flag_eq<<<nb, 256, 0, k.stream>>>(k.d_flag.p, n, 1, k.d_flag2.p);
-    CUDA_TRY(cub::DeviceSelect::Flagged(k.cub_tmp.p, tmp, k.d_world.p, k.d_flag2.p, k.d_sel_pts.p, k.d_count.p, n, k.stream));
-    CUDA_TRY(cudaMemcpyAsync(k.h_count.p, k.d_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, k.stream));
-    CUDA_TRY(cudaStreamSynchronize(k.stream));
-    const int na = k.h_count.p[0];
-    k_flag_eq<<<nb, 256, 0, k.stream>>>(k.d_flag.p, n, 2, k.d_flag2.p);
-    CUDA_TRY(cub::DeviceSelect::Flagged(k.cub_tmp.p, tmp, k.d_world.p, k.d_flag2.p, k.d_sel_pts.p + na, k.d_count.p, n, k.stream));
-    CUDA_TRY(cudaMemcpyAsync(k.h_count.p, k.d_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, k.stream));
-    CUDA_TRY(cudaStreamSynchronize(k.stream));
-    const int nd = k.h_count.p[0];
-    LAUNCH_COUNT(3);
-    if (n_added) *n_added = na;
-    if (n_no_downsample) *n_no_downsample = nd;
-    return k.map->insert_device(k.d_sel_pts.p, (int64_t)na + nd);
+    // points_to_add first, then point_no_need_downsample, each in scan order (:579-580); the counts stay on the device: the
+    // insert is enqueued right behind on the scan's size with the real count read by its kernels, so the whole
+    // MapIncremental costs one stream synchronisation (the one at the end of the insert)
+    k_partition3<<<1, 1024, 0, k.stream>>>(k.d_flag.p, k.d_world.p, n, k.d_sel_pts.p, k.d_count.p);
+    LAUNCH_COUNT(2);
+    CUDA_TRY(cudaMemcpyAsync(k.h_count.p, k.d_count.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, k.stream));
+    const int32_t rc = k.map->insert_device(k.d_sel_pts.p, (int64_t)n, k.d_count.p + 2, k.h_count.p + 2);
+    if (n_added) *n_added = k.h_count.p[0];
+    if (n_no_downsample) *n_no_downsample = k.h_count.p[1];
+    return rc;
 }
 
 }  // extern "C"

@@ -15,10 +15,15 @@ std::atomic<int64_t> g_kernel_launches{0};
 
 // ------------------------------------------------------------------ insert kernels
 // 1. voxel key of every incoming point (IVox::Pos2Grid, ivox3d.h:284-286)
-__global__ void k_point_keys(const float4* __restrict__ pts, int n, float inv_res, uint64_t* __restrict__ keys,
-                             int32_t* __restrict__ vals, MapCounters* ctr) {
+__global__ void k_point_keys(const float4* __restrict__ pts, int n, const int32_t* __restrict__ d_count, float inv_res,
+                             uint64_t* __restrict__ keys, int32_t* __restrict__ vals, MapCounters* ctr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (d_count && i >= *d_count) {  // past the real end of a batch whose size is only known on the device: skipped like a dropped point
+        keys[i] = kDropKey;
+        vals[i] = i;
+        return;
+    }
     float4 p = pts[i];
     int cx = pos2cell(p.x, inv_res), cy = pos2cell(p.y, inv_res), cz = pos2cell(p.z, inv_res);
     // a non-finite or out-of-range point is dropped, not inserted: its key sorts behind every voxel key and the run of
@@ -123,6 +128,157 @@ __global__ void k_scatter_points(const float4* __restrict__ pts, const int32_t* 
     float4 p = pts[src];
     p.w = __int_as_float(base_ord + src);
     pool[dst0 + (i - run_off[lo])] = p;
+}
+
+// ---- sort-free insert for small batches (a scan's MapIncremental): four short kernels, no radix sort.
+//   k_ins_slots    every point finds or creates its voxel (atomicCAS on the key) and takes an arrival position among the
+//                  batch points of that voxel (bcnt[slot]++, all zero between batches); position 0 = the voxel's leader
+//   k_ins_reserve  leaders make room for old + new points (bump allocation, doubling; old points move along)
+//   k_ins_scatter  every point is written behind the voxel's old points at its arrival position
+//   k_ins_finish   leaders put the new segment into insertion order (sort by ordinal: arrival order is not deterministic,
+//                  the result is), publish the new count and clear bcnt
+// The final table and pool hold exactly what the sorted path produces: voxel-contiguous runs in insertion order.
+__global__ void k_ins_slots(const float4* __restrict__ pts, int n, const int32_t* __restrict__ d_count, float inv_res, int base_ord,
+                            MapEntry* ent, int2* aux, uint32_t tmask, uint32_t capacity_voxels, int32_t* bcnt, MapCounters* ctr,
+                            int32_t* __restrict__ p_slot, int32_t* __restrict__ p_pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p_slot[i] = -1;
+    if (d_count && i >= *d_count) return;
+    const float4 p = pts[i];
+    const int cx = pos2cell(p.x, inv_res), cy = pos2cell(p.y, inv_res), cz = pos2cell(p.z, inv_res);
+    if (!cell_in_range(cx, cy, cz) || !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+        atomicAdd(&ctr->err_range, 1u);
+        return;
+    }
+    const uint64_t key = pack_key(cx, cy, cz);
+    uint32_t slot = hash_key(key) & tmask;
+    while (true) {
+        const uint64_t k = ent[slot].key;
+        if (k == key) break;
+        if (k == kEmptyKey) {
+            const uint64_t old = atomicCAS((unsigned long long*)&ent[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (old == kEmptyKey) {
+                const unsigned nv = atomicAdd(&ctr->num_voxels, 1u) + 1u;
+                if (nv >= capacity_voxels) atomicAdd(&ctr->err_capacity, 1u);
+                break;
+            }
+            if (old == key) break;
+        }
+        slot = next_slot(slot, tmask);
+    }
+    p_slot[i] = (int)slot;
+    p_pos[i] = atomicAdd(&bcnt[slot], 1);
+    atomicMax(&aux[slot].y, base_ord + i);  // LRU recency = ordinal of the last point that touched the voxel
+}
+__global__ void k_ins_reserve(int n, const int32_t* __restrict__ p_slot, const int32_t* __restrict__ p_pos, MapEntry* ent, int2* aux,
+                              const int32_t* __restrict__ bcnt, uint64_t pool_cap, MapCounters* ctr, float4* pool) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = p_slot[i];
+    if (slot < 0 || p_pos[i] != 0) return;
+    const int c = bcnt[slot];
+    const int start = ent[slot].start, count = ent[slot].count, cap = aux[slot].x;
+    const int newcount = count + c;
+    if (newcount > cap) {
+        const int newcap = cap == 0 ? newcount : max(2 * cap, newcount);
+        const unsigned long long st = atomicAdd(&ctr->pool_top, (unsigned long long)newcap);
+        if (st + (unsigned long long)newcap > pool_cap) {
+            atomicAdd(&ctr->err_pool, 1u);
+            return;
+        }
+        for (int j = 0; j < count; ++j) pool[st + j] = pool[start + j];
+        ent[slot].start = (int)st;
+        aux[slot].x = newcap;
+    }
+    atomicAdd(&ctr->live_points, (unsigned long long)c);
+    if ((unsigned)newcount > ctr->max_count) atomicMax(&ctr->max_count, (unsigned)newcount);
+}
+__global__ void k_ins_scatter(const float4* __restrict__ pts, int n, const int32_t* __restrict__ p_slot, const int32_t* __restrict__ p_pos,
+                              const MapEntry* __restrict__ ent, int base_ord, float4* pool) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = p_slot[i];
+    if (slot < 0) return;
+    float4 p = pts[i];
+    p.w = __int_as_float(base_ord + i);
+    pool[ent[slot].start + ent[slot].count + p_pos[i]] = p;
+}
+constexpr int kInsSmallRun = 16;  // new points per voxel up to which the leader orders the segment itself
+__global__ void k_ins_finish(int n, const int32_t* __restrict__ p_slot, const int32_t* __restrict__ p_pos, MapEntry* ent, int32_t* bcnt,
+                             float4* pool, int32_t* __restrict__ big, int32_t* __restrict__ nbig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = p_slot[i];
+    if (slot < 0 || p_pos[i] != 0) return;
+    const int c = bcnt[slot];
+    if (c > kInsSmallRun) {  // a voxel that took many points of this batch: ordered by a whole block (k_ins_finish_big)
+        big[atomicAdd(nbig, 1)] = slot;
+        return;
+    }
+    const int count = ent[slot].count;
+    float4* seg = pool + ent[slot].start + count;
+    for (int a = 1; a < c; ++a) {  // insertion sort by ordinal
+        const float4 v = seg[a];
+        const int ov = __float_as_int(v.w);
+        int b = a - 1;
+        while (b >= 0 && __float_as_int(seg[b].w) > ov) { seg[b + 1] = seg[b]; --b; }
+        seg[b + 1] = v;
+    }
+    ent[slot].count = count + c;
+    bcnt[slot] = 0;
+}
+// One block per listed voxel: the rank of a new point inside its voxel = the number of batch points of the voxel with a
+// smaller batch index; a bitmap over the batch indices (shared memory) turns that into a prefix popcount.
+constexpr int kInsBitmapWords = 65536 / 32;
+__global__ void __launch_bounds__(256) k_ins_finish_big(const int32_t* __restrict__ big, const int32_t* __restrict__ nbig, MapEntry* ent,
+                                                        int32_t* bcnt, float4* pool, float4* __restrict__ scratch, int base_ord) {
+    __shared__ uint32_t bits[kInsBitmapWords];
+    __shared__ int pre[kInsBitmapWords];
+    __shared__ int wsum[8];
+    const int tid = threadIdx.x;
+    for (int v = blockIdx.x; v < *nbig; v += gridDim.x) {
+        const int slot = big[v];
+        const int c = bcnt[slot], count = ent[slot].count;
+        float4* seg = pool + ent[slot].start + count;
+        float4* tmp = scratch + (size_t)blockIdx.x * 65536;  // per block: a block handles one listed voxel at a time
+        for (int w = tid; w < kInsBitmapWords; w += 256) bits[w] = 0u;
+        __syncthreads();
+        for (int e = tid; e < c; e += 256) {
+            const float4 p = seg[e];
+            tmp[e] = p;
+            const int b = __float_as_int(p.w) - base_ord;
+            atomicOr(&bits[b >> 5], 1u << (b & 31));
+        }
+        __syncthreads();
+        {  // exclusive prefix of the word popcounts: 8 consecutive words per thread
+            int loc[8], sum = 0;
+            for (int k = 0; k < 8; ++k) { loc[k] = sum; sum += __popc(bits[tid * 8 + k]); }
+            int incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += u;
+            }
+            if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < (tid >> 5); ++w) woff += wsum[w];
+            const int base = woff + incl - sum;
+            for (int k = 0; k < 8; ++k) pre[tid * 8 + k] = base + loc[k];
+        }
+        __syncthreads();
+        for (int e = tid; e < c; e += 256) {
+            const float4 p = tmp[e];
+            const int b = __float_as_int(p.w) - base_ord;
+            seg[pre[b >> 5] + __popc(bits[b >> 5] & ((1u << (b & 31)) - 1u))] = p;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ent[slot].count = count + c;
+            bcnt[slot] = 0;
+        }
+        __syncthreads();
+    }
 }
 
 // ---- LRU eviction (IVox::AddPoints, ivox3d.h:268-275): a new voxel that brings the map to `capacity_` voxels evicts the
@@ -361,7 +517,7 @@ int32_t Map::clear() {
 void Map::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    cudaFree(d_ent); cudaFree(d_aux); cudaFree(d_pool); cudaFree(d_ctr);
+    cudaFree(d_ent); cudaFree(d_aux); cudaFree(d_pool); cudaFree(d_ctr); cudaFree(d_bcnt);
     in_pts.release(); k_in.release(); k_out.release(); k_uniq.release();
     v_in.release(); v_out.release(); run_cnt.release(); run_off.release(); run_dst.release(); run_reloc.release();
     d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
@@ -393,6 +549,8 @@ int32_t Map::grow_pool(uint64_t min_cap) {
 }
 
 constexpr int32_t kSplitBatch = 100;  // internal: evict_for_batch needs the batch replayed in smaller pieces
+constexpr int64_t kFastInsertMax = 65536;  // batches up to this size take the sort-free insert path
+constexpr int kBigBlocks = 16;             // blocks of its big-voxel ordering pass
 
 int32_t Map::rehash() {
     MapEntry* ne = nullptr;
@@ -489,7 +647,7 @@ int32_t Map::evict_for_batch(int64_t n) {
     return B200_OK;
 }
 
-int32_t Map::insert_device(const float4* d_pts, int64_t n) {
+int32_t Map::insert_device(const float4* d_pts, int64_t n, const int32_t* d_count, const int32_t* h_count) {
     if (n == 0) return B200_OK;
     if (n > (int64_t)0x3fffffff) B200_FAIL(B200_ERR_ARG, "batch too large");
     CUDA_SET_DEVICE(device);
@@ -498,13 +656,46 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
         int32_t rc = grow_pool((uint64_t)n);
         if (rc) return rc;
     }
+    // small batch that cannot reach the voxel capacity: the sort-free path (four kernels instead of ~17)
+    static const bool fast_ok = !(getenv("B200_INSERT_FAST") && atoi(getenv("B200_INSERT_FAST")) == 0);
+    if (fast_ok && n <= kFastInsertMax && h_ctr.num_voxels + tombstones + (uint64_t)n < prm.capacity_voxels) {
+        CUDA_TRY(v_in.reserve(n)); CUDA_TRY(v_out.reserve(n));
+        if (!d_bcnt) {
+            CUDA_TRY(cudaMalloc(&d_bcnt, (size_t)tsize * sizeof(int32_t)));
+            CUDA_TRY(cudaMemsetAsync(d_bcnt, 0, (size_t)tsize * sizeof(int32_t), stream));
+        }
+        const int nbf = (int)((n + 255) / 256);
+        CUDA_TRY(cudaMemsetAsync(&d_ctr->err_range, 0, 3 * sizeof(unsigned int), stream));
+        k_ins_slots<<<nbf, 256, 0, stream>>>(d_pts, (int)n, d_count, inv_res, (int)next_ord, d_ent, d_aux, tsize - 1, (uint32_t)prm.capacity_voxels,
+                                             d_bcnt, d_ctr, v_in.p, v_out.p);
+        k_ins_reserve<<<nbf, 256, 0, stream>>>((int)n, v_in.p, v_out.p, d_ent, d_aux, d_bcnt, pool_cap, d_ctr, d_pool);
+        k_ins_scatter<<<nbf, 256, 0, stream>>>(d_pts, (int)n, v_in.p, v_out.p, d_ent, (int)next_ord, d_pool);
+        int32_t* d_nbig = d_nruns.p + 2;
+        CUDA_TRY(run_dst.reserve(n));
+        CUDA_TRY(k_in.reserve((size_t)kBigBlocks * 65536 * 2));  // scratch of the big-voxel pass: 65536 float4 per block
+        CUDA_TRY(cudaMemsetAsync(d_nbig, 0, sizeof(int32_t), stream));
+        k_ins_finish<<<nbf, 256, 0, stream>>>((int)n, v_in.p, v_out.p, d_ent, d_bcnt, d_pool, run_dst.p, d_nbig);
+        k_ins_finish_big<<<kBigBlocks, 256, 0, stream>>>(run_dst.p, d_nbig, d_ent, d_bcnt, d_pool, (float4*)k_in.p, (int)next_ord);
+        LAUNCH_COUNT(5);
+        CUDA_TRY(cudaMemcpyAsync(h_ctr_pin.p, d_ctr, sizeof(MapCounters), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaGetLastError());
+        h_ctr = *h_ctr_pin.p;
+        next_ord += d_count ? (int64_t)*h_count : n;
+        h_ctr.num_points = (unsigned long long)next_ord;
+        dropped_last = h_ctr.err_range;
+        dropped_total += h_ctr.err_range;
+        if (h_ctr.err_pool) B200_FAIL(B200_ERR_NOMEM, "point pool exhausted");
+        if (h_ctr.err_capacity) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity exceeded (internal: fast insert taken too close to the capacity)");
+        return B200_OK;
+    }
     CUDA_TRY(k_in.reserve(n)); CUDA_TRY(k_out.reserve(n)); CUDA_TRY(k_uniq.reserve(n));
     CUDA_TRY(v_in.reserve(n)); CUDA_TRY(v_out.reserve(n));
     CUDA_TRY(run_cnt.reserve(n)); CUDA_TRY(run_off.reserve(n)); CUDA_TRY(run_dst.reserve(n)); CUDA_TRY(run_reloc.reserve(2 * n));
     const int nb = (int)((n + 255) / 256);
     // the three error counters describe ONE batch (they used to be cumulative: one bad point failed every later insert)
     CUDA_TRY(cudaMemsetAsync(&d_ctr->err_range, 0, 3 * sizeof(unsigned int), stream));
-    k_point_keys<<<nb, 256, 0, stream>>>(d_pts, (int)n, inv_res, k_in.p, v_in.p, d_ctr);
+    k_point_keys<<<nb, 256, 0, stream>>>(d_pts, (int)n, d_count, inv_res, k_in.p, v_in.p, d_ctr);
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, k_in.p, k_out.p, v_in.p, v_out.p, (int)n, 0, 64, stream);
     cub::DeviceRunLengthEncode::Encode(nullptr, t2, k_out.p, k_uniq.p, run_cnt.p, d_nruns.p, (int)n, stream);
@@ -521,6 +712,11 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
         int32_t rc = evict_for_batch(n);
         if (rc == kSplitBatch) {  // nothing has been modified yet: replay the batch as two halves (exact, down to single points)
             if (n == 1) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity too small");
+            if (d_count) {  // the split needs the real size on the host
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                n = *h_count;
+                if (n <= 1) B200_FAIL(B200_ERR_CAPACITY, "voxel capacity too small");
+            }
             rc = insert_device(d_pts, n / 2);
             return rc ? rc : insert_device(d_pts + n / 2, n - n / 2);
         }
@@ -534,7 +730,7 @@ int32_t Map::insert_device(const float4* d_pts, int64_t n) {
     CUDA_TRY(cudaMemcpyAsync(h_ctr_pin.p, d_ctr, sizeof(MapCounters), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     h_ctr = *h_ctr_pin.p;
-    next_ord += n;
+    next_ord += d_count ? (int64_t)*h_count : n;
     h_ctr.num_points = (unsigned long long)next_ord;
     dropped_last = h_ctr.err_range;  // non-fatal: the rest of the batch is in the map
     dropped_total += h_ctr.err_range;

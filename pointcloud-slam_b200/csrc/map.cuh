@@ -391,6 +391,12 @@ __device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, f
             if (d2 < m.max_range2) key = __float_as_uint(d2);  // d2 >= +0: the unsigned order of the bits is the float order
         }
         base += 32 - first_new;
+        // a later chunk only matters if one of its candidates beats the carried fifth-best (an equal distance loses to the
+        // carried winner, which has the lower enumeration rank): dense voxels then cost a gather and a vote per chunk
+        if (first_new) {
+            const uint32_t fifth = __shfl_sync(FULL, d2bits, 4);
+            if (!__any_sync(FULL, lane >= first_new && key < fifth)) continue;
+        }
         // selection: winner r = lowest lane among the smallest remaining keys
         int src = lane;      // lane r < 5 learns which lane holds winner r
         uint32_t k = key;
@@ -609,6 +615,7 @@ struct Map {
     float4* d_pool = nullptr;
     uint64_t pool_cap = 0;
     MapCounters* d_ctr = nullptr;
+    int32_t* d_bcnt = nullptr;  // [tsize] batch points per voxel of the insert in flight (sort-free path), all zero between inserts
     MapCounters h_ctr{};   // mirror after the last insert
     int64_t next_ord = 0;
     uint64_t tombstones = 0, evicted_total = 0;
@@ -656,7 +663,9 @@ struct Map {
     int32_t init(const b200_map_params* p, int dev);
     void destroy();
     int32_t clear();
-    int32_t insert_device(const float4* d_pts, int64_t n);  // points already on the device (x,y,z,*)
+    // points already on the device (x,y,z,*).  d_count / h_count (optional): the batch is the first *d_count (<= n) points,
+    // a count that is still being produced on the stream; h_count is its pinned host copy, valid after the call
+    int32_t insert_device(const float4* d_pts, int64_t n, const int32_t* d_count = nullptr, const int32_t* h_count = nullptr);
     int32_t insert_host(const float* xyz, int64_t n, int64_t stride);
     int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt);
     int32_t grow_pool(uint64_t min_cap);

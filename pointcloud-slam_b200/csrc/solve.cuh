@@ -38,7 +38,8 @@ struct Ctl {
     int done;
     int t;
     unsigned int ticket;  // blocks of the current k_obs launch that have published their partials
-    int pad1[3];
+    int fault;            // the filter block's watchdog fired: worker tickets never arrived
+    int pad1[2];
     // stats
     int passes, knn_passes, any_valid, converged;
     int n_eff[B200_MAX_PASSES], knn[B200_MAX_PASSES];
