@@ -141,7 +141,7 @@ typedef struct {
     double outlier_ratio; /* setOutlierRatio */
     double trans_eps;     /* setTransformationEpsilon */
     int32_t max_iter;     /* setMaximumIterations */
-    int32_t search;       /* 1 DIRECT1, 7 DIRECT7, 27 DIRECT26 (ndt_omp.h NeighborSearchMethod) */
+    int32_t search;       /* 0 KDTREE (radiusSearch over the leaf centroids, ndt_omp_impl.hpp:217-219), 1 DIRECT1, 7 DIRECT7, 27 DIRECT26 (ndt_omp.h NeighborSearchMethod) */
     int32_t min_pts;      /* min_points_per_voxel_ = 6 (voxel_grid_covariance_omp.h:210) */
     double eig_ratio;     /* min_covar_eigvalue_mult_ = 0.01 (voxel_grid_covariance_omp.h:211) */
 } b200_ndt_params;
@@ -172,6 +172,8 @@ int32_t b200_ndt_align(b200_ndt* ndt, const float* guess16, float* final16, b200
 int32_t b200_ndt_derivatives(b200_ndt* ndt, const double* p6, double* score, double* g6, double* H36);
 /* computeHessian (double path, ndt_omp_impl.hpp:499-560) */
 int32_t b200_ndt_hessian(b200_ndt* ndt, const double* p6, double* H36);
+/* getMaxEigen() (ndt_omp.h:209-223): largest eigenvalue of the Hessian align() ended with (b200_ndt_result.hessian) / 100000 */
+int32_t b200_ndt_max_eigen(const double* hessian36, double* max_eigen);
 /* parity primitive: the Newton direction Eigen::JacobiSVD<Matrix<double,6,6>>(H, FullU | FullV).solve(rhs) of
  * computeTransformation (ndt_omp_impl.hpp:112-114) as the device computes it.  *path (may be NULL): 0 = pivoted-elimination
  * shortcut (H comfortably full rank), 1 = literal two-sided Jacobi SVD with Eigen's 6-eps rank threshold; force_svd = 1

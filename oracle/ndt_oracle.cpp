@@ -31,6 +31,8 @@ struct Leaf {
     double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // Leaf() sets cov_ to identity (.h:103-112) and the sums accumulate on top of it
     double icov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     double evals[3] = {0, 0, 0};
+    float centroid[3] = {0, 0, 0};  // leaf.centroid: fp32 running sum in input order, then / (float) nr_points (vgc_impl:241-242, 289)
+    bool in_kdtree = false;         // pushed into voxel_centroids_ (nr_points >= min_points at that moment, vgc_impl:297-326)
 };
 
 struct F3 { float x, y, z; };
@@ -95,6 +97,7 @@ struct Ndt {
             Leaf& lf = leaves[(size_t)idx];
             double pt[3] = {p[0], p[1], p[2]};
             for (int a = 0; a < 3; ++a) lf.mean[a] += pt[a];
+            for (int a = 0; a < 3; ++a) lf.centroid[a] += p[a];
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b) lf.cov[a * 3 + b] += pt[a] * pt[b];
             ++lf.nr_points;
@@ -104,7 +107,9 @@ struct Ndt {
             Leaf& lf = kv.second;
             double pt_sum[3] = {lf.mean[0], lf.mean[1], lf.mean[2]};
             for (int a = 0; a < 3; ++a) lf.mean[a] /= lf.nr_points;
+            for (int a = 0; a < 3; ++a) lf.centroid[a] /= (float)lf.nr_points;
             if (lf.nr_points < prm.min_pts) continue;
+            lf.in_kdtree = true;
             double np = lf.nr_points;
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b)
@@ -149,7 +154,12 @@ struct Ndt {
         static const int d7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
         int ijk[3] = {(int)std::floor(x / leaf), (int)std::floor(y / leaf), (int)std::floor(z / leaf)};
         int cnt = 0;
-        int nrel = prm.search == 1 ? 1 : prm.search == 27 ? 27 : 7;
+        // KDTREE (search == 0): target_cells_.radiusSearch(pt, resolution_) = every kd-tree centroid with fp32 squared distance
+        // < resolution^2 (voxel_grid_covariance_omp.h:477-505; FLANN L2_Simple + RadiusResultSet, third party).  A centroid lies in
+        // its own cell, so the hits are found in the 27-cell block; FLANN returns them by ascending distance - only the order
+        // of the per-point sums depends on that (here: block order).  Leaves dropped after entering the kd-tree (bad
+        // covariance, nr_points = -1) would still be returned by the reference with an unusable covariance; skipped here.
+        int nrel = prm.search == 1 ? 1 : (prm.search == 27 || prm.search == 0) ? 27 : 7;
         for (int ni = 0; ni < nrel; ++ni) {
             int d[3];
             if (nrel == 27) {  // pcl::getAllNeighborCellIndices(): i,j,k in -1..1, x slowest
@@ -162,7 +172,14 @@ struct Ndt {
             int id = (ijk[0] + d[0] - min_b[0]) * divb_mul[0] + (ijk[1] + d[1] - min_b[1]) * divb_mul[1] +
                      (ijk[2] + d[2] - min_b[2]) * divb_mul[2];
             auto it = leaves.find((size_t)id);
-            if (it != leaves.end() && it->second.nr_points >= prm.min_pts) out[cnt++] = &it->second;
+            if (it != leaves.end() && it->second.nr_points >= prm.min_pts) {
+                if (prm.search == 0) {
+                    const float ax = x - it->second.centroid[0], ay = y - it->second.centroid[1], az = z - it->second.centroid[2];
+                    const float d = (ax * ax + ay * ay) + az * az;
+                    if (!(d < (float)((double)leaf * (double)leaf))) continue;
+                }
+                out[cnt++] = &it->second;
+            }
         }
         return cnt;
     }

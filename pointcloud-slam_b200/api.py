@@ -127,6 +127,7 @@ def lib():
         L.b200_ndt_derivatives.argtypes = [vp, vp, vp, vp, vp]
         L.b200_ndt_hessian.argtypes = [vp, vp, vp]
         L.b200_ndt_newton_direction.argtypes = [vp, vp, vp, i32, vp, vp]
+        L.b200_ndt_max_eigen.argtypes = [vp, vp]
         L.b200_ndt_score_batch.argtypes = [vp, vp, i64, vp]
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
@@ -447,7 +448,7 @@ class NormalDistributionsTransform:
         self._dirty = True
 
     def setNeighborhoodSearchMethod(self, m):
-        self._p.search = {"DIRECT1": 1, "DIRECT7": 7, "DIRECT26": 27}.get(m, m)
+        self._p.search = {"KDTREE": 0, "DIRECT1": 1, "DIRECT7": 7, "DIRECT26": 27}.get(m, m)
         self._dirty = True
 
     def setNumThreads(self, n):  # accepted for source compatibility; the device decides
@@ -497,6 +498,13 @@ class NormalDistributionsTransform:
 
     def getFinalNumIteration(self):
         return self.result.iters
+
+    def getMaxEigen(self):
+        """ndt_omp.h:209-223: the largest eigenvalue of the final Hessian / 100000 (localization-lost heuristic)."""
+        H = np.array(self.result.hessian, dtype=np.float64)
+        out = C.c_double(0)
+        _check(lib().b200_ndt_max_eigen(_p(H), C.byref(out)))
+        return out.value
 
     def getTransformationProbability(self):
         return self.result.trans_probability

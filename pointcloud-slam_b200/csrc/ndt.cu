@@ -120,7 +120,8 @@ __global__ void k_ndt_keys(const float4* __restrict__ pts, int n, GridDims gd, u
 __global__ void __launch_bounds__(256) k_ndt_accumulate(const float4* __restrict__ pts, const int32_t* __restrict__ sorted_idx,
                                                         const uint32_t* __restrict__ uniq, const int32_t* __restrict__ run_off,
                                                         const int32_t* __restrict__ run_cnt, const int32_t* __restrict__ nruns,
-                                                        uint32_t sentinel, double* __restrict__ sums /*[nruns][9]*/) {
+                                                        uint32_t sentinel, double* __restrict__ sums /*[nruns][9]*/,
+                                                        float* __restrict__ centroid /*[nruns][3]*/) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int nr = *nruns;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate(const float4* __restrict
         if (uniq[r] == sentinel) continue;  // the non-finite bucket
         const int off = run_off[r], cnt = run_cnt[r];
         double acc = (lane == 3 || lane == 6 || lane == 8) ? 1.0 : 0.0;
+        float facc = 0.0f;  // lanes 9..11: leaf.centroid, the fp32 running sum of x / y / z in input order (vgc_impl:241-242)
         for (int base = 0; base < cnt; base += 32) {
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (base + lane < cnt) p = __ldg(pts + __ldg(sorted_idx + off + base + lane));
@@ -140,9 +142,11 @@ __global__ void __launch_bounds__(256) k_ndt_accumulate(const float4* __restrict
                 const double a = (double)(sa == 0 ? x : sa == 1 ? y : z);
                 const double b = sb == 3 ? 1.0 : (double)(sb == 0 ? x : sb == 1 ? y : z);
                 acc += a * b;
+                facc += lane == 9 ? x : lane == 10 ? y : z;
             }
         }
         if (lane < 9) sums[(size_t)r * 9 + lane] = acc;
+        else if (lane < 12) centroid[(size_t)r * 3 + (lane - 9)] = facc / (float)cnt;  // leaf.centroid /= (float) nr_points (:289)
     }
 }
 
@@ -1162,6 +1166,7 @@ struct Ndt {
     DevBuf<LeafF> d_leafF;
     DevBuf<LeafD> d_leafD;
     DevBuf<double> d_cov, d_sums;
+    DevBuf<float> d_centroid;
     DevBuf<int32_t> d_npts, d_vals_in, d_vals_out, d_run_cnt, d_run_off, d_small;
     DevBuf<uint32_t> d_keys_in, d_keys_out, d_uniq;
     DevBuf<uint8_t> d_valid, cub_tmp;
@@ -1180,6 +1185,11 @@ struct Ndt {
     PinnedBuf<unsigned long long> h_best;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;  // around the score kernel alone (roofline of k_ndt_score_batch)
+    // upload of page-locked caller clouds: copy stream + a ring of chunk events
+    static constexpr int kChunkEvents = 9;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[kChunkEvents] = {};
+    DevBuf<uint8_t> d_raw;
     double d1 = 0, d2 = 0, d3 = 0;
     float last_ms = 0.f;
     int last_launches = 0;
@@ -1187,6 +1197,7 @@ struct Ndt {
     int32_t init(const b200_ndt_params* p, int dev);
     void destroy();
     void gauss();
+    int nst() const { return prm.search == 0 ? 27 : prm.search; }  // stencil cells per point (KDTREE filters the 27-cell block by centroid distance)
     View view() const;
     int32_t upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>& dst);
     int32_t set_target(const float* xyz, int64_t n, int64_t stride);
@@ -1200,7 +1211,7 @@ struct Ndt {
 int32_t Ndt::init(const b200_ndt_params* p, int dev) {
     prm = *p;
     if (!(prm.resolution > 0.f)) B200_FAIL(B200_ERR_ARG, "resolution must be > 0");
-    if (prm.search != 1 && prm.search != 27) prm.search = 7;
+    if (prm.search != 1 && prm.search != 27 && prm.search != 0) prm.search = 7;  // 0 = KDTREE, 1 / 7 / 27 = DIRECT1 / DIRECT7 / DIRECT26
     if (prm.min_pts <= 0) prm.min_pts = 6;
     if (!(prm.eig_ratio > 0)) prm.eig_ratio = 0.01;
     device = dev;
@@ -1226,7 +1237,7 @@ void Ndt::destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     d_tgt.release(); d_src.release(); d_src_raw.release(); d_tgt_sorted.release(); s_keys_in.release(); s_keys_out.release();
-    s_vals_in.release(); s_vals_out.release(); d_cell2run.release(); s_tmp.release(); d_fit.release(); d_cell2leaf.release(); d_nbr7.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release();
+    s_vals_in.release(); s_vals_out.release(); d_cell2run.release(); s_tmp.release(); d_fit.release(); d_cell2leaf.release(); d_nbr7.release(); d_leafF.release(); d_leafD.release(); d_cov.release(); d_sums.release(); d_centroid.release();
     d_npts.release(); d_vals_in.release(); d_vals_out.release(); d_run_cnt.release(); d_run_off.release(); d_small.release();
     d_keys_in.release(); d_keys_out.release(); d_uniq.release(); d_valid.release(); cub_tmp.release();
     h_stage.release(); h_small.release(); d_ctl.release(); d_partials.release(); d_p_in.release(); d_scores.release(); d_poses.release();
@@ -1235,6 +1246,13 @@ void Ndt::destroy() {
     if (ev1) cudaEventDestroy(ev1);
     if (evs0) cudaEventDestroy(evs0);
     if (evs1) cudaEventDestroy(evs1);
+    if (copy_stream) {
+        cudaStreamSynchronize(copy_stream);
+        for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
+    }
+    d_raw.release();
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
 }
@@ -1254,17 +1272,58 @@ View Ndt::view() const {
     v.nbr7 = have_nbr7 ? d_nbr7.p : nullptr;
     for (int k = 0; k < 3; ++k) { v.min_b[k] = gd.min_b[k]; v.max_b[k] = gd.max_b[k]; v.mul[k] = gd.mul[k]; }
     v.leaf = prm.resolution;
-    v.nst = prm.search;
+    v.nst = nst();
+    v.kdtree = prm.search == 0 ? 1 : 0;
+    v.kd_r2 = (float)((double)prm.resolution * (double)prm.resolution);
+    v.centroid = d_centroid.p;
     v.d1 = d1; v.d2 = d2; v.d3 = d3;
     return v;
 }
 
 // strided host cloud -> pinned float4 staging -> device, in chunks: while chunk c crosses PCIe, chunk c+1 is being packed
 // by a few host threads
+// strided xyz records -> float4 (x, y, z, 0), for clouds that crossed PCIe as the caller laid them out
+__global__ void k_ndt_unpack(const uint8_t* __restrict__ raw, int64_t stride, int64_t n, float4* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(raw + i * stride);
+    dst[i] = make_float4(p[0], p[1], p[2], 0.0f);
+}
+
+// Host cloud -> device float4.
+//  * page-locked caller memory (b200_host_alloc, cudaHostRegister) with records of at most 16 bytes: the raw bytes cross PCIe
+//    straight from the caller's buffer in 1M-point chunks on a copy stream and are unpacked on the device, chunk c while
+//    chunk c + 1 is still in flight - no host pass over the cloud at all (a 10M-point xyz cloud is 120 MB = ~2.3 ms of PCIe);
+//  * anything else: packed into the pinned stage by a few host threads, chunk c + 1 while chunk c crosses PCIe.
 int32_t Ndt::upload(const float* xyz, int64_t n, int64_t stride, DevBuf<float4>& dst) {
-    CUDA_TRY(h_stage.reserve((size_t)n));
     CUDA_TRY(dst.reserve((size_t)n));
     const int64_t chunk = 1 << 20;
+    cudaPointerAttributes at{};
+    const bool pinned = stride % 4 == 0 && stride <= 16 && cudaPointerGetAttributes(&at, xyz) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave an error behind on old drivers
+    if (pinned) {
+        const size_t raw_bytes = (size_t)(n - 1) * stride + 12;
+        CUDA_TRY(d_raw.reserve(raw_bytes));
+        if (!copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (auto& e : ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(ev_chunk[0], stream));           // the copy stream starts after whatever used d_raw / dst before
+        CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_chunk[0], 0));
+        int c = 0;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk, ++c) {
+            const int64_t c1 = std::min<int64_t>(n, c0 + chunk);
+            const size_t b0 = (size_t)c0 * stride, b1 = c1 == n ? raw_bytes : (size_t)c1 * stride;
+            CUDA_TRY(cudaMemcpyAsync(d_raw.p + b0, (const uint8_t*)xyz + b0, b1 - b0, cudaMemcpyHostToDevice, copy_stream));
+            cudaEvent_t ev = ev_chunk[1 + c % (kChunkEvents - 1)];
+            CUDA_TRY(cudaEventRecord(ev, copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
+            k_ndt_unpack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, stream>>>(d_raw.p + b0, stride, c1 - c0, dst.p + c0);
+            LAUNCH_COUNT(1);
+        }
+        return B200_OK;
+    }
+    CUDA_TRY(h_stage.reserve((size_t)n));
     const int nt = n > chunk ? 8 : 1;
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t c1 = std::min<int64_t>(n, c0 + chunk);
@@ -1349,13 +1408,14 @@ int32_t Ndt::build_target(int64_t n) {
     CUDA_TRY(cudaStreamSynchronize(stream));
     nruns = h_small.p[0];
     CUDA_TRY(d_sums.reserve((size_t)nruns * 9));
+    CUDA_TRY(d_centroid.reserve((size_t)nruns * 3 + 4));
     CUDA_TRY(d_leafF.reserve(nruns)); CUDA_TRY(d_leafD.reserve(nruns)); CUDA_TRY(d_cov.reserve((size_t)nruns * 9));
     CUDA_TRY(d_npts.reserve(nruns)); CUDA_TRY(d_valid.reserve(nruns));
     int32_t* d_nvalid = d_small.p + 9;
     CUDA_TRY(cudaMemsetAsync(d_nvalid, 0, sizeof(int32_t), stream));
     CUDA_TRY(cudaMemsetAsync(d_cov.p, 0, (size_t)nruns * 9 * sizeof(double), stream));
     const int acc_blocks = std::min((nruns + 7) / 8, sm_count * 8);
-    k_ndt_accumulate<<<std::max(acc_blocks, 1), 256, 0, stream>>>(d_tgt.p, d_vals_out.p, d_uniq.p, d_run_off.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p);
+    k_ndt_accumulate<<<std::max(acc_blocks, 1), 256, 0, stream>>>(d_tgt.p, d_vals_out.p, d_uniq.p, d_run_off.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p, d_centroid.p);
     k_ndt_finalize<<<(nruns + 127) / 128, 128, 0, stream>>>(d_uniq.p, d_run_cnt.p, d_nruns, sentinel, d_sums.p, prm.min_pts, prm.eig_ratio, d_leafF.p,
                                                             d_leafD.p, d_cov.p, d_npts.p, d_valid.p, d_cell2leaf.p, d_nvalid);
     LAUNCH_COUNT(5);
@@ -1402,7 +1462,7 @@ int32_t Ndt::run(int h, const float* d_guesses, const double* d_p, int phase) {
     if (n_src < 1) B200_FAIL(B200_ERR_ARG, "no source set");
     CUDA_TRY(d_ctl.reserve(h));
     CUDA_TRY(h_ctl.reserve(h));
-    const int64_t items = (int64_t)n_src * prm.search;
+    const int64_t items = (int64_t)n_src * nst();
     if (!eval_blocks_per_sm) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_blocks_per_sm, k_ndt_eval<false>, EVAL_THREADS, 0));
         if (eval_blocks_per_sm < 1) eval_blocks_per_sm = 1;
@@ -1470,7 +1530,7 @@ int32_t Ndt::score_batch_device(const float* d_poses16, int64_t h, double* d_out
     const View v = view();
     CUDA_TRY(cudaEventRecord(evs0, stream));
     if (prm.search == 1) k_ndt_score_batch<1><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
-    else if (prm.search == 27) k_ndt_score_batch<27><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
+    else if (nst() == 27) k_ndt_score_batch<27><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
     else k_ndt_score_batch<7><<<grid, SCORE_THREADS, 0, stream>>>(v, d_poses16, d_partials.p);
     CUDA_TRY(cudaEventRecord(evs1, stream));
     k_ndt_score_finish<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_partials.p, nch, h, n_src, d_out);
@@ -1676,6 +1736,48 @@ int32_t b200_ndt_align(b200_ndt* n, const float* guess16, float* final16, b200_n
     fill_result(c, final16, result, k.last_ms);
     if (!c.done) { B200_FAIL(B200_NOT_CONVERGED, "evaluation budget exhausted"); }
     return c.converged ? B200_OK : B200_NOT_CONVERGED;
+}
+
+/* getMaxEigen() (ndt_omp.h:209-223): the largest eigenvalue of hessian_eigen_ (the Hessian the last align() ended with)
+ * divided by 100000 - the quantity the localization node's "lost" heuristic watches (localization.cpp:424-470).  The
+ * reference runs Eigen::EigenSolver (real Schur form) on the 6 x 6 matrix; the accumulated Hessian is symmetric up to rounding, so
+ * its eigenvalues are real and a symmetric Jacobi sweep over (H + H^T) / 2 returns the same values to fp64 rounding.  A
+ * 6 x 6 scalar diagnostic evaluated on the host from the result block - nothing of the hot path runs here. */
+int32_t b200_ndt_max_eigen(const double* hessian36, double* max_eigen) {
+    if (!hessian36 || !max_eigen) B200_FAIL(B200_ERR_ARG, "null argument");
+    double A[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) A[i * 6 + j] = 0.5 * (hessian36[i * 6 + j] + hessian36[j * 6 + i]);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 6; ++i) {
+            diag += A[i * 6 + i] * A[i * 6 + i];
+            for (int j = i + 1; j < 6; ++j) off += A[i * 6 + j] * A[i * 6 + j];
+        }
+        if (off <= 1e-300 || off <= 1e-34 * diag) break;
+        for (int p = 0; p < 5; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                const double apq = A[p * 6 + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 6; ++k) {
+                    const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                    A[k * 6 + p] = c * akp - sn * akq;
+                    A[k * 6 + q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 6; ++k) {
+                    const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                    A[p * 6 + k] = c * apk - sn * aqk;
+                    A[q * 6 + k] = sn * apk + c * aqk;
+                }
+            }
+    }
+    double mx = A[0];
+    for (int i = 1; i < 6; ++i) mx = std::max(mx, A[i * 6 + i]);
+    *max_eigen = mx / 100000.0;
+    return B200_OK;
 }
 
 /* align() for h independent initial guesses in one batch (global relocalization with refinement): results[h], finals h x 16 */

@@ -57,6 +57,9 @@ struct View {
     const float4* src;
     int n_src;
     const int* cell2leaf;
+    const float* centroid;  // [leaves][3] fp32 centroids (leaf.centroid, the cloud the reference's kd-tree indexes); KDTREE mode only
+    int kdtree;        // neighbourhood = radiusSearch(point, resolution) over the centroids (ndt_omp_impl.hpp:217-219)
+    float kd_r2;       // its squared radius as FLANN sees it: (float)(resolution * resolution)
     const int* nbr7;   // [cells][8]: leaf slot (or -1) of the DIRECT7 neighbourhood cells of every grid cell, [7] = how many exist
     const LeafF* leafF;
     const LeafD* leafD;
@@ -92,7 +95,17 @@ __device__ __forceinline__ int nbr_leaf(const View& v, float tx, float ty, float
           v.min_b[2] - iz <= dz && v.max_b[2] - iz >= dz))
         return -1;
     const int id = (ix + dx - v.min_b[0]) * v.mul[0] + (iy + dy - v.min_b[1]) * v.mul[1] + (iz + dz - v.min_b[2]) * v.mul[2];
-    return __ldg(v.cell2leaf + id);
+    int lf = __ldg(v.cell2leaf + id);
+    if (v.kdtree && lf >= 0) {
+        // VoxelGridCovariance::radiusSearch (voxel_grid_covariance_omp.h:477-505): the kd-tree holds the fp32 centroids of the
+        // leaves; FLANN's L2_Simple adds the squared differences in x, y, z order in fp32 and its radius result set keeps
+        // dist < radius^2.  A centroid lies inside its own cell, so every hit is in the 27-cell block around the point.
+        const float cx = __ldg(v.centroid + 3 * lf), cy = __ldg(v.centroid + 3 * lf + 1), cz = __ldg(v.centroid + 3 * lf + 2);
+        const float ax = tx - cx, ay = ty - cy, az = tz - cz;
+        const float d = (ax * ax + ay * ay) + az * az;
+        if (!(d < v.kd_r2)) lf = -1;
+    }
+    return lf;
 }
 
 // pcl::transformPointCloud (PCL 1.7/1.8 scalar form) with a row-major 3x4 float matrix

@@ -14,7 +14,7 @@
 
 namespace b200host {
 
-enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };  // ndt_omp.h:61-66 (KDTREE falls back to DIRECT7)
+enum NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };  // ndt_omp.h:61-66
 
 template <typename CloudT>
 class NormalDistributionsTransform {
@@ -34,7 +34,7 @@ class NormalDistributionsTransform {
     void setMaximumIterations(int n) { prm_.max_iter = n; dirty_ = true; }             // pcl::Registration
     void setNumThreads(int) {}                                                         // :117, the device decides
     void setNeighborhoodSearchMethod(NeighborSearchMethod m) {                         // :189
-        prm_.search = m == DIRECT1 ? 1 : m == DIRECT26 ? 27 : 7;
+        prm_.search = m == KDTREE ? 0 : m == DIRECT1 ? 1 : m == DIRECT26 ? 27 : 7;
         dirty_ = true;
     }
     void setInputTarget(const std::shared_ptr<const CloudT>& cloud) { target_ = cloud; target_dirty_ = true; }   // :125-130
@@ -59,6 +59,11 @@ class NormalDistributionsTransform {
     const float* getFinalTransformation() const { return final_; }                        // column-major 4x4
     double getTransformationProbability() const { return result_.trans_probability; }   // ndt_omp.h:200-204
     int getFinalNumIteration() const { return result_.iters; }                            // :226-230
+    double getMaxEigen() const {                                                          // :209-223 (localization-lost heuristic)
+        double v = 0;
+        check(b200_ndt_max_eigen(result_.hessian, &v), "b200_ndt_max_eigen");
+        return v;
+    }
     const double* getHessian() const { return result_.hessian; }
     /// pcl::Registration::getFitnessScore(max_range): mean squared nearest-neighbour distance after the last align
     double getFitnessScore(double max_range = 1.7976931348623157e308) {

@@ -296,3 +296,34 @@ def test_align_with_no_overlap_stops_like_the_reference(oracle, api, synth, ndt_
     rc1 = g.align(guess)
     assert rc1 == rc0 and (g.result.iters, g.result.evals, g.result.converged) == (r0.iters, r0.evals, r0.converged)
     np.testing.assert_allclose(g.getFinalTransformation(), T0, atol=1e-6)
+
+
+def test_kdtree_neighbourhood_mode(oracle, api, synth, ndt_small):
+    """KDTREE search method (ndt_omp_impl.hpp:216-219): radiusSearch(point, resolution) over the fp32 leaf centroids.  Same
+    neighbourhood sizes as the oracle, derivatives within 1e-6, the hits are a subset of the DIRECT26 block, and align agrees."""
+    o, g = pair(oracle, api, ndt_small, search=0)
+    o26, g26 = pair(oracle, api, ndt_small, search=27)
+    for d in ([0, 0, 0, 0, 0, 0], [0.12, -0.08, 0.03, 0.004, -0.006, 0.01]):
+        p = ndt_small["p_true"] + np.array(d)
+        s0, g0, H0 = o.derivatives(p)
+        s1, g1, H1 = g.computeDerivatives(p)
+        assert abs(s1 - s0) <= H_TOL * abs(s0) and relerr(g1, g0) <= H_TOL and relerr(H1, H0) <= H_TOL
+        n_kd, n_26 = g.nbhd_total(p), g26.nbhd_total(p)
+        assert n_kd == o.nbhd_total(p) and 0 < n_kd < n_26
+    guess = synth.pose_vec_to_matrix(ndt_small["p_true"] + np.array([0.05, -0.04, 0.02, 0.0, 0.0, 0.005])).astype(np.float32)
+    rc0, T0, r0 = o.align(guess)
+    rc1 = g.align(guess)
+    assert rc1 == rc0 and (g.result.iters, g.result.evals) == (r0.iters, r0.evals)
+    assert np.abs(np.array(g.result.p_final) - np.array(r0.p_final)).max() < POSE_TOL
+    poses = synth.hypothesis_grid(ndt_small["p_true"], 3, 3, 2, 1.0)
+    np.testing.assert_allclose(g.calculateScore(poses), o.score_batch(poses), rtol=1e-12)
+
+
+def test_get_max_eigen(oracle, api, synth, ndt_small):
+    """getMaxEigen (ndt_omp.h:209-223): max eigenvalue of the final Hessian / 100000 (LAPACK's general eigen solver as the check)."""
+    o, g = pair(oracle, api, ndt_small)
+    guess = synth.pose_vec_to_matrix(ndt_small["p_true"] + np.array([0.05, -0.04, 0.02, 0.0, 0.0, 0.005])).astype(np.float32)
+    g.align(guess)
+    H = np.array(g.result.hessian).reshape(6, 6)
+    want = np.linalg.eigvals(H).real.max() / 100000.0
+    assert abs(g.getMaxEigen() - want) <= 1e-9 * abs(want)
