@@ -124,6 +124,16 @@ int32_t b200_iekf_obs_model(b200_iekf* ekf, const float* scan_body_xyz, int64_t 
  * nearest_points_ (as insertion ordinals) — any pointer may be NULL. */
 int32_t b200_iekf_point_state(b200_iekf* ekf, int64_t n, float* plane4, float* residual, uint8_t* selected, int32_t* nn_idx5,
                               int32_t* nn_count);
+/* esekf::predict (IKFoM_toolkit/esekfom/esekfom.hpp:269-374) with jueying_lio's process model (use-ikfom.hpp:36-77) over the K IMU
+ * intervals of a scan, as ImuProcess::UndistortPcl drives it (imu_processing.hpp:190-241): steps8 = K x 8 doubles
+ * {dt, offs_t, acc_avr[3], angvel_avr[3]}, Q12 = diagonal of Q_ (gyr, acc, bias gyr, bias acc).  x26 / P23x23 are propagated
+ * in place on the device in one launch; poses22 (K x 22, may be NULL) receives the IMUpose_ entries b200_scan_undistort takes. */
+int32_t b200_iekf_predict(b200_iekf* ekf, const double* steps8, int32_t K, const double* Q12, double* x26, double* P23x23,
+                          double* poses22);
+/* laserCloudWorld of LaserMapping::PublishFrameWorld (laser_mapping.cc:747-773): the last scan moved to the world frame by
+ * PointBodyToWorld (:855-864, fp64) at state x, written as records of stride_bytes (x, y, z first, the rest zero; 48 = the
+ * pcl::PointXYZINormal layout of the /cloud_registered message, see host/pcd_io.hpp pack_pointcloud2_xyzinormal). */
+int32_t b200_iekf_world_scan(b200_iekf* ekf, const double* x26, float* out_xyz, int64_t stride_bytes, int64_t max_points, int64_t* n_out);
 /* LaserMapping::MapIncremental() at state x using the neighbours cached by the last update. */
 int32_t b200_iekf_map_incremental(b200_iekf* ekf, const double* x26, int32_t ekf_inited, int32_t* n_added,
                                   int32_t* n_no_downsample);

@@ -83,6 +83,7 @@ def lib():
         L.orc_state_boxplus.argtypes = [vp, vp]
         L.orc_state_boxminus.argtypes = [vp, vp, vp]
         L.orc_inverse.argtypes = [vp, i32, vp]
+        L.orc_predict.argtypes = [vp, i32, vp, vp, vp, vp]
         L.orc_ndt_create.restype = vp
         L.orc_ndt_create.argtypes = [C.POINTER(NdtParams)]
         L.orc_ndt_destroy.argtypes = [vp]
@@ -267,6 +268,17 @@ def boxminus(x, y):
     d = np.zeros(23)
     lib().orc_state_boxminus(_p(x), _p(y), _p(d))
     return d
+
+
+def predict(steps, Q12, x, P):
+    """esekf::predict over K IMU intervals (steps [K,8] = dt, offs_t, acc_avr, angvel_avr); returns x, P, IMUpose_ [K,22]."""
+    steps = np.ascontiguousarray(steps, dtype=np.float64).reshape(-1, 8)
+    Q12 = np.ascontiguousarray(Q12, dtype=np.float64)
+    x = np.array(x, dtype=np.float64)
+    P = np.array(P, dtype=np.float64)
+    poses = np.zeros((len(steps), 22))
+    lib().orc_predict(_p(steps), len(steps), _p(Q12), _p(x), _p(P), _p(poses))
+    return x, P, poses
 
 
 def inverse(A):

@@ -905,4 +905,92 @@ void orc_state_boxminus(const double* x26, const double* y26, double* dx23) {
 }
 void orc_inverse(const double* A, int32_t n, double* out) { lu_inverse(A, n, out); }
 
+/* esekf::predict (esekfom.hpp:269-374) with the process model of use-ikfom.hpp:36-77 (get_f, df_dx, df_dw), K steps.
+ * steps: K x 8 doubles {dt, offs_t, acc_avr[3], angvel_avr[3]} - what ImuProcess::UndistortPcl hands to kf_state.predict for
+ * every IMU interval (imu_processing.hpp:190-241); Q12 = diagonal of Q_ (cov_gyr, cov_acc, cov_bias_gyr, cov_bias_acc).
+ * poses22 (K x 22, optional) = the IMUpose_ entries pushed after each step: {offs_t, acc_s_last, angvel_last, vel, pos, R}
+ * (imu_processing.hpp:225-236).  Quirks kept: the SO3 / S2 blocks of F_x1 are built from MTK::exp(.., scalar(1 / 2)) whose
+ * scale is the INTEGER quotient 0, i.e. the identity rotation (esekfom.hpp:307,331). */
+void orc_predict(const double* steps, int32_t K, const double* Q12, double* x26, double* P, double* poses22) {
+    State s = load_state(x26);
+    const int n = 23;
+    for (int k = 0; k < K; ++k) {
+        const double dt = steps[k * 8], offs_t = steps[k * 8 + 1];
+        const double* acc = steps + k * 8 + 2;
+        const double* gyr = steps + k * 8 + 5;
+        // get_f
+        double omega[3], am[3], a_in[3], R[9];
+        for (int i = 0; i < 3; ++i) { omega[i] = gyr[i] - s.bg[i]; am[i] = acc[i] - s.ba[i]; }
+        qrot(s.rot, am, a_in);
+        qtoR(s.rot, R);
+        // df_dx (24 x 23, rows by flattened dim) and df_dw (24 x 12): only the non-zero blocks
+        double Mx0[6], zero2[2] = {0, 0};
+        S2_Mx(s.grav, zero2, Mx0);                 // cov.block<3,2>(12, 21)
+        double Hacc[9], RH[9];
+        hat3(am, Hacc);
+        mm3(R, Hacc, RH);                          // cov.block<3,3>(12, 3) = -R * hat(acc - ba)
+        const State before = s;
+        // x_.oplus(f_, dt): vect += scale * vec, SO3 *= exp(vec, scale), S2 rotated by exp(0) (build_manifold.hpp MTK_OPLUS)
+        for (int i = 0; i < 3; ++i) s.pos[i] += dt * before.vel[i];
+        s.rot = qmul(s.rot, so3_exp(omega, dt / 2));
+        { const double z3[3] = {0, 0, 0}; s.offR = qmul(s.offR, so3_exp(z3, dt / 2)); }
+        for (int i = 0; i < 3; ++i) s.vel[i] += dt * (a_in[i] + before.grav[i]);
+        // F_x1 and f_x_final / f_w_final
+        double F[23 * 23] = {0}, G[23 * 12] = {0};
+        for (int i = 0; i < n; ++i) F[i * n + i] = 1.0;
+        double seg[3], A[9];
+        for (int i = 0; i < 3; ++i) seg[i] = -1 * omega[i] * dt;
+        A_matrix(seg, A);
+        // rot rows: f_x_final.block<3,1>(3, i) = A * f_x_.block<3,1>(3, i), f_x_(3..5, 15..17) = -I ; f_w_(3..5, 0..2) = -I
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) { F[(3 + r) * n + 15 + c] += (-A[r * 3 + c]) * dt; G[(3 + r) * 12 + c] = -A[r * 3 + c]; }
+        // pos rows: d pos / d vel = I
+        for (int r = 0; r < 3; ++r) F[r * n + 12 + r] += 1.0 * dt;
+        // vel rows
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) {
+                F[(12 + r) * n + 3 + c] += (-RH[r * 3 + c]) * dt;
+                F[(12 + r) * n + 18 + c] += (-R[r * 3 + c]) * dt;
+                G[(12 + r) * 12 + 3 + c] = -R[r * 3 + c];
+            }
+            for (int c = 0; c < 2; ++c) F[(12 + r) * n + 21 + c] += Mx0[r * 2 + c] * dt;
+        }
+        for (int r = 0; r < 3; ++r) { G[(15 + r) * 12 + 6 + r] = 1.0; G[(18 + r) * 12 + 9 + r] = 1.0; }
+        // S2 block of F_x1: Nx(x_) * I * Mx(x_before, 0); its f_x rows are zero (df_dx has no grav rows)
+        double Nx[6];
+        S2_Nx_yy(s.grav, Nx);
+        for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 2; ++c)
+                F[(21 + r) * n + 21 + c] = Nx[r * 3] * Mx0[c] + Nx[r * 3 + 1] * Mx0[2 + c] + Nx[r * 3 + 2] * Mx0[4 + c];
+        // P_ = F P F^T + (dt G) Q (dt G)^T
+        double T[23 * 23], Pn[23 * 23];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double v = 0;
+                for (int c = 0; c < n; ++c) v += F[i * n + c] * P[c * n + j];
+                T[i * n + j] = v;
+            }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double v = 0;
+                for (int c = 0; c < n; ++c) v += T[i * n + c] * F[j * n + c];
+                double w = 0;
+                for (int c = 0; c < 12; ++c) w += ((dt * G[i * 12 + c]) * Q12[c]) * (dt * G[j * 12 + c]);
+                Pn[i * n + j] = v + w;
+            }
+        std::memcpy(P, Pn, sizeof Pn);
+        if (poses22) {  // imu_processing.hpp:225-236
+            double* o = poses22 + (size_t)k * 22;
+            double am2[3], as[3], R2[9];
+            for (int i = 0; i < 3; ++i) am2[i] = acc[i] - s.ba[i];
+            qrot(s.rot, am2, as);
+            qtoR(s.rot, R2);
+            o[0] = offs_t;
+            for (int i = 0; i < 3; ++i) { o[1 + i] = as[i] + s.grav[i]; o[4 + i] = gyr[i] - s.bg[i]; o[7 + i] = s.vel[i]; o[10 + i] = s.pos[i]; }
+            for (int i = 0; i < 9; ++i) o[13 + i] = R2[i];
+        }
+    }
+    store_state(s, x26);
+}
+
 }  // extern "C"

@@ -89,6 +89,8 @@ int32_t orc_esti_plane(const float* pts_xyz, int32_t n, float thr, float* plane4
 void orc_state_boxplus(double* x26, const double* dx23);
 void orc_state_boxminus(const double* x26, const double* y26, double* dx23);
 void orc_inverse(const double* A, int32_t n, double* out);
+/* esekf::predict over K IMU intervals; steps K x 8 {dt, offs_t, acc_avr[3], angvel_avr[3]}, Q12 = diag(Q_), poses22 K x 22 (optional) */
+void orc_predict(const double* steps, int32_t K, const double* Q12, double* x26, double* P, double* poses22);
 
 /* ---- pclomp NDT -------------------------------------------------------- */
 typedef struct orc_ndt orc_ndt;

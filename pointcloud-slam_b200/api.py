@@ -99,6 +99,8 @@ def lib():
     L.b200_iekf_obs_model.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, vp]
     L.b200_iekf_point_state.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.b200_iekf_map_incremental.argtypes = [vp, vp, i32, vp, vp]
+    L.b200_iekf_predict.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.b200_iekf_world_scan.argtypes = [vp, vp, vp, i64, i64, vp]
     L.b200_iekf_set_profiling.argtypes = [vp, i32]
     L.b200_iekf_set_graph.argtypes = [vp, i32]
     L.b200_iekf_kernel_times.argtypes = [vp, vp, i32]
@@ -383,6 +385,25 @@ class Esekf:
         cnt = np.empty(n, np.int32)
         _check(lib().b200_iekf_point_state(self.h, n, _p(plane), _p(res), _p(sel), _p(nn), _p(cnt)))
         return dict(plane=plane, residual=res, selected=sel, nn_idx=nn, nn_count=cnt)
+
+    def predict(self, steps, Q12):
+        """esekf::predict over the IMU intervals of a scan (steps [K,8] = dt, offs_t, acc_avr, angvel_avr) on the device; updates
+        x / P in place and returns the IMUpose_ list [K,22] for the undistortion pass."""
+        steps = np.ascontiguousarray(steps, dtype=np.float64).reshape(-1, 8)
+        Q12 = np.ascontiguousarray(Q12, dtype=np.float64)
+        poses = np.zeros((len(steps), 22))
+        self.x = np.ascontiguousarray(self.x, dtype=np.float64)
+        self.P = np.ascontiguousarray(self.P, dtype=np.float64)
+        _check(lib().b200_iekf_predict(self.h, _p(steps), len(steps), _p(Q12), _p(self.x), _p(self.P), _p(poses)))
+        return poses
+
+    def world_scan(self, x=None, cols=3):
+        """laserCloudWorld of PublishFrameWorld: the last scan in the world frame at state x ([n, cols] float32, xyz first)."""
+        x = np.ascontiguousarray(self.x if x is None else x, dtype=np.float64)
+        out = np.zeros((self._n, cols), np.float32)
+        n = C.c_int64(0)
+        _check(lib().b200_iekf_world_scan(self.h, _p(x), _p(out), out.strides[0], self._n, C.byref(n)))
+        return out[:n.value]
 
     def MapIncremental(self, x=None, ekf_inited=True):
         x = np.ascontiguousarray(self.x if x is None else x, dtype=np.float64)

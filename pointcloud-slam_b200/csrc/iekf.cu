@@ -352,6 +352,108 @@ __global__ void __launch_bounds__(OBS_THREADS, 1) k_obs(const float4* __restrict
     if (tid == 0) atomicAdd(&ctl->ticket, 1u);
 }
 
+// ------------------------------------------------------------------ forward propagation (esekf::predict, esekfom.hpp:269-374)
+// K IMU intervals in ONE launch of one block: per step the state-dependent pieces of the process model (use-ikfom.hpp:36-77:
+// get_f, df_dx, df_dw) on three lanes, F = F_x1 + f_x_final dt and G = f_w_final assembled in shared memory, then
+// P = F P F^T + (dt G) Q (dt G)^T with one thread per covariance entry.  Quirks of the reference kept: the SO3 / S2 blocks of
+// F_x1 come from MTK::exp(.., scalar(1 / 2)) - an INTEGER quotient, scale 0, the identity rotation (esekfom.hpp:307,331).
+// steps: K x 8 {dt, offs_t, acc_avr[3], angvel_avr[3]} (imu_processing.hpp:190-241); poses22: K x 22 IMUpose_ entries
+// {offs_t, acc_s_last, angvel_last, vel, pos, R} (:225-236) for the backward undistortion pass (b200_scan_undistort).
+struct PredictSmem {
+    double x[26], xb[26];
+    double F[NS * NS], P[NS * NS], T[NS * NS];
+    double G[NS * 12];
+    double R[9], RH[9], A[9], Mx0[6], Nx[6], omega[3], am[3], a_in[3];
+};
+__global__ void __launch_bounds__(544, 1) k_iekf_predict(const double* __restrict__ steps, int K, const double* __restrict__ Q12,
+                                                         double* x_io, double* P_io, double* __restrict__ poses22) {
+    __shared__ PredictSmem s;
+    using namespace mf;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid < 26) s.x[tid] = x_io[tid];
+    for (int i = tid; i < NS * NS; i += nt) s.P[i] = P_io[i];
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const double dt = steps[k * 8], offs_t = steps[k * 8 + 1];
+        const double* acc = steps + k * 8 + 2;
+        const double* gyr = steps + k * 8 + 5;
+        for (int i = tid; i < NS * NS; i += nt) s.F[i] = (i / NS == i % NS) ? 1.0 : 0.0;
+        for (int i = tid; i < NS * 12; i += nt) s.G[i] = 0.0;
+        if (tid < 26) s.xb[tid] = s.x[tid];
+        __syncthreads();
+        if (tid == 0) {  // rotation chain of the state (get_f, df_dx blocks, x_.oplus)
+            for (int i = 0; i < 3; ++i) { s.omega[i] = gyr[i] - s.xb[17 + i]; s.am[i] = acc[i] - s.xb[20 + i]; }
+            const Q rot = ldq(s.xb + 3);
+            qrot(rot, s.am, s.a_in);
+            qtoR(rot, s.R);
+            double H[9];
+            hat(s.am, H);
+            mm3(s.R, H, s.RH);
+            for (int i = 0; i < 3; ++i) s.x[i] = s.xb[i] + dt * s.xb[14 + i];
+            stq(s.x + 3, qmul(rot, so3_exp(s.omega, dt / 2)));
+            const double z3[3] = {0.0, 0.0, 0.0};
+            stq(s.x + 7, qmul(ldq(s.xb + 7), so3_exp(z3, dt / 2)));
+            for (int i = 0; i < 3; ++i) s.x[14 + i] = s.xb[14 + i] + dt * (s.a_in[i] + s.xb[23 + i]);
+        } else if (tid == 32) {  // gravity manifold pieces (the gravity vector itself does not move: its rate is zero)
+            const double zero2[2] = {0.0, 0.0};
+            S2_Mx(s.xb + 23, zero2, s.Mx0);
+            S2_Nx_yy(s.xb + 23, s.Nx);
+        } else if (tid == 64) {
+            double seg[3];
+            for (int i = 0; i < 3; ++i) seg[i] = -1 * (gyr[i] - s.xb[17 + i]) * dt;
+            A_matrix(seg, s.A);
+        }
+        __syncthreads();
+        if (tid < 9) {  // 3 x 3 blocks, one entry per thread
+            const int r = tid / 3, c = tid % 3;
+            s.F[(3 + r) * NS + 15 + c] += (-s.A[r * 3 + c]) * dt;
+            s.G[(3 + r) * 12 + c] = -s.A[r * 3 + c];
+            s.F[(12 + r) * NS + 3 + c] += (-s.RH[r * 3 + c]) * dt;
+            s.F[(12 + r) * NS + 18 + c] += (-s.R[r * 3 + c]) * dt;
+            s.G[(12 + r) * 12 + 3 + c] = -s.R[r * 3 + c];
+            if (c < 2) s.F[(12 + r) * NS + 21 + c] += s.Mx0[r * 2 + c] * dt;
+            if (r == c) {
+                s.F[r * NS + 12 + r] += 1.0 * dt;
+                s.G[(15 + r) * 12 + 6 + r] = 1.0;
+                s.G[(18 + r) * 12 + 9 + r] = 1.0;
+            }
+            if (r < 2 && c < 2) s.F[(21 + r) * NS + 21 + c] = s.Nx[r * 3] * s.Mx0[c] + s.Nx[r * 3 + 1] * s.Mx0[2 + c] + s.Nx[r * 3 + 2] * s.Mx0[4 + c];
+        }
+        __syncthreads();
+        if (tid < NS * NS) {  // T = F P
+            const int i = tid / NS, j = tid % NS;
+            double v = 0.0;
+            for (int c = 0; c < NS; ++c) v += s.F[i * NS + c] * s.P[c * NS + j];
+            s.T[tid] = v;
+        }
+        __syncthreads();
+        double pn = 0.0;
+        if (tid < NS * NS) {  // P = T F^T + (dt G) Q (dt G)^T
+            const int i = tid / NS, j = tid % NS;
+            double v = 0.0, w = 0.0;
+            for (int c = 0; c < NS; ++c) v += s.T[i * NS + c] * s.F[j * NS + c];
+            for (int c = 0; c < 12; ++c) w += ((dt * s.G[i * 12 + c]) * Q12[c]) * (dt * s.G[j * 12 + c]);
+            pn = v + w;
+        }
+        __syncthreads();
+        if (tid < NS * NS) s.P[tid] = pn;
+        if (poses22 && tid == 0) {  // imu_processing.hpp:225-236, from the propagated state
+            double* o = poses22 + (size_t)k * 22;
+            double am2[3], as[3], R2[9];
+            for (int i = 0; i < 3; ++i) am2[i] = acc[i] - s.x[20 + i];
+            const Q rot = ldq(s.x + 3);
+            qrot(rot, am2, as);
+            qtoR(rot, R2);
+            o[0] = offs_t;
+            for (int i = 0; i < 3; ++i) { o[1 + i] = as[i] + s.x[23 + i]; o[4 + i] = gyr[i] - s.x[17 + i]; o[7 + i] = s.x[14 + i]; o[10 + i] = s.x[i]; }
+            for (int i = 0; i < 9; ++i) o[13 + i] = R2[i];
+        }
+        __syncthreads();
+    }
+    if (tid < 26) x_io[tid] = s.x[tid];
+    for (int i = tid; i < NS * NS; i += nt) P_io[i] = s.P[i];
+}
+
 // ------------------------------------------------------------------ MapIncremental (laser_mapping.cc:525-583)
 // flag: 0 = drop, 1 = points_to_add, 2 = point_no_need_downsample
 __global__ void k_map_incremental_flags(const float4* __restrict__ scan, int n, const double* __restrict__ x, PointState ps, int ekf_inited,
@@ -392,6 +494,24 @@ __global__ void k_map_incremental_flags(const float4* __restrict__ scan, int n, 
     }
     flag[i] = f;
 }
+// PointBodyToWorld (laser_mapping.cc:855-864) of the whole scan: fp64 quaternion arithmetic, narrowed on store - the cloud
+// PublishFrameWorld sends as /cloud_registered (:747-773).  Records are written at `stride` bytes (x, y, z first; 48 = the
+// PointXYZINormal layout of the message, the other bytes are left as they are).
+__global__ void k_body_to_world(const float4* __restrict__ scan, int n, const double* __restrict__ x, uint8_t* __restrict__ out, int64_t stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using namespace mf;
+    const float4 pb = scan[i];
+    double pbd[3] = {pb.x, pb.y, pb.z}, t1[3], t2[3];
+    qrot(ldq(x + 7), pbd, t1);
+    for (int k = 0; k < 3; ++k) t1[k] = t1[k] + x[11 + k];
+    qrot(ldq(x + 3), t1, t2);
+    float* o = reinterpret_cast<float*>(out + (size_t)i * stride);
+    o[0] = (float)(t2[0] + x[0]);
+    o[1] = (float)(t2[1] + x[1]);
+    o[2] = (float)(t2[2] + x[2]);
+}
+
 // Stable three-way partition of the scan by flag, one block: points_to_add (flag 1) first, then point_no_need_downsample
 // (flag 2), each in scan order (laser_mapping.cc:579-580) - the order the insertion ordinals follow.  counts = {na, nd, na + nd}.
 // Thread t owns the contiguous slice [t * per, (t + 1) * per) of the scan: two counts per thread, one block scan, then every
@@ -480,7 +600,8 @@ struct Iekf {
     DevBuf<int32_t> d_count;
     DevBuf<double> d_x;
     PinnedBuf<int32_t> h_count;
-    PinnedBuf<double> h_x;
+    PinnedBuf<double> h_x, h_pred;
+    DevBuf<double> d_pred;
 
     int32_t init(const b200_iekf_params* p, Map* m);
     void destroy();
@@ -546,7 +667,7 @@ void Iekf::destroy() {
     cudaFree(ps.plane); cudaFree(ps.resid); cudaFree(ps.sel); cudaFree(ps.nn_cnt); cudaFree(ps.nn);
     d_scan.release(); d_raw.release(); d_nb.release(); d_nbc.release(); h_stage.release(); h_out.release();
     d_world.release(); d_sel_pts.release(); d_flag.release(); d_flag2.release(); cub_tmp.release(); d_count.release(); d_x.release();
-    h_count.release(); h_x.release();
+    h_count.release(); h_x.release(); h_pred.release(); d_pred.release();
     if (gexec) cudaGraphExecDestroy(gexec);
     for (auto& e : evk) if (e) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
@@ -879,6 +1000,56 @@ int32_t b200_iekf_point_state(b200_iekf* ekf, int64_t n, float* plane4, float* r
                 }
         }
     }
+    return B200_OK;
+}
+
+/* esekf::predict over K IMU intervals on the device (see k_iekf_predict) */
+int32_t b200_iekf_predict(b200_iekf* ekf, const double* steps8, int32_t K, const double* Q12, double* x26, double* P, double* poses22) {
+    if (!ekf || !steps8 || !Q12 || !x26 || !P || K < 1 || K > 4096) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Iekf& k = ekf->k;
+    CUDA_SET_DEVICE(k.map->device);
+    const size_t n_in = (size_t)K * 8 + 12 + 26 + NS * NS, n_out = 26 + NS * NS + (size_t)K * 22;
+    CUDA_TRY(k.h_pred.reserve(n_in + n_out));
+    CUDA_TRY(k.d_pred.reserve(n_in + (size_t)K * 22));
+    double* h = k.h_pred.p;
+    memcpy(h, steps8, sizeof(double) * K * 8);
+    memcpy(h + (size_t)K * 8, Q12, sizeof(double) * 12);
+    memcpy(h + (size_t)K * 8 + 12, x26, sizeof(double) * 26);
+    memcpy(h + (size_t)K * 8 + 38, P, sizeof(double) * NS * NS);
+    double* d = k.d_pred.p;
+    CUDA_TRY(cudaMemcpyAsync(d, h, n_in * sizeof(double), cudaMemcpyHostToDevice, k.stream));
+    double *d_steps = d, *d_Q = d + (size_t)K * 8, *d_x = d_Q + 12, *d_P = d_x + 26, *d_poses = d + n_in;
+    k_iekf_predict<<<1, 544, 0, k.stream>>>(d_steps, K, d_Q, d_x, d_P, d_poses);
+    LAUNCH_COUNT(1);
+    double* ho = h + n_in;
+    CUDA_TRY(cudaMemcpyAsync(ho, d_x, (26 + NS * NS) * sizeof(double), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaMemcpyAsync(ho + 26 + NS * NS, d_poses, (size_t)K * 22 * sizeof(double), cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    CUDA_TRY(cudaGetLastError());
+    memcpy(x26, ho, sizeof(double) * 26);
+    memcpy(P, ho + 26, sizeof(double) * NS * NS);
+    if (poses22) memcpy(poses22, ho + 26 + NS * NS, sizeof(double) * K * 22);
+    return B200_OK;
+}
+
+/* the last scan in the world frame at state x (laserCloudWorld of PublishFrameWorld, laser_mapping.cc:747-773) */
+int32_t b200_iekf_world_scan(b200_iekf* ekf, const double* x26, float* out_xyz, int64_t stride_bytes, int64_t max_points, int64_t* n_out) {
+    if (!ekf || !x26 || !out_xyz || stride_bytes < 12 || stride_bytes % 4) B200_FAIL(B200_ERR_ARG, "bad argument");
+    Iekf& k = ekf->k;
+    const int n = k.last_n;
+    if (n < 1 || !k.last_scan) B200_FAIL(B200_ERR_ARG, "no scan has been processed");
+    if (max_points < n) B200_FAIL(B200_ERR_ARG, "output buffer too small");
+    CUDA_SET_DEVICE(k.map->device);
+    CUDA_TRY(k.d_raw.reserve((size_t)n * stride_bytes));
+    memcpy(k.h_x.p, x26, sizeof(double) * 26);
+    CUDA_TRY(cudaMemcpyAsync(k.d_x.p, k.h_x.p, sizeof(double) * 26, cudaMemcpyHostToDevice, k.stream));
+    CUDA_TRY(cudaMemsetAsync(k.d_raw.p, 0, (size_t)n * stride_bytes, k.stream));
+    k_body_to_world<<<(n + 255) / 256, 256, 0, k.stream>>>(k.last_scan, n, k.d_x.p, k.d_raw.p, stride_bytes);
+    LAUNCH_COUNT(1);
+    CUDA_TRY(cudaMemcpyAsync(out_xyz, k.d_raw.p, (size_t)n * stride_bytes, cudaMemcpyDeviceToHost, k.stream));
+    CUDA_TRY(cudaStreamSynchronize(k.stream));
+    CUDA_TRY(cudaGetLastError());
+    if (n_out) *n_out = n;
     return B200_OK;
 }
 

@@ -92,6 +92,22 @@ class Esekf {
         return rc == B200_OK;
     }
 
+    /// One IMU interval as ImuProcess::UndistortPcl hands it to kf_state.predict (imu_processing.hpp:190-241)
+    struct ImuStep {
+        double dt, offs_t, acc_avr[3], angvel_avr[3];
+    };
+    /// esekf::predict (esekfom.hpp:269-374) over all IMU intervals of a scan in one device launch.  Q12 = diagonal of Q_
+    /// (cov_gyr, cov_acc, cov_bias_gyr, cov_bias_acc).  imu_poses (optional) receives IMUpose_ as 22 doubles per step
+    /// {offset_time, acc, gyr, vel, pos, rot row-major} - the input of b200_scan_undistort.
+    void predict(const std::vector<ImuStep>& steps, const double Q12[12], std::vector<double>* imu_poses = nullptr) {
+        static_assert(sizeof(ImuStep) == 8 * sizeof(double), "ImuStep must be 8 packed doubles");
+        if (steps.empty()) return;
+        if (imu_poses) imu_poses->resize(steps.size() * 22);
+        check(b200_iekf_predict(kf_, reinterpret_cast<const double*>(steps.data()), (int32_t)steps.size(), Q12, x_.data(), P_.data(),
+                                imu_poses ? imu_poses->data() : nullptr),
+              "b200_iekf_predict");
+    }
+
     /// LaserMapping::MapIncremental (laser_mapping.cc:525-583) with the neighbours cached by the last update
     void MapIncremental(bool flg_EKF_inited, int* n_added = nullptr, int* n_no_downsample = nullptr) {
         int32_t a = 0, b = 0;

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
+#include <iomanip>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -138,6 +139,118 @@ inline std::vector<std::string> list_frames(const std::string& dir) {
     std::vector<std::string> out;
     for (auto& p : v) out.push_back(p.second);
     return out;
+}
+
+// ------------------------------------------------------------------ tiled prior maps: the area list
+// jueying_slam/include/dynamic_map.h:14-106: one CSV line per map tile, `path,x_min,y_min,z_min,x_max,y_max,z_max`
+// (read_csv splits on ',' only; write_arealist formats with std::to_string = "%f"), is_in_area (:113-116) selects the
+// tiles whose xy box, grown by a margin, contains the pose; create_pcd (:127-156) concatenates them in list order.
+struct Area {
+    std::string path;
+    double x_min = 0, y_min = 0, z_min = 0, x_max = 0, y_max = 0, z_max = 0;
+};
+using AreaList = std::vector<Area>;
+
+inline AreaList read_arealist(const std::string& path) {
+    std::ifstream ifs(path.c_str());
+    if (!ifs) throw std::runtime_error("cannot open " + path);
+    AreaList ret;
+    std::string line;
+    while (std::getline(ifs, line)) {
+        std::istringstream iss(line);
+        std::string col;
+        std::vector<std::string> cols;
+        while (std::getline(iss, col, ',')) cols.push_back(col);
+        if (cols.size() < 7) throw std::runtime_error("arealist line with fewer than 7 columns: " + line);
+        Area a;
+        a.path = cols[0];
+        a.x_min = std::stod(cols[1]); a.y_min = std::stod(cols[2]); a.z_min = std::stod(cols[3]);
+        a.x_max = std::stod(cols[4]); a.y_max = std::stod(cols[5]); a.z_max = std::stod(cols[6]);
+        ret.push_back(a);
+    }
+    return ret;
+}
+inline void write_arealist(const std::string& path, const AreaList& areas) {
+    std::ofstream ofs(path.c_str());
+    if (!ofs) throw std::runtime_error("cannot write " + path);
+    for (const Area& a : areas)
+        ofs << a.path << "," << std::to_string(a.x_min) << "," << std::to_string(a.y_min) << "," << std::to_string(a.z_min) << ","
+            << std::to_string(a.x_max) << "," << std::to_string(a.y_max) << "," << std::to_string(a.z_max) << std::endl;
+}
+inline bool is_in_area(double x, double y, const Area& a, double m) {
+    return (a.x_min - m) <= x && x <= (a.x_max + m) && (a.y_min - m) <= y && y <= (a.y_max + m);
+}
+/// the tiles create_pcd(p_x, p_y, areas, global_path, margin) would load, in list order
+inline std::vector<std::string> areas_near(double x, double y, const AreaList& areas, const std::string& global_path, double margin) {
+    std::vector<std::string> out;
+    for (const Area& a : areas)
+        if (is_in_area(x, y, a, margin)) out.push_back(global_path + a.path);
+    return out;
+}
+/// create_pcd: the concatenation of those tiles (binary / ascii .pcd), ready for setInputTarget
+inline std::vector<PointXYZI> create_pcd(double x, double y, const AreaList& areas, const std::string& global_path, double margin) {
+    std::vector<PointXYZI> all;
+    for (const std::string& f : areas_near(x, y, areas, global_path, margin)) {
+        const std::vector<PointXYZI> part = load_pcd(f);
+        all.insert(all.end(), part.begin(), part.end());
+    }
+    return all;
+}
+
+// ------------------------------------------------------------------ trajectory file
+// LaserMapping::Savetrajectory (jueying_lio/src/laser_mapping.cc:825-841): TUM text, header line, stamp with 6 decimals,
+// the other seven numbers with 15.
+struct StampedPose {
+    double stamp, x, y, z, qx, qy, qz, qw;
+};
+inline void save_trajectory_tum(const std::string& path, const std::vector<StampedPose>& poses) {
+    std::ofstream ofs(path, std::ios::out);
+    if (!ofs.is_open()) throw std::runtime_error("Failed to open traj_file: " + path);
+    ofs << "#timestamp x y z q_x q_y q_z q_w" << std::endl;
+    for (const StampedPose& p : poses) {
+        ofs.setf(std::ios::fixed);
+        ofs.precision(6);
+        ofs << p.stamp << " ";
+        ofs.precision(15);
+        ofs << p.x << " " << p.y << " " << p.z << " " << p.qx << " " << p.qy << " " << p.qz << " " << p.qw << std::endl;
+    }
+}
+
+// ------------------------------------------------------------------ /cloud_registered: sensor_msgs/PointCloud2 payload
+// PublishFrameWorld (laser_mapping.cc:747-773) sends pcl::toROSMsg(PointCloud<PointXYZINormal>): height 1, width n,
+// point_step 48, little endian, the eight FLOAT32 fields at the offsets of pcl::PointXYZINormal.  The blob below is that
+// message body without the ROS header (stamp = lidar_end_time, frame_id "camera_init" are set by the node).
+struct PointField {
+    const char* name;
+    uint32_t offset;
+    uint8_t datatype;  // 7 = sensor_msgs::PointField::FLOAT32
+    uint32_t count;
+};
+struct PointCloud2Blob {
+    uint32_t height = 1, width = 0, point_step = 48, row_step = 0;
+    bool is_bigendian = false, is_dense = true;
+    std::vector<PointField> fields;
+    std::vector<uint8_t> data;
+};
+inline const std::vector<PointField>& xyzinormal_fields() {
+    static const std::vector<PointField> f = {{"x", 0, 7, 1},         {"y", 4, 7, 1},          {"z", 8, 7, 1},          {"intensity", 32, 7, 1},
+                                               {"normal_x", 16, 7, 1}, {"normal_y", 20, 7, 1}, {"normal_z", 24, 7, 1}, {"curvature", 36, 7, 1}};
+    return f;
+}
+/// xyz (+ optional per-point intensity) at `stride` bytes -> the PointCloud2 body of a PointXYZINormal cloud
+inline PointCloud2Blob pack_pointcloud2_xyzinormal(const float* xyz, size_t n, size_t stride_bytes, const float* intensity = nullptr) {
+    PointCloud2Blob b;
+    b.width = (uint32_t)n;
+    b.row_step = b.point_step * b.width;
+    b.fields = xyzinormal_fields();
+    b.data.assign(n * 48, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xyz) + i * stride_bytes);
+        float rec[12] = {p[0], p[1], p[2], 1.0f, 0, 0, 0, 0, intensity ? intensity[i] : 0.0f, 0, 0, 0};  // data[3] = 1 (PCL_ADD_POINT4D)
+        std::memcpy(&b.data[i * 48], rec, 48);
+        if (!(p[0] == p[0] && p[1] == p[1] && p[2] == p[2])) b.is_dense = false;
+    }
+    return b;
 }
 
 }  // namespace b200host

@@ -313,3 +313,41 @@ def test_lru_eviction_matches_reference_semantics(oracle, api, synth, small_cfg,
         np.testing.assert_array_equal(c1, c0)
         np.testing.assert_array_equal(i1, i0)
     assert o.num_voxels == capacity - 1   # the map sits at the capacity: evictions did happen
+
+
+def test_predict_parity(oracle, api, synth, small_cfg):
+    """esekf::predict over the IMU intervals of a scan, on the device in one launch, against the oracle: state, covariance and
+    the IMUpose_ list the undistortion pass consumes."""
+    from test_oracle_lio import imu_steps, Q12
+    x0 = synth.make_state([1.0, -2.0, 0.5], [0.02, -0.01, 0.7])
+    x0[14:17] = [0.8, -0.3, 0.05]
+    x0[17:20] = [0.001, -0.002, 0.0005]
+    x0[20:23] = [0.01, 0.02, -0.01]
+    P0 = synth.init_cov()
+    g = api.IVox(resolution=0.5, nearby=18)
+    kf = api.Esekf(g)
+    for K in (1, 20, 57):
+        steps = imu_steps(K, seed=K)
+        x_o, P_o, poses_o = oracle.predict(steps, Q12, x0, P0)
+        kf.change_x(x0)
+        kf.change_P(P0)
+        poses_g = kf.predict(steps, Q12)
+        assert np.abs(oracle.boxminus(kf.get_x(), x_o)).max() < 1e-12
+        assert relerr(kf.get_P(), P_o) < 1e-12
+        assert relerr(poses_g, poses_o) < 1e-12
+
+
+def test_world_scan_is_point_body_to_world(oracle, api, synth, small_cfg):
+    """/cloud_registered: the scan moved by PointBodyToWorld (laser_mapping.cc:855-864, fp64 quaternion arithmetic narrowed on
+    store) at the posterior - against the same transform in numpy fp64."""
+    o, g, kf = pair(oracle, api, "horizon", small_cfg["map"])
+    kf.change_x(small_cfg["x_prop"])
+    kf.change_P(small_cfg["P"])
+    kf.update_iterated_dyn_share_modified(small_cfg["scan"])
+    x = kf.get_x()
+    w = kf.world_scan(cols=12)            # 48-byte PointXYZINormal records
+    assert w.shape == (len(small_cfg["scan"]), 12) and np.all(w[:, 3:] == 0)
+    R, Ro = synth.quat_to_R(x[3:7]), synth.quat_to_R(x[7:11])
+    want = (R @ (Ro @ small_cfg["scan"].astype(np.float64).T + x[11:14, None]) + x[0:3, None]).T
+    assert np.abs(w[:, :3] - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+    assert (w[:, :3] == want.astype(np.float32)).mean() > 0.98       # identical after narrowing for all but rounding-boundary cases

@@ -207,3 +207,61 @@ def test_update_bookkeeping(oracle, small_cfg):
     assert rc == 1 and st2.passes == 4
     np.testing.assert_array_equal(x2, small_cfg["x_prop"])
     np.testing.assert_array_equal(P2, small_cfg["P"])
+
+
+def imu_steps(K=20, seed=4):
+    """K IMU intervals the way UndistortPcl feeds predict (imu_processing.hpp:190-241): dt ~ 5 ms, gravity-compensated motion."""
+    rng = np.random.default_rng(seed)
+    steps = np.zeros((K, 8))
+    steps[:, 0] = rng.uniform(0.004, 0.006, K)
+    steps[:, 1] = np.cumsum(steps[:, 0])
+    steps[:, 2:5] = np.array([0.3, -0.2, 9.81]) + rng.normal(0, 0.2, (K, 3))
+    steps[:, 5:8] = np.array([0.05, -0.1, 0.4]) + rng.normal(0, 0.05, (K, 3))
+    return steps
+
+
+Q12 = np.array([0.1] * 3 + [0.1] * 3 + [1e-4] * 3 + [1e-4] * 3)   # gyr_cov, acc_cov, b_gyr_cov, b_acc_cov (config/livox.yaml:13-16)
+
+
+def test_predict_restatement(oracle, synth):
+    """esekf::predict (esekfom.hpp:269-374): the mean follows the strap-down kinematics of get_f, the covariance stays symmetric
+    positive definite and grows by the process noise, and one step equals the closed form F P F^T + G Q G^T built here in numpy."""
+    x0 = synth.make_state([1.0, -2.0, 0.5], [0.02, -0.01, 0.7])
+    x0[14:17] = [0.8, -0.3, 0.05]            # vel
+    x0[17:20] = [0.001, -0.002, 0.0005]      # bg
+    x0[20:23] = [0.01, 0.02, -0.01]          # ba
+    P0 = synth.init_cov()
+    steps = imu_steps(1)
+    x1, P1, poses = oracle.predict(steps, Q12, x0, P0)
+    dt, acc, gyr = steps[0, 0], steps[0, 2:5], steps[0, 5:8]
+    R = synth.quat_to_R(x0[3:7])
+    a_in = R @ (acc - x0[20:23]) + x0[23:26]
+    np.testing.assert_allclose(x1[0:3], x0[0:3] + dt * x0[14:17], atol=1e-14)
+    np.testing.assert_allclose(x1[14:17], x0[14:17] + dt * a_in, atol=1e-13)
+    dq = synth.quat_from_rotvec((gyr - x0[17:20]) * dt)
+    np.testing.assert_allclose(x1[3:7], synth.quat_mul(x0[3:7], dq), atol=1e-14)
+    for sl in (slice(7, 14), slice(17, 26)):                      # extrinsics, biases, gravity do not move
+        np.testing.assert_array_equal(x1[sl], x0[sl])
+    np.testing.assert_allclose(P1, P1.T, atol=1e-15)
+    assert np.linalg.eigvalsh(0.5 * (P1 + P1.T)).min() > 0
+    # the velocity rows of F against central differences of the mean propagation (tangent perturbations of the prior)
+    def vel_after(dx):
+        xp = oracle.boxplus(x0, dx)
+        return oracle.predict(steps, Q12, xp, P0)[0][14:17]
+    for col in (3, 4, 5, 12, 13, 18, 19, 20):                     # d vel' / d (rot, vel, ba)
+        e = np.zeros(23)
+        e[col] = 1e-6
+        fd = (vel_after(e) - vel_after(-e)) / 2e-6
+        F_col = (np.eye(3)[:, col - 12] if 12 <= col < 15 else 0) + 0
+        if 3 <= col < 6:
+            am = acc - x0[20:23]
+            hat = np.array([[0, -am[2], am[1]], [am[2], 0, -am[0]], [-am[1], am[0], 0]])
+            F_col = (-R @ hat * dt)[:, col - 3]
+        elif 18 <= col < 21:
+            F_col = (-R * dt)[:, col - 18]
+        np.testing.assert_allclose(fd, F_col, atol=2e-8)
+    # IMUpose_ entry: offset time, world acceleration incl. gravity, bias-free angular rate, velocity, position, rotation
+    assert poses.shape == (1, 22) and poses[0, 0] == steps[0, 1]
+    np.testing.assert_allclose(poses[0, 7:10], x1[14:17])
+    np.testing.assert_allclose(poses[0, 10:13], x1[0:3])
+    np.testing.assert_allclose(poses[0, 13:22].reshape(3, 3), synth.quat_to_R(x1[3:7]), atol=1e-14)
