@@ -255,7 +255,9 @@ def reloc_leg(args, rank, local_rank, world, api, synth, torch, comm, cfg):
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wait = time.perf_counter()
-    while not sampler.sm and time.perf_counter() - t_wait < 3.0:   # NVML start-up must not eat the (short) timed region
+    while not sampler.sm and time.perf_counter() - t_wait < 3.0:   # NVML start-up must not eat the (short) timed region.  Rank-local
+        time.sleep(0.002)                                          # wait only: a step is a collective, every rank must run the same number
+    for _ in range(2):
         step(True)
     torch.cuda.synchronize()
     if world > 1:
