@@ -11,7 +11,8 @@
 //              leaf sums x, y, z, intensity in fp32 in input order and divides by the count (the arithmetic of
 //              pcl::CentroidPoint) -> centroids in ascending leaf-index order.  The result can stay on the device and feed
 //              b200_iekf_update_device directly.
-// map builder  a voxel hash table in HBM {key, sum x/y/z/intensity in fp64, count}; every keyframe is transformed (fp32,
+// map builder  a voxel hash table in HBM, one 32-byte record per voxel {key, count, fp32 sums of the offsets from the voxel corner
+//              and of the intensity}; every keyframe is transformed (fp32,
 //              pcl::transformPointCloud order) and accumulated with atomics, so keyframes stream through in any order
 //              and any number per launch.  Across GPUs (one process each, keyframes split in contiguous blocks) the
 //              partial sums are exchanged by voxel ownership (hash of the key) with grouped ncclSend/ncclRecv and merged;
@@ -193,12 +194,12 @@ __global__ void k_undistort(const float* __restrict__ raw, const int32_t* __rest
 }
 
 // ------------------------------------------------------------------ map builder
-struct __align__(16) Xfer {  // what travels between ranks
+struct __align__(16) Xfer {  // what travels between ranks: 32 bytes per voxel
     unsigned long long key;
     unsigned int n, pad;
-    double sx, sy, sz, si;
+    float4 s;  // sums of (x, y, z) - voxel corner and of the intensity, like Vox::s
 };
-static_assert(sizeof(Xfer) == 48, "exchange record");
+static_assert(sizeof(Xfer) == 32, "exchange record");
 
 __device__ __forceinline__ uint32_t mix64(unsigned long long k) {
     k ^= k >> 33;
@@ -209,19 +210,35 @@ __device__ __forceinline__ uint32_t mix64(unsigned long long k) {
     return (uint32_t)k;
 }
 
-// One voxel = ONE 64-byte record (two sectors of one line): key, count and the four sums.  The first layout kept them in three
-// arrays, i.e. three different lines per point (ncu r01: 178 MB of DRAM traffic per 24-keyframe launch).
-struct __align__(64) Vox {
+// One voxel = ONE 32-byte record = one DRAM sector: key, count and the four sums.  The first layout kept key / fp64 sums / count
+// in three arrays (three lines per point, 178 MB of DRAM traffic per 24-keyframe launch, ncu r01) and paid five atomics per
+// point (four fp64 adds and the count).  Here a point costs TWO: one 16-byte vector atomic (red.global.add.v4.f32, sm_90+)
+// and the count.  fp32 sums are exact enough because they are taken RELATIVE TO THE VOXEL'S CORNER: the offsets are below one
+// leaf (0.1 m), so a voxel of a hundred points keeps its centroid to ~1e-8 m wherever the voxel sits (coordinates of a
+// survey reach kilometres: absolute fp32 sums would be off by millimetres and depend on the order of the atomics).
+// The corner is recovered from the key, so the offsets are rank independent and travel as they are.
+struct __align__(32) Vox {
     unsigned long long key;
     unsigned int cnt, pad;
-    double sx, sy, sz, si;
-    double pad2[2];
+    float4 s;  // sum of (x - cx * leaf, y - cy * leaf, z - cz * leaf, intensity)
 };
-static_assert(sizeof(Vox) == 64, "voxel record");
+static_assert(sizeof(Vox) == 32, "voxel record");
 struct Table {
     Vox* v;
     uint32_t mask;
 };
+__device__ __forceinline__ void unpack_cell(unsigned long long key, int& cx, int& cy, int& cz) {  // key = pack_key(cz, cy, cx)
+    cx = (int)(key & 0x1FFFFFull) - kKeyBias;
+    cy = (int)((key >> 21) & 0x1FFFFFull) - kKeyBias;
+    cz = (int)((key >> 42) & 0x1FFFFFull) - kKeyBias;
+}
+// one point into its voxel: offset from the voxel corner (exact in fp64, then narrowed), one vector atomic + the count
+__device__ __forceinline__ void vox_add(Vox* v, float x, float y, float z, float inten, int cx, int cy, int cz, double leaf) {
+    const float4 d = make_float4((float)((double)x - (double)cx * leaf), (float)((double)y - (double)cy * leaf),
+                                 (float)((double)z - (double)cz * leaf), inten);
+    atomicAdd(&v->s, d);
+    atomicAdd(&v->cnt, 1u);
+}
 
 // `created` counts the voxels this thread created; the caller adds the warp's total to the voxel counter with ONE atomic at
 // the end of the kernel (count_created) - an atomicAdd per new voxel is millions of atomics on a single address.
@@ -257,7 +274,7 @@ __device__ __forceinline__ void count_created(unsigned int created, unsigned int
 struct PoseM {
     float m[12];  // row-major 3x4, travels as a kernel argument (no per-keyframe copy)
 };
-__global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM pose, float inv_leaf, Table t, unsigned int* n_voxels,
+__global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM pose, float inv_leaf, double leaf, Table t, unsigned int* n_voxels,
                              unsigned int capacity, unsigned int* err) {
     const float* M = pose.m;
     unsigned int created = 0;
@@ -272,11 +289,7 @@ __global__ void k_accumulate(const float4* __restrict__ pts, int64_t n, PoseM po
         const unsigned long long key = pack_key(cz, cy, cx);
         const int s = table_slot(t, key, created, err);
         if (s < 0) continue;
-        atomicAdd(&t.v[s].sx, (double)x);
-        atomicAdd(&t.v[s].sy, (double)y);
-        atomicAdd(&t.v[s].sz, (double)z);
-        atomicAdd(&t.v[s].si, (double)p.w);
-        atomicAdd(&t.v[s].cnt, 1u);
+        vox_add(t.v + s, x, y, z, p.w, cx, cy, cz, leaf);
     }
     count_created(created, n_voxels, capacity, err);
 }
@@ -293,7 +306,7 @@ struct FrameDesc {
 struct FrameBatch {
     FrameDesc f[kFrameBatch];
 };
-__global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float inv_leaf, Table t, unsigned int* n_voxels, unsigned int capacity,
+__global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float inv_leaf, double leaf, Table t, unsigned int* n_voxels, unsigned int capacity,
                                                           unsigned int* err) {
     const FrameDesc& d = fb.f[blockIdx.y];
     const float* M = d.m;
@@ -311,11 +324,7 @@ __global__ void __launch_bounds__(256) k_accumulate_batch(FrameBatch fb, float i
         const unsigned long long key = pack_key(cz, cy, cx);
         const int s = table_slot(t, key, created, err);
         if (s < 0) continue;
-        atomicAdd(&t.v[s].sx, (double)x);
-        atomicAdd(&t.v[s].sy, (double)y);
-        atomicAdd(&t.v[s].sz, (double)z);
-        atomicAdd(&t.v[s].si, (double)p.w);
-        atomicAdd(&t.v[s].cnt, 1u);
+        vox_add(t.v + s, x, y, z, p.w, cx, cy, cz, leaf);
     }
     count_created(created, n_voxels, capacity, err);
 }
@@ -345,13 +354,16 @@ __global__ void k_table_list(Table t, unsigned long long* __restrict__ keys, uin
     slots[i] = s;
 }
 
-__global__ void k_extract(Table t, const uint32_t* __restrict__ slots, int64_t m, float4* __restrict__ out, int32_t* __restrict__ out_cnt) {
+__global__ void k_extract(Table t, double leaf, const uint32_t* __restrict__ slots, int64_t m, float4* __restrict__ out, int32_t* __restrict__ out_cnt) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint32_t s = slots[i];
     const Vox a = t.v[s];
     const double n = (double)a.cnt;
-    out[i] = make_float4((float)(a.sx / n), (float)(a.sy / n), (float)(a.sz / n), (float)(a.si / n));
+    int cx, cy, cz;
+    unpack_cell(a.key, cx, cy, cz);
+    out[i] = make_float4((float)((double)cx * leaf + (double)a.s.x / n), (float)((double)cy * leaf + (double)a.s.y / n),
+                         (float)((double)cz * leaf + (double)a.s.z / n), (float)((double)a.s.w / n));
     if (out_cnt) out_cnt[i] = (int32_t)a.cnt;
 }
 
@@ -380,7 +392,7 @@ __global__ void k_owner_scatter(Table t, int nranks, unsigned long long* __restr
     if (owner < 0) return;
     const unsigned long long i = base + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
     const Vox a = t.v[s];
-    out[i] = Xfer{k, a.cnt, 0u, a.sx, a.sy, a.sz, a.si};
+    out[i] = Xfer{k, a.cnt, 0u, a.s};
 }
 __global__ void k_merge_records(const Xfer* __restrict__ rec, int64_t m, Table t, unsigned int* n_voxels, unsigned int capacity, unsigned int* err) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -389,10 +401,7 @@ __global__ void k_merge_records(const Xfer* __restrict__ rec, int64_t m, Table t
         const Xfer r = rec[i];
         const int s = table_slot(t, r.key, created, err);
         if (s >= 0) {
-            atomicAdd(&t.v[s].sx, r.sx);
-            atomicAdd(&t.v[s].sy, r.sy);
-            atomicAdd(&t.v[s].sz, r.sz);
-            atomicAdd(&t.v[s].si, r.si);
+            atomicAdd(&t.v[s].s, r.s);
             atomicAdd(&t.v[s].cnt, r.n);
         }
     }
@@ -492,7 +501,7 @@ struct Builder {
         PoseM pm;
         pose_matrix(pose7, pm.m);
         const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-        k_accumulate<<<blocks, 256, 0, stream>>>(d_frame, n, pm, inv_leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
+        k_accumulate<<<blocks, 256, 0, stream>>>(d_frame, n, pm, inv_leaf, (double)leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
         LAUNCH_COUNT(1);
         ++frames;
         points += n;
@@ -513,7 +522,7 @@ struct Builder {
                 points += ns[c0 + j];
             }
             const int blocks = (int)std::min<int64_t>((nmax + 255) / 256, 148 * 8);
-            k_accumulate_batch<<<dim3(blocks, k), 256, 0, stream>>>(fb, inv_leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
+            k_accumulate_batch<<<dim3(blocks, k), 256, 0, stream>>>(fb, inv_leaf, (double)leaf, tab, d_ctr, (unsigned int)capacity, d_ctr + 1);
             LAUNCH_COUNT(1);
             frames += k;
         }
@@ -929,7 +938,7 @@ int64_t b200_mapbuild_extract(b200_mapbuild* h, float* out_xyzi, int32_t* out_co
     const int64_t w = std::min<int64_t>(m, max_out);
     if (w > 0 && out_xyzi) {
         if (b.d_out.reserve(m) != cudaSuccess || b.d_cnt.reserve(m) != cudaSuccess) return -1;
-        vox::k_extract<<<(unsigned)((m + 255) / 256), 256, 0, b.stream>>>(b.tab, b.d_slots2.p, m, b.d_out.p, b.d_cnt.p);
+        vox::k_extract<<<(unsigned)((m + 255) / 256), 256, 0, b.stream>>>(b.tab, (double)b.leaf, b.d_slots2.p, m, b.d_out.p, b.d_cnt.p);
         LAUNCH_COUNT(1);
         cudaMemcpyAsync(out_xyzi, b.d_out.p, w * sizeof(float4), cudaMemcpyDeviceToHost, b.stream);
         if (out_count) cudaMemcpyAsync(out_count, b.d_cnt.p, w * sizeof(int32_t), cudaMemcpyDeviceToHost, b.stream);
