@@ -201,6 +201,56 @@ int32_t b200_ndt_align_batch(b200_ndt* ndt, const float* guesses16, int64_t h, f
 int32_t b200_ndt_grid(b200_ndt* ndt, int32_t* min_b3, int32_t* div_b3);
 
 /* ------------------------------------------------------------------------- *
+ * B3 (alternative) — Generalized ICP.  Replaces pclomp::GeneralizedIterativeClosestPoint<PointT, PointT>
+ * (pointcloud_match/ndt_omp/include/pclomp/gicp_omp.h:60-135, gicp_omp_impl.hpp), the registration object
+ * jueying_slam/src/localization.cpp:163,175-177 selects with ndt_neighbor_search_method == "GICP_OMP" and drives through
+ * pcl::Registration (setInputTarget :277, setInputSource / align / hasConverged / getFitnessScore /
+ * getFinalTransformation :323-328).  4x4 matrices are column-major floats like Eigen::Matrix4f::data().
+ * ------------------------------------------------------------------------- */
+typedef struct b200_gicp b200_gicp;
+typedef struct {
+    int32_t k_correspondences;     /* setCorrespondenceRandomness, 20 (gicp_omp.h:116) */
+    double gicp_epsilon;           /* 0.001 (gicp_omp.h:117) */
+    double rotation_epsilon;       /* setRotationEpsilon, 2e-3 (gicp_omp.h:118) */
+    double transformation_epsilon; /* setTransformationEpsilon, 5e-4 (gicp_omp.h:125) */
+    double corr_dist_threshold;    /* setMaxCorrespondenceDistance, 5.0 (gicp_omp.h:126) */
+    int32_t max_iterations;        /* setMaximumIterations, 200 (gicp_omp.h:124) */
+    int32_t max_inner_iterations;  /* setMaximumOptimizerIterations, 20 (gicp_omp.h:120) */
+} b200_gicp_params;                /* a field <= 0 takes the reference's default */
+typedef struct {
+    int32_t converged;   /* hasConverged() */
+    int32_t iterations;  /* nr_iterations_ */
+    int32_t last_m;      /* correspondences of the last pass */
+    int32_t last_inner;  /* BFGS steps of the last pass */
+    int32_t last_status; /* BFGSSpace status the last pass ended with: 0 Success, 1 NoProgress, -1 Running */
+    int32_t inner_total; /* BFGS steps over the whole align */
+    int32_t n_f, n_df, n_fdf; /* cost-functor calls: operator(), df, fdf (gicp_omp_impl.hpp:245-368) */
+    double delta;        /* the last pass's convergence measure (gicp_omp_impl.hpp:483-494) */
+    float gpu_ms;
+} b200_gicp_result;
+int32_t b200_gicp_create(const b200_gicp_params* params, int32_t device, b200_gicp** out);
+int32_t b200_gicp_destroy(b200_gicp* h);
+/* setInputTarget (gicp_omp.h:173-178): builds the exact-search index (the kd-tree's role); target covariances are recomputed by the next align */
+int32_t b200_gicp_set_target(b200_gicp* h, const float* xyz, int64_t n, int64_t stride_bytes);
+/* setInputSource (gicp_omp.h:141-157) */
+int32_t b200_gicp_set_source(b200_gicp* h, const float* xyz, int64_t n, int64_t stride_bytes);
+/* align(output, guess) -> computeTransformation (gicp_omp_impl.hpp:371-516).  guess16 NULL = identity.  B200_OK, or
+ * B200_NOT_CONVERGED when the loop broke on an optimiser exception (fewer than 4 correspondences). */
+int32_t b200_gicp_align(b200_gicp* h, const float* guess16, float* final16, b200_gicp_result* result);
+/* getFitnessScore(max_range) with the source moved by T16 (NULL = the last final transformation) */
+int32_t b200_gicp_fitness_score(b200_gicp* h, const float* T16, double max_range, double* score, int64_t* n_in_range);
+/* parity probes.  covariances: computeCovariances (gicp_omp_impl.hpp:49-123) of the source (which = 0) or the target (1), n x 9
+ * doubles row-major, and optionally the k neighbour indices per point in ascending (distance, index) order.
+ * correspondences: the matching half of one pass at (transformation_, guess): tgt_idx[i] = matched target point or -1, maha9[i] =
+ * mahalanobis_[i].block<3,3>, d2[i] = squared distance to the nearest target point (exact whenever it is below the gate).
+ * cost: the functor at x (x y z roll pitch yaw) on the correspondences of the last align / correspondences call. */
+int32_t b200_gicp_covariances(b200_gicp* h, int32_t which, double* cov9, int32_t* knn_idx);
+int32_t b200_gicp_correspondences(b200_gicp* h, const float* trans16, const float* guess16, int32_t* tgt_idx, float* maha9, float* d2, int64_t* m);
+int32_t b200_gicp_cost(b200_gicp* h, const double* x6, double* f_op, double* f_fdf, double* g6, int64_t* m);
+/* the search grid chosen for a cloud: cell size, dense cells, occupied cells */
+int32_t b200_gicp_index_info(b200_gicp* h, int32_t which, float* leaf, int64_t* cells, int64_t* occupied);
+
+/* ------------------------------------------------------------------------- *
  * Sharded paths (one process per GPU, NCCL over NVLink).  The reference is single-process and has no
  * counterpart: each hypothesis is scored with the reference's calculateScore arithmetic.
  * ------------------------------------------------------------------------- */

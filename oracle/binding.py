@@ -38,6 +38,17 @@ class NdtParams(C.Structure):
                 ("eig_ratio", C.c_double), ("num_threads", C.c_int32)]
 
 
+class GicpParams(C.Structure):
+    _fields_ = [("k_correspondences", C.c_int32), ("gicp_epsilon", C.c_double), ("rotation_epsilon", C.c_double),
+                ("transformation_epsilon", C.c_double), ("corr_dist_threshold", C.c_double), ("max_iterations", C.c_int32),
+                ("max_inner_iterations", C.c_int32), ("num_threads", C.c_int32)]
+
+
+class GicpResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int32), ("last_m", C.c_int32), ("last_inner", C.c_int32),
+                ("last_status", C.c_int32), ("inner_total", C.c_int32), ("n_f", C.c_int32), ("n_df", C.c_int32), ("n_fdf", C.c_int32)]
+
+
 class NdtResult(C.Structure):
     _fields_ = [("converged", C.c_int32), ("iters", C.c_int32), ("evals", C.c_int32), ("hess_evals", C.c_int32),
                 ("trans_probability", C.c_double), ("hessian", C.c_double * 36), ("score", C.c_double),
@@ -46,7 +57,7 @@ class NdtResult(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "undistort_oracle.cpp", "loam_oracle.cpp", "smallmat.h", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("lio_oracle.cpp", "ndt_oracle.cpp", "voxelgrid_oracle.cpp", "undistort_oracle.cpp", "loam_oracle.cpp", "gicp_oracle.cpp", "smallmat.h", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -124,6 +135,24 @@ def lib():
         L.orc_eigen_selfadjoint3.argtypes = [vp, vp, vp]
         L.orc_jacobi_svd_solve6.argtypes = [vp, vp, vp, vp]
         L.orc_matrix_from_pose.argtypes = [vp, vp]
+        L.orc_gicp_create.restype = vp
+        L.orc_gicp_create.argtypes = [C.POINTER(GicpParams)]
+        L.orc_gicp_destroy.argtypes = [vp]
+        L.orc_gicp_set_target.argtypes = [vp, vp, i64, i64]
+        L.orc_gicp_set_source.argtypes = [vp, vp, i64, i64]
+        L.orc_gicp_covariances.restype = i32
+        L.orc_gicp_covariances.argtypes = [vp, i32, vp]
+        L.orc_gicp_align.restype = i32
+        L.orc_gicp_align.argtypes = [vp, vp, vp, C.POINTER(GicpResult)]
+        L.orc_gicp_correspondences.restype = i64
+        L.orc_gicp_correspondences.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orc_gicp_cost.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orc_gicp_apply_state.argtypes = [vp, vp]
+        L.orc_gicp_estimate.restype = i32
+        L.orc_gicp_estimate.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_gicp_knn.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, vp]
+        L.orc_bfgs_test.restype = i32
+        L.orc_bfgs_test.argtypes = [vp, i32, vp, vp]
         _LIB = L
     return _LIB
 
@@ -445,3 +474,100 @@ class OracleLoam:
         it = lib().orc_loam_optimize(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), iter_num,
                                      C.byref(nsel), C.byref(conv), C.byref(deg), _p(AtA))
         return t, dict(iters=it, n_sel=nsel.value, converged=bool(conv.value), degenerate=bool(deg.value), AtA=AtA)
+
+
+# ------------------------------------------------------------------ pclomp::GeneralizedIterativeClosestPoint
+def gicp_params(k_correspondences=20, gicp_epsilon=0.001, rotation_epsilon=2e-3, transformation_epsilon=5e-4, corr_dist_threshold=5.0,
+                max_iterations=200, max_inner_iterations=20, num_threads=0) -> GicpParams:
+    """Defaults of the constructor (gicp_omp.h:115-135)."""
+    p = GicpParams()
+    p.k_correspondences, p.gicp_epsilon, p.rotation_epsilon = k_correspondences, gicp_epsilon, rotation_epsilon
+    p.transformation_epsilon, p.corr_dist_threshold = transformation_epsilon, corr_dist_threshold
+    p.max_iterations, p.max_inner_iterations, p.num_threads = max_iterations, max_inner_iterations, num_threads
+    return p
+
+
+class OracleGicp:
+    def __init__(self, **kw):
+        self.params = gicp_params(**kw)
+        self.h = lib().orc_gicp_create(C.byref(self.params))
+        self.n_src = self.n_tgt = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_gicp_destroy(self.h)
+            self.h = None
+
+    def set_target(self, pts):
+        pts = _f32(pts)
+        self.n_tgt = pts.shape[0]
+        lib().orc_gicp_set_target(self.h, _p(pts), pts.shape[0], pts.strides[0])
+
+    def set_source(self, pts):
+        pts = _f32(pts)
+        self.n_src = pts.shape[0]
+        lib().orc_gicp_set_source(self.h, _p(pts), pts.shape[0], pts.strides[0])
+
+    def covariances(self, which):
+        """which: 'source' | 'target' -> [n, 3, 3]"""
+        n = self.n_tgt if which == "target" else self.n_src
+        out = np.zeros((n, 3, 3))
+        rc = lib().orc_gicp_covariances(self.h, 1 if which == "target" else 0, _p(out))
+        if rc != 0:
+            raise ValueError("cloud smaller than k_correspondences")
+        return out
+
+    def align(self, guess=None):
+        g = np.ascontiguousarray((np.eye(4) if guess is None else np.asarray(guess)).T, dtype=np.float32)  # column-major
+        fin = np.zeros(16, np.float32)
+        r = GicpResult()
+        rc = lib().orc_gicp_align(self.h, _p(g), _p(fin), C.byref(r))
+        return rc, fin.reshape(4, 4).T.copy(), r
+
+    def correspondences(self, trans=None, guess=None):
+        t = np.ascontiguousarray((np.eye(4) if trans is None else np.asarray(trans)).T, dtype=np.float32)
+        g = np.ascontiguousarray((np.eye(4) if guess is None else np.asarray(guess)).T, dtype=np.float32)
+        idx = np.zeros(self.n_src, np.int32)
+        maha = np.zeros((self.n_src, 3, 3), np.float32)
+        d2 = np.zeros(self.n_src, np.float32)
+        m = lib().orc_gicp_correspondences(self.h, _p(t), _p(g), _p(idx), _p(maha), _p(d2))
+        return int(m), idx, maha, d2
+
+    def estimate(self, trans=None):
+        """estimateRigidTransformationBFGS on the correspondences of the last correspondences() call, from `trans`."""
+        t = np.ascontiguousarray((np.eye(4) if trans is None else np.asarray(trans)).T, dtype=np.float32).reshape(-1)
+        inner, status = C.c_int32(), C.c_int32()
+        calls = np.zeros(3, np.int32)
+        rc = lib().orc_gicp_estimate(self.h, _p(t), C.byref(inner), C.byref(status), _p(calls))
+        return rc, t.reshape(4, 4).T.copy(), inner.value, status.value, calls
+
+    def cost(self, x6):
+        """operator()(x), fdf's f, df's gradient, fdf's gradient on the correspondences of the last correspondences() call"""
+        x = np.ascontiguousarray(x6, dtype=np.float64)
+        f0, f1 = C.c_double(), C.c_double()
+        g0, g1 = np.zeros(6), np.zeros(6)
+        lib().orc_gicp_cost(self.h, _p(x), C.byref(f0), C.byref(f1), _p(g0), _p(g1))
+        return f0.value, f1.value, g0, g1
+
+
+def gicp_apply_state(x6):
+    x = np.ascontiguousarray(x6, dtype=np.float64)
+    t = np.zeros(16, np.float32)
+    lib().orc_gicp_apply_state(_p(x), _p(t))
+    return t.reshape(4, 4).T.copy()
+
+
+def exact_knn(pts, queries, k, brute=False):
+    pts, queries = _f32(pts), _f32(queries)
+    idx = np.zeros((len(queries), k), np.int32)
+    d2 = np.zeros((len(queries), k), np.float32)
+    lib().orc_gicp_knn(_p(pts), pts.shape[0], pts.strides[0], _p(queries), queries.shape[0], queries.strides[0], k, int(brute), _p(idx), _p(d2))
+    return idx, d2
+
+
+def bfgs_test(x0, max_inner=20):
+    x = np.array(x0, dtype=np.float64)
+    inner = C.c_int32()
+    calls = np.zeros(3, np.int32)
+    st = lib().orc_bfgs_test(_p(x), max_inner, C.byref(inner), _p(calls))
+    return int(st), x, inner.value, calls

@@ -164,6 +164,49 @@ int32_t orc_loam_features(orc_loam* h, const float* corner, int64_t nc, int64_t 
 int32_t orc_loam_optimize(orc_loam* h, const float* corner, int64_t nc, int64_t sc, const float* surf, int64_t ns, int64_t ss, float* t6,
                           int32_t iter_num, int32_t* n_sel, int32_t* converged, int32_t* degenerate, double* AtA_first);
 
+/* ---- pclomp::GeneralizedIterativeClosestPoint (gicp_omp.h / gicp_omp_impl.hpp) ---- */
+typedef struct orc_gicp orc_gicp;
+typedef struct {
+    int32_t k_correspondences;      /* 20 */
+    double gicp_epsilon;            /* 0.001 */
+    double rotation_epsilon;        /* 2e-3 */
+    double transformation_epsilon;  /* 5e-4 */
+    double corr_dist_threshold;     /* 5.0 */
+    int32_t max_iterations;         /* 200 */
+    int32_t max_inner_iterations;   /* 20 */
+    int32_t num_threads;
+} orc_gicp_params;
+typedef struct {
+    int32_t converged;
+    int32_t iterations;  /* nr_iterations_ */
+    int32_t last_m;      /* correspondences of the last pass */
+    int32_t last_inner;  /* BFGS steps of the last pass */
+    int32_t last_status; /* BFGSSpace status the last pass ended with */
+    int32_t inner_total;
+    int32_t n_f, n_df, n_fdf; /* functor calls over the whole align */
+} orc_gicp_result;
+orc_gicp* orc_gicp_create(const orc_gicp_params* p);
+void orc_gicp_destroy(orc_gicp* h);
+void orc_gicp_set_target(orc_gicp* h, const float* xyz, int64_t n, int64_t stride_bytes);
+void orc_gicp_set_source(orc_gicp* h, const float* xyz, int64_t n, int64_t stride_bytes);
+/* computeCovariances of the source (which = 0) or the target (1): n x 9 doubles, row-major; -1 when the cloud has fewer than k points */
+int32_t orc_gicp_covariances(orc_gicp* h, int32_t which, double* cov9);
+/* align(output, guess): 0 converged, 2 not converged, -1 error */
+int32_t orc_gicp_align(orc_gicp* h, const float* guess16_colmajor, float* final16_colmajor, orc_gicp_result* r);
+/* the correspondence half of one pass of computeTransformation at (transformation_, guess): tgt_idx[i] = matched target point or -1,
+ * maha9 = mahalanobis_[i].block<3,3> (row-major), d2 = squared distance to the nearest target point; returns the match count */
+int64_t orc_gicp_correspondences(orc_gicp* h, const float* trans16_colmajor, const float* guess16_colmajor, int32_t* tgt_idx, float* maha9, float* d2);
+/* the cost functor on the correspondences of the last orc_gicp_correspondences call: operator(), fdf's f, df's and fdf's gradients */
+void orc_gicp_cost(orc_gicp* h, const double* x6, double* f_op, double* f_fdf, double* g_df6, double* g_fdf6);
+/* estimateRigidTransformationBFGS on those correspondences, starting from (and returning) trans16; -1 = exception */
+int32_t orc_gicp_estimate(orc_gicp* h, float* trans16_colmajor, int32_t* inner, int32_t* status, int32_t* calls3);
+void orc_gicp_apply_state(const double* x6, float* t16_colmajor); /* applyState on the identity */
+/* exact k nearest neighbours (ascending distance, ties to the lower index): grid search, or brute force when brute != 0 */
+void orc_gicp_knn(const float* xyz, int64_t n, int64_t stride, const float* q, int64_t nq, int64_t qstride, int32_t k, int32_t brute, int32_t* idx,
+                  float* d2);
+/* pcl::BFGS driven like estimateRigidTransformationBFGS on a fixed smooth 6-D test function; returns the BFGSSpace status */
+int32_t orc_bfgs_test(double* x6, int32_t max_inner, int32_t* inner, int32_t* calls3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -586,4 +586,118 @@ inline void jacobi_svd_solve6(const double H[36], const double rhs[6], double x[
     }
 }
 
+// ---------------------------------------------------------------------------
+// JacobiSVD<Matrix<double,N,N>>(A, ComputeFullU | ComputeFullV): the decomposition itself, any small N (square: no QR
+// preconditioner).  Same sources as jacobi_svd_solve6: JacobiSVD.h:666-792, misc/RealSvd2x2.h:18-51, Jacobi.h:83-113.
+// A, U, V row-major; singular values descending.  Used by the GICP oracle with N = 3 (gicp_omp_impl.hpp:109-111).
+// ---------------------------------------------------------------------------
+template <int N>
+inline bool jacobi_svd(const double* A, double* Uo, double* Vo, double* sv) {
+    const double eps = std::numeric_limits<double>::epsilon(), dmin = std::numeric_limits<double>::min();
+    const double precision = 2.0 * eps;
+    double scale = 0.0;
+    bool bad = false;
+    for (int i = 0; i < N * N; ++i) {
+        const double a = std::fabs(A[i]);
+        if (a != a) bad = true;
+        if (a > scale) scale = a;
+    }
+    if (bad || !std::isfinite(scale)) {
+        for (int i = 0; i < N * N; ++i) Uo[i] = Vo[i] = std::numeric_limits<double>::quiet_NaN();
+        for (int i = 0; i < N; ++i) sv[i] = std::numeric_limits<double>::quiet_NaN();
+        return false;
+    }
+    if (scale == 0.0) scale = 1.0;
+    double W[N][N], U[N][N], V[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            W[i][j] = A[i * N + j] / scale;
+            U[i][j] = V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    double maxDiag = 0.0;
+    for (int i = 0; i < N; ++i) maxDiag = std::max(maxDiag, std::fabs(W[i][i]));
+    bool finished = false;
+    while (!finished) {
+        finished = true;
+        for (int p = 1; p < N; ++p)
+            for (int q = 0; q < p; ++q) {
+                const double thr = std::max(dmin, precision * maxDiag);
+                if (!(std::fabs(W[p][q]) > thr || std::fabs(W[q][p]) > thr)) continue;
+                finished = false;
+                double m[2][2] = {{W[p][p], W[p][q]}, {W[q][p], W[q][q]}};
+                // real_2x2_jacobi_svd: rot1 makes m symmetric, then makeJacobi diagonalises it
+                double c1 = 1.0, s1 = 0.0;
+                const double t = m[0][0] + m[1][1], d = m[1][0] - m[0][1];
+                if (!(std::fabs(d) < dmin)) {
+                    const double u = t / d, tmp = std::sqrt(1.0 + u * u);
+                    s1 = 1.0 / tmp;
+                    c1 = u / tmp;
+                }
+                if (!(c1 == 1.0 && s1 == 0.0))
+                    for (int k = 0; k < 2; ++k) {
+                        const double x = m[0][k], y = m[1][k];
+                        m[0][k] = c1 * x + s1 * y;
+                        m[1][k] = -s1 * x + c1 * y;
+                    }
+                double cr = 1.0, sr = 0.0;
+                const double deno = 2.0 * std::fabs(m[0][1]);
+                if (!(deno < dmin)) {
+                    const double tau = (m[0][0] - m[1][1]) / deno, w = std::sqrt(tau * tau + 1.0);
+                    const double tt = tau > 0.0 ? 1.0 / (tau + w) : 1.0 / (tau - w);
+                    const double sign_t = tt > 0.0 ? 1.0 : -1.0, nn = 1.0 / std::sqrt(tt * tt + 1.0);
+                    sr = -sign_t * (m[0][1] / std::fabs(m[0][1])) * std::fabs(tt) * nn;
+                    cr = nn;
+                }
+                const double cl = c1 * cr - s1 * (-sr), sl = c1 * (-sr) + s1 * cr;  // j_left = rot1 * j_right.transpose()
+                if (!(cl == 1.0 && sl == 0.0)) {
+                    for (int k = 0; k < N; ++k) {
+                        const double x = W[p][k], y = W[q][k];
+                        W[p][k] = cl * x + sl * y;
+                        W[q][k] = -sl * x + cl * y;
+                    }
+                    for (int k = 0; k < N; ++k) {
+                        const double x = U[k][p], y = U[k][q];
+                        U[k][p] = cl * x + sl * y;
+                        U[k][q] = -sl * x + cl * y;
+                    }
+                }
+                if (!(cr == 1.0 && -sr == 0.0)) {
+                    for (int k = 0; k < N; ++k) {
+                        const double x = W[k][p], y = W[k][q];
+                        W[k][p] = cr * x - sr * y;
+                        W[k][q] = sr * x + cr * y;
+                    }
+                    for (int k = 0; k < N; ++k) {
+                        const double x = V[k][p], y = V[k][q];
+                        V[k][p] = cr * x - sr * y;
+                        V[k][q] = sr * x + cr * y;
+                    }
+                }
+                maxDiag = std::max(maxDiag, std::max(std::fabs(W[p][p]), std::fabs(W[q][q])));
+            }
+    }
+    for (int i = 0; i < N; ++i) {
+        const double a = W[i][i];
+        sv[i] = std::fabs(a);
+        if (a < 0.0)
+            for (int k = 0; k < N; ++k) U[k][i] = -U[k][i];
+    }
+    for (int i = 0; i < N; ++i) sv[i] *= scale;
+    for (int i = 0; i < N; ++i) {
+        int pos = 0;
+        double mx = sv[i];
+        for (int j = 1; j < N - i; ++j)
+            if (sv[i + j] > mx) { mx = sv[i + j]; pos = j; }
+        if (mx == 0.0) break;
+        if (pos) {
+            pos += i;
+            std::swap(sv[i], sv[pos]);
+            for (int k = 0; k < N; ++k) { std::swap(U[k][pos], U[k][i]); std::swap(V[k][pos], V[k][i]); }
+        }
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) { Uo[i * N + j] = U[i][j]; Vo[i * N + j] = V[i][j]; }
+    return true;
+}
+
 }  // namespace orc
