@@ -32,6 +32,7 @@ sequence   configs[2] (N = 1): sliding-map odometry over --seq-scans scans (defa
 fullmap    configs[4]: construct_full_map over --fullmap-frames keyframes x 100k points (default 10000 = full size), keyframes
            cut into one block per rank, partial voxel sums exchanged over NCCL (strong scaling).
 scan2map   jueying_slam's LOAM-style scan2MapOptimization for one scan (N = 1).
+gicp       pclomp GICP align of a 20k-point scan against a 1M-point map (N = 1).
 summary    the headline numbers of every leg once more, last on the line.
 """
 from __future__ import annotations
@@ -757,6 +758,52 @@ def loam_leg(args, local_rank, api, synth):
     return out
 
 
+def gicp_leg(args, local_rank, api, synth):
+    """pclomp GICP ("GICP_OMP" in localization.cpp) - 20k-point scan against a 1M-point local map, constructor defaults."""
+    world = synth.make_world(synth.SEED, beams=True)
+    mp = synth.sample_map(100_000 if args.small else 1_000_000, synth.SEED, world=world)
+    p_true = np.array([3.0, -2.0, 1.2, 0.0, 0.0, 0.6])
+    T = synth.pose_vec_to_matrix(p_true)
+    scan = np.ascontiguousarray(synth.raycast(T[:3, 3], T[:3, :3], synth.livox_dirs(24000, synth.SEED), world, seed=synth.SEED)[:20000])
+    guess = synth.pose_vec_to_matrix(p_true + np.array([0.15, -0.1, 0.05, 0.01, -0.01, 0.03]))
+    g = api.GeneralizedIterativeClosestPoint(device=local_rank)
+    t0 = time.perf_counter()
+    g.setInputTarget(mp)
+    g.setInputSource(scan)
+    g.covariances("target")                       # the reference computes them inside the first align (gicp_omp_impl.hpp:383-394)
+    t_first = (time.perf_counter() - t0) * 1e3
+    dev, wall = [], []
+    for k in range(min(args.steps, 20) + 3):
+        api.flush_l2(local_rank)
+        t0 = time.perf_counter()
+        rc = g.align(guess)
+        if k >= 3:
+            wall.append((time.perf_counter() - t0) * 1e3)
+            dev.append(g.result.gpu_ms)
+    fin, r = g.getFinalTransformation(), g.result
+    out = {"workload": f"pclomp GICP (k = 20, BFGS): {len(scan)}-pt scan vs {len(mp)}-pt map, 0.19 m / 2 deg initial error, constructor defaults",
+           "index_and_target_covariances_ms_e2e": t_first, "align_ms": {"device": mean(dev), "e2e_wall": mean(wall)},
+           "outer_iterations": int(r.iterations), "bfgs_steps": int(r.inner_total), "functor_calls": [int(r.n_f), int(r.n_df), int(r.n_fdf)],
+           "matches": int(r.last_m), "converged": bool(r.converged), "index": g.index_info("target"),
+           "pose_error": {"trans_m": float(np.abs(fin[:3, 3] - T[:3, 3]).max()), "rot": float(np.abs(fin[:3, :3] - T[:3, :3]).max())}}
+    if not args.no_cpu:
+        from oracle import binding as ob
+        o = ob.OracleGicp(num_threads=host_threads())
+        o.set_target(mp)
+        o.set_source(scan)
+        t0 = time.perf_counter()
+        o.covariances("target")
+        t_cov = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        rc0, fin0, r0 = o.align(guess)
+        out["cpu_baseline"] = {"align_ms": (time.perf_counter() - t0) * 1e3, "covariances_ms": t_cov, "cores": host_threads(), "kind": "port",
+                               "sample": "one full align; the port's exact neighbour search is a uniform grid, not PCL's kd-tree"}
+        out["parity"] = {"outer_iterations_equal": bool(r0.iterations == r.iterations), "matches_equal": bool(r0.last_m == r.last_m),
+                         "max_transform_diff": float(np.abs(fin0 - fin).max())}
+    g.close()
+    return out
+
+
 # =============================================================================================== arms
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = its restatement in oracle/
@@ -863,6 +910,10 @@ def run_b200(args, rank, local_rank, world):
             extra["sequence"] = sequence_leg(args, local_rank, api, synth, args.seq_scans, args.seq_parity)
         if not args.no_ndt:
             extra["scan2map"] = loam_leg(args, local_rank, api, synth)
+            try:
+                extra["gicp"] = gicp_leg(args, local_rank, api, synth)
+            except Exception as e:  # the newest leg must not take the headline down with it
+                extra["gicp"] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
@@ -899,6 +950,9 @@ def run_b200(args, rank, local_rank, world):
         fm = extra["fullmap"]
         summ.update({"fullmap_keyframes": args.fullmap_frames, "fullmap_keyframes_per_s": fm["value"], "fullmap_seconds": fm["seconds"],
                      "fullmap_exchange_ms": fm["exchange_ms"], "fullmap_parity": fm.get("parity")})
+    if "gicp" in extra and "align_ms" in extra["gicp"]:
+        gi = extra["gicp"]
+        summ.update({"gicp_align_ms": gi["align_ms"]["device"], "gicp_cpu_align_ms": (gi.get("cpu_baseline") or {}).get("align_ms"), "gicp_parity": gi.get("parity")})
     line["summary"] = summ
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -52,6 +52,18 @@ class NdtResult(C.Structure):
                 ("p_final", C.c_double * 6), ("gpu_ms", C.c_float)]
 
 
+class GicpParams(C.Structure):
+    _fields_ = [("k_correspondences", C.c_int32), ("gicp_epsilon", C.c_double), ("rotation_epsilon", C.c_double),
+                ("transformation_epsilon", C.c_double), ("corr_dist_threshold", C.c_double), ("max_iterations", C.c_int32),
+                ("max_inner_iterations", C.c_int32)]
+
+
+class GicpResult(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int32), ("last_m", C.c_int32), ("last_inner", C.c_int32),
+                ("last_status", C.c_int32), ("inner_total", C.c_int32), ("n_f", C.c_int32), ("n_df", C.c_int32), ("n_fdf", C.c_int32),
+                ("delta", C.c_double), ("gpu_ms", C.c_float)]
+
+
 class LoamStats(C.Structure):
     _fields_ = [("iters", C.c_int32), ("n_sel", C.c_int32), ("converged", C.c_int32), ("degenerate", C.c_int32), ("gpu_ms", C.c_float),
                 ("AtA_first", C.c_double * 36)]
@@ -175,6 +187,16 @@ def lib():
     L.b200_loam_set_map.argtypes = [vp, vp, i64, i64, vp, i64, i64]
     L.b200_loam_optimize.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, i32, C.POINTER(LoamStats)]
     L.b200_loam_features.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, vp, vp, vp]
+    L.b200_gicp_create.argtypes = [C.POINTER(GicpParams), i32, C.POINTER(vp)]
+    L.b200_gicp_destroy.argtypes = [vp]
+    L.b200_gicp_set_target.argtypes = [vp, vp, i64, i64]
+    L.b200_gicp_set_source.argtypes = [vp, vp, i64, i64]
+    L.b200_gicp_align.argtypes = [vp, vp, vp, C.POINTER(GicpResult)]
+    L.b200_gicp_fitness_score.argtypes = [vp, vp, C.c_double, vp, vp]
+    L.b200_gicp_covariances.argtypes = [vp, i32, vp, vp]
+    L.b200_gicp_correspondences.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.b200_gicp_cost.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b200_gicp_index_info.argtypes = [vp, i32, vp, vp, vp]
     _LIB = L
     return L
 
@@ -860,3 +882,127 @@ class ScanToMap:
         nsel = C.c_int32(0)
         _check(lib().b200_loam_features(self.h, _p(c), c.shape[0], c.strides[0], _p(s), s.shape[0], s.strides[0], _p(t), _p(flags), _p(coeff), C.byref(nsel)))
         return nsel.value, flags, coeff
+
+
+class GeneralizedIterativeClosestPoint:
+    """pclomp::GeneralizedIterativeClosestPoint's surface (gicp_omp.h:60-283 + the pcl::Registration calls
+    jueying_slam/src/localization.cpp:277,323-328 makes) on the GPU engine."""
+
+    def __init__(self, device=0):
+        self._p = GicpParams(20, 0.001, 2e-3, 5e-4, 5.0, 200, 20)  # ctor defaults, gicp_omp.h:115-127
+        self._device = device
+        self.h = None
+        self._target = None
+        self._source = None
+        self.result = GicpResult()
+        self._final = np.eye(4, dtype=np.float32)
+        self._dirty = True
+
+    def _handle(self):
+        if self.h is None or self._dirty:
+            if self.h is not None:
+                lib().b200_gicp_destroy(self.h)
+            self.h = C.c_void_p()
+            _check(lib().b200_gicp_create(C.byref(self._p), self._device, C.byref(self.h)))
+            self._dirty = False
+            if self._target is not None:
+                _check(lib().b200_gicp_set_target(self.h, _p(self._target), self._target.shape[0], self._target.strides[0]))
+            if self._source is not None:
+                _check(lib().b200_gicp_set_source(self.h, _p(self._source), self._source.shape[0], self._source.strides[0]))
+        return self.h
+
+    def close(self):
+        if getattr(self, "h", None):
+            try:
+                lib().b200_gicp_destroy(self.h)
+            except TypeError:  # interpreter shutdown
+                pass
+            self.h = None
+
+    __del__ = close
+
+    def _set(self, name, v):
+        setattr(self._p, name, v)
+        self._dirty = True
+
+    def setCorrespondenceRandomness(self, k):
+        self._set("k_correspondences", int(k))
+
+    def setRotationEpsilon(self, e):
+        self._set("rotation_epsilon", float(e))
+
+    def setTransformationEpsilon(self, e):
+        self._set("transformation_epsilon", float(e))
+
+    def setMaxCorrespondenceDistance(self, d):
+        self._set("corr_dist_threshold", float(d))
+
+    def setMaximumIterations(self, n):
+        self._set("max_iterations", int(n))
+
+    def setMaximumOptimizerIterations(self, n):
+        self._set("max_inner_iterations", int(n))
+
+    def setInputTarget(self, cloud):
+        self._target = _cloud(cloud)
+        if self.h is not None and not self._dirty:
+            _check(lib().b200_gicp_set_target(self.h, _p(self._target), self._target.shape[0], self._target.strides[0]))
+
+    def setInputSource(self, cloud):
+        self._source = _cloud(cloud)
+        if self.h is not None and not self._dirty:
+            _check(lib().b200_gicp_set_source(self.h, _p(self._source), self._source.shape[0], self._source.strides[0]))
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, dtype=np.float32)
+        gcm = np.ascontiguousarray(g.T)
+        out = np.zeros((4, 4), np.float32)
+        rc = lib().b200_gicp_align(self._handle(), _p(gcm), _p(out), C.byref(self.result))
+        _check(rc, soft=(0, 2))
+        self._final = out.T.copy()
+        return rc
+
+    def hasConverged(self):
+        return bool(self.result.converged)
+
+    def getFinalTransformation(self):
+        return self._final
+
+    def getFitnessScore(self, max_range=1.7976931348623157e308, T=None):
+        s, nr = C.c_double(0), C.c_int64(0)
+        t = None if T is None else np.ascontiguousarray(np.asarray(T, dtype=np.float32).T)
+        _check(lib().b200_gicp_fitness_score(self._handle(), None if t is None else _p(t), max_range, C.byref(s), C.byref(nr)))
+        self.fitness_in_range = nr.value
+        return s.value
+
+    # parity probes
+    def covariances(self, which, with_neighbours=False):
+        cloud = self._target if which == "target" else self._source
+        n = cloud.shape[0]
+        cov = np.zeros((n, 3, 3))
+        knn = np.zeros((n, self._p.k_correspondences), np.int32) if with_neighbours else None
+        _check(lib().b200_gicp_covariances(self._handle(), 1 if which == "target" else 0, _p(cov), None if knn is None else _p(knn)))
+        return (cov, knn) if with_neighbours else cov
+
+    def correspondences(self, trans=None, guess=None):
+        t = np.ascontiguousarray((np.eye(4) if trans is None else np.asarray(trans)).T, dtype=np.float32)
+        g = np.ascontiguousarray((np.eye(4) if guess is None else np.asarray(guess)).T, dtype=np.float32)
+        n = self._source.shape[0]
+        idx = np.zeros(n, np.int32)
+        maha = np.zeros((n, 3, 3), np.float32)
+        d2 = np.zeros(n, np.float32)
+        m = C.c_int64(0)
+        _check(lib().b200_gicp_correspondences(self._handle(), _p(t), _p(g), _p(idx), _p(maha), _p(d2), C.byref(m)))
+        return m.value, idx, maha, d2
+
+    def cost(self, x6):
+        x = np.ascontiguousarray(x6, dtype=np.float64)
+        f0, f1, m = C.c_double(), C.c_double(), C.c_int64()
+        g = np.zeros(6)
+        _check(lib().b200_gicp_cost(self._handle(), _p(x), C.byref(f0), C.byref(f1), _p(g), C.byref(m)))
+        return f0.value, f1.value, g, m.value
+
+    def index_info(self, which):
+        leaf, cells, occ = C.c_float(), C.c_int64(), C.c_int64()
+        _check(lib().b200_gicp_index_info(self._handle(), 1 if which == "target" else 0, C.byref(leaf), C.byref(cells), C.byref(occ)))
+        return dict(leaf=leaf.value, cells=cells.value, occupied=occ.value)

@@ -6,6 +6,7 @@
 #include <random>
 
 #include "esekf_gpu.hpp"
+#include "gicp_gpu.hpp"
 #include "ndt_gpu.hpp"
 #include "scan2map_gpu.hpp"
 
@@ -83,6 +84,19 @@ int main() {
                     ndt.getTransformationProbability());
         if (!ndt.hasConverged() || aligned.points.size() != scan.size()) return 4;
         std::printf("fitness %.5f\n", ndt.getFitnessScore());
+        {   // the "GICP_OMP" registration object on the same clouds
+            GeneralizedIterativeClosestPoint<Cloud> gicp;
+            gicp.setInputTarget(target);
+            gicp.setInputSource(source);
+            Cloud aligned2;
+            gicp.align(aligned2);
+            const float* G = gicp.getFinalTransformation();
+            std::printf("gicp converged %d iters %d m %d t %.4f %.4f %.4f fitness %.6f\n", (int)gicp.hasConverged(), gicp.getFinalNumIteration(), gicp.result().last_m,
+                        G[12], G[13], G[14], gicp.getFitnessScore());
+            if (!gicp.hasConverged() || aligned2.points.size() != scan.size() || std::fabs(G[12] - 0.03f) > 0.02f || std::fabs(G[13] + 0.02f) > 0.02f ||
+                std::fabs(G[14] - 0.01f) > 0.02f)
+                return 8;
+        }
         // scan pre-processing chain: downsample on the device, then the update straight from device memory
         ScanPreprocessor pre;
         double pose22[2 * 22] = {0};
