@@ -121,6 +121,7 @@ def lib():
     L.b200_map_stencil_points.argtypes = [vp, vp, i64, i64, vp, vp]
     L.b200_map_last_knn_ms.restype = C.c_float
     L.b200_map_last_knn_ms.argtypes = [vp]
+    L.b200_map_tma_timeouts.restype = i64
     L.b200_map_evicted.restype = i64
     L.b200_map_evicted.argtypes = [vp]
     L.b200_map_dropped.restype = i64
@@ -199,6 +200,11 @@ def lib():
     L.b200_gicp_index_info.argtypes = [vp, i32, vp, vp, vp]
     _LIB = L
     return L
+
+
+def knn_tma_timeouts() -> int:
+    """Queries of the TMA-staged search (B200_KNN_MODE=9) whose bulk copies hit the watchdog and took the gather path (expected 0)."""
+    return int(lib().b200_map_tma_timeouts())
 
 
 def _check(rc: int, soft=(0,)):

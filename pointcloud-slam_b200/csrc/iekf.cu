@@ -189,6 +189,29 @@ __global__ void __launch_bounds__(256) k_search_w(MapView map, const float4* __r
     if (lane == 0) nbc_out[q] = (unsigned char)c;
 }
 
+// warp-per-query with the candidate runs staged in shared memory by 1-D TMA bulk copies (knn5_warp_t<true>, B200_KNN_MODE=9)
+__global__ void __launch_bounds__(256) k_search_t(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
+                                                  float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
+    pdl_trigger();
+    pdl_wait();
+    if (ctl->done || !ctl->converge) return;
+    __shared__ PassConsts pc;
+    __shared__ __align__(16) float4 s_stage[8][kStageCap];
+    __shared__ __align__(8) uint64_t s_bar[8];
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(PassConsts) / 4)) ((float*)&pc)[tid] = ((const float*)&ctl->pc)[tid];
+    __syncthreads();
+    const int q = (blockIdx.x * blockDim.x + tid) >> 5, lane = tid & 31;
+    if (q >= ctl->n) return;
+    const float4 pbody = __ldg(scan + q);
+    const float3 pw = body_to_world(pc, pbody.x, pbody.y, pbody.z);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_warp_t<true>(map, pw.x, pw.y, pw.z, lane, mine, key, s_stage[tid >> 5], s_bar + (tid >> 5));
+    if (lane < 5) nb_out[(size_t)q * 5 + lane] = mine;
+    if (lane == 0) nbc_out[q] = (unsigned char)c;
+}
+
 // balanced 8-lanes-per-query variant (knn5_g8p, map.cuh)
 __global__ void __launch_bounds__(256, 5) k_search_p(MapView map, const float4* __restrict__ scan, const Ctl* __restrict__ ctl,
                                                   float4* __restrict__ nb_out, unsigned char* __restrict__ nbc_out) {
@@ -711,6 +734,8 @@ int32_t Iekf::enqueue(const float4* d_pts, const Ctl* d_hdr, unsigned search_gri
         const bool pdl = !events;  // kernel -> kernel edges only (an event record in between makes it a full dependency anyway)
         if (mode == 8) {
             CUDA_TRY(launch_k(k_search_p, dim3(search_grid * KNN_BLOCK / 256), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
+        } else if (mode == 9) {
+            CUDA_TRY(launch_k(k_search_t, dim3(search_grid * (32 / KNN_G) * KNN_BLOCK / 256), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
         } else if (mode == 7) {
             CUDA_TRY(launch_k(k_search_w, dim3(search_grid * (32 / KNN_G) * KNN_BLOCK / 256), dim3(256), stream, pdl, mv, d_pts, (const Ctl*)d_ctl, d_nb.p, d_nbc.p));
         } else {

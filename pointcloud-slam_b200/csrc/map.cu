@@ -431,6 +431,24 @@ __global__ void __launch_bounds__(256) k_knn5_w(MapView m, const float4* __restr
     if (lane == 0) cnt[qi] = c;
 }
 
+// warp-per-query with TMA staging (knn5_warp_t<true>): every warp owns kStageCap float4 of shared memory and one mbarrier
+__global__ void __launch_bounds__(256) k_knn5_t(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                                float* __restrict__ d2, int32_t* __restrict__ cnt) {
+    __shared__ __align__(16) float4 s_stage[8][kStageCap];
+    __shared__ __align__(8) uint64_t s_bar[8];
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (qi >= n) return;  // whole warps leave together
+    const float4 p = __ldg(q + qi);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_warp_t<true>(m, p.x, p.y, p.z, lane, mine, key, s_stage[w], s_bar + w);
+    if (lane < 5) {
+        idx[qi * 5 + lane] = __float_as_int(mine.w);
+        d2[qi * 5 + lane] = (key == 0xffffffffu) ? 0.0f : __uint_as_float(key);
+    }
+    if (lane == 0) cnt[qi] = c;
+}
+
 // number of map points resident in the occupied stencil cells of every query (the sum C_i of the roofline's
 // algorithmic-byte formula), and the number of occupied cells
 __global__ void k_stencil_points(MapView m, const float4* __restrict__ q, int n, unsigned long long* __restrict__ out) {
@@ -766,6 +784,8 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
         int mode = knn_mode();
         if (mode == 8) {  // 8 lanes per query, candidates balanced through shared memory
             k_knn5_p<<<(unsigned)((n * 8 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
+        } else if (mode == 9) {  // one warp per query, runs staged in shared memory by 1-D TMA bulk copies
+            k_knn5_t<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         } else if (mode == 7) {  // one warp per query
             k_knn5_w<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         } else {
@@ -866,6 +886,11 @@ int32_t b200_flush_l2(int32_t device) {
 
 /* device time (CUDA events) of the search kernel of the last b200_map_knn5 call */
 float b200_map_last_knn_ms(b200_map* map) { return map ? map->m.last_knn_ms : 0.f; }
+int64_t b200_map_tma_timeouts(void) {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, b200::g_knn_tma_timeouts, sizeof v) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
 int64_t b200_map_evicted(b200_map* map) { return map ? (int64_t)map->m.evicted_total : 0; }
 int64_t b200_map_dropped(b200_map* map, int64_t* last_batch) {
     if (!map) return 0;

@@ -334,9 +334,51 @@ __device__ __forceinline__ int knn5_group(const MapView& m, float qx, float qy, 
 //      fit, ride along as lanes 0..4 of the next chunk (they precede every later candidate in enumeration order).
 // Returns the number found; lane r < count holds winner r: the point (x, y, z, ordinal bits) in `mine` and the bits of its
 // fp32 squared distance in `d2bits`.  Results are bit-identical to knn5_group (same arithmetic, same total order).
-__device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, float qz, int lane, float4& mine, uint32_t& d2bits) {
+//
+// TMA variant (STAGED = true, "W1T", B200_KNN_MODE=9): the recipe BASELINE.json's north_star names for the gather - after the
+// probe and the scan, lane s hands ITS run to the TMA engine as one 1-D bulk copy (cp.async.bulk.shared.global, cnt x 16
+// bytes, completion counted in bytes on a per-warp mbarrier) into the warp's staging area at the run's slot offset, so the
+// candidates of the query land in shared memory already in enumeration order.  Step 3 then reads slot i with one LDS.128:
+// no five-step cell search, no dependent global gather.  A query with more candidates than the staging area holds
+// (kStageCap) or whose copies do not complete within the watchdog takes the gather path below; results are bit-identical
+// either way (same candidates in the same order through the same selection).
+constexpr int kStageCap = 160;  // candidates per warp: 2.5 KB of shared memory, 20 KB per 256-thread block
+static __device__ unsigned int g_knn_tma_timeouts = 0;  // queries whose bulk copies hit the watchdog (expected: 0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // the async proxy must see the initialised barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ int knn5_warp_t(const MapView& m, float qx, float qy, float qz, int lane, float4& mine, uint32_t& d2bits,
+                                           float4* stage, uint64_t* bar) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t INF = 0xffffffffu;
+    if (STAGED) {  // one phase per warp and launch: the barrier is armed once, parity 0
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+    }
     // ---- 1. probe
     int start = 0, cnt = 0;
     {
@@ -368,6 +410,17 @@ __device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, f
     mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     d2bits = INF;
     int found = 0;
+    bool staged = false;  // warp-uniform
+    if (STAGED && total > 0 && total <= kStageCap) {
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 16u);
+        __syncwarp();
+        if (cnt > 0) bulk_g2s(stage + excl, m.pool + start, (uint32_t)cnt * 16u, bar);
+        const long long t0 = clock64();
+        bool done = mbar_try_wait(bar, 0);
+        while (!done && clock64() - t0 < 200000000ll) done = mbar_try_wait(bar, 0);  // ~0.1 s watchdog, then the gather path
+        staged = __all_sync(FULL, done);
+        if (!staged && lane == 0) atomicAdd(&g_knn_tma_timeouts, 1u);
+    }
     // ---- 3 + 4. chunks: the first takes 32 candidates, later ones 27 new ones next to the 5 carried winners
     for (int base = 0; base < total;) {
         const int first_new = base == 0 ? 0 : 5;
@@ -375,16 +428,19 @@ __device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, f
         const bool fresh = lane >= first_new && i < total;
         int pos = 0;
         const int ii = fresh ? i : 0;
+        int addr = 0;
+        if (!STAGED || !staged) {
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {  // largest cell with excl <= slot (its run is not empty); all lanes shuffle
-            const int v = __shfl_sync(FULL, excl, pos + step);
-            if (v <= ii) pos += step;
+            for (int step = 16; step > 0; step >>= 1) {  // largest cell with excl <= slot (its run is not empty); all lanes shuffle
+                const int v = __shfl_sync(FULL, excl, pos + step);
+                if (v <= ii) pos += step;
+            }
+            addr = __shfl_sync(FULL, start, pos) + (ii - __shfl_sync(FULL, excl, pos));
         }
-        const int addr = __shfl_sync(FULL, start, pos) + (ii - __shfl_sync(FULL, excl, pos));
         float4 p = mine;              // lanes 0..4 of a later chunk keep the carried winner
         uint32_t key = lane >= first_new ? INF : d2bits;
         if (fresh) {
-            p = __ldg(m.pool + addr);
+            p = (STAGED && staged) ? stage[ii] : __ldg(m.pool + addr);
             // distance2 (ivox3d_node.hpp:13-15): (map point - query).squaredNorm() in fp32
             const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -417,6 +473,9 @@ __device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, f
         else if (lane < 5) { mine = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); d2bits = INF; }
     }
     return found;
+}
+__device__ __forceinline__ int knn5_warp(const MapView& m, float qx, float qy, float qz, int lane, float4& mine, uint32_t& d2bits) {
+    return knn5_warp_t<false>(m, qx, qy, qz, lane, mine, d2bits, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ 8 lanes per query, balanced through shared memory ("G8P")
@@ -646,7 +705,7 @@ struct Map {
     int knn_mode() const {
         static const char* env = getenv("B200_KNN_MODE");
         if (env) return atoi(env);
-        return 7;  // 7 = warp per query (knn5_warp); 8 = balanced 8-lanes-per-query body (knn5_g8p); 0 / 1 / 4 / 5 = the round-1 walks (A/B timing)
+        return 7;  // 7 = warp per query (knn5_warp); 9 = the same with TMA-staged candidates (knn5_warp_t<true>); 8 = balanced 8-lanes-per-query body (knn5_g8p); 0 / 1 / 4 / 5 = the round-1 walks (A/B timing)
     }
     int knn_mode_g8() const {  // density-driven choice among the 8-lanes-per-query walks (LOAM front end, A/B timing)
         static const char* env = getenv("B200_KNN_MODE");

@@ -30,4 +30,5 @@ for name, res, nearby in (("sparse", 0.2, 26), ("dense", 2.5, 18)):
     out[name] = dict(knn=hashlib.md5(i1.tobytes() + d1.tobytes() + c1.tobytes()).hexdigest(),
                      oracle_equal=bool(np.array_equal(i0, i1) and np.array_equal(d0, d1) and np.array_equal(c0, c1)),
                      x=hashlib.md5(kf.get_x().tobytes()).hexdigest(), rc=int(rc), mean_candidates=float(g.stencil_points(q)[0]) / len(q))
+out["tma_timeouts"] = api.knn_tma_timeouts()
 print(json.dumps(out))

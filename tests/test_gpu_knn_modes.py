@@ -31,8 +31,9 @@ def test_all_walk_variants_agree_bit_for_bit():
         assert ref[regime]["oracle_equal"], regime
         assert ref[regime]["rc"] == 0
     assert ref["sparse"]["mean_candidates"] < 40 < 64 < ref["dense"]["mean_candidates"]   # both sides of the flat-list capacity
-    for mode in (8, 7, 0, 1, 4, 5):
-        got = run_mode(mode)
+    for mode in (9, 8, 7, 0, 1, 4, 5):   # 9: candidate runs staged in shared memory by 1-D TMA bulk copies (the dense regime exceeds the
+        got = run_mode(mode)             #    staging area on most queries and takes the gather path)
+        assert got["tma_timeouts"] == 0, mode
         for regime in ("sparse", "dense"):
             assert got[regime]["oracle_equal"], (mode, regime)
             assert got[regime]["knn"] == ref[regime]["knn"], (mode, regime)
