@@ -62,6 +62,11 @@ int32_t b200_map_insert(b200_map* map, const float* xyz, int64_t n, int64_t stri
  * sqdist[n*5] float squared distances; count[n]. */
 int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist,
                       int32_t* count);
+/* the same search, also returning the neighbours themselves: neighbours_xyz = n x 5 x 3 floats (rows past count[i] are zero).
+ * This is what IVox::GetClosestPoint's closest_pt carries (ivox3d.h:79); a caller needs no host-side copy of the map, which
+ * would go stale as soon as MapIncremental inserts on the device. */
+int32_t b200_map_knn5_points(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist,
+                             int32_t* count, float* neighbours_xyz);
 /* IVox::NumValidGrids() (ivox3d.h:88) / NumPoints() (ivox3d.h:85) */
 int64_t b200_map_num_voxels(b200_map* map);
 int64_t b200_map_num_points(b200_map* map);

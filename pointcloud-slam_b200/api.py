@@ -99,6 +99,7 @@ def lib():
     L.b200_map_destroy.argtypes = [vp]
     L.b200_map_insert.argtypes = [vp, vp, i64, i64]
     L.b200_map_knn5.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    L.b200_map_knn5_points.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
     L.b200_map_num_voxels.restype = i64
     L.b200_map_num_voxels.argtypes = [vp]
     L.b200_map_num_points.restype = i64
@@ -287,6 +288,17 @@ class IVox:
         cnt = np.empty(n, np.int32)
         _check(lib().b200_map_knn5(self.h, _p(q), n, q.strides[0], _p(idx), _p(d2), _p(cnt)))
         return idx, d2, cnt
+
+    def GetClosestPointsXYZ(self, points):
+        """b200_map_knn5_points: like GetClosestPoint, plus the neighbours' coordinates [n, 5, 3] straight from the device map."""
+        q = _cloud(points)
+        n = q.shape[0]
+        idx = np.empty((n, 5), np.int32)
+        d2 = np.empty((n, 5), np.float32)
+        cnt = np.empty(n, np.int32)
+        nb = np.zeros((n, 5, 3), np.float32)
+        _check(lib().b200_map_knn5_points(self.h, _p(q), n, q.strides[0], _p(idx), _p(d2), _p(cnt), _p(nb)))
+        return idx, d2, cnt, nb
 
     def stencil_points(self, points):
         """(sum of map points, occupied cells) over the stencils of the queries — roofline bookkeeping."""

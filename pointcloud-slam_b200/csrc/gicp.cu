@@ -15,17 +15,22 @@
 //                   moved source point, distance gate, Mahalanobis matrix (R C1 R^T + C2)^-1 in fp64 -> ONE 64-byte record
 //                   per source point {target xyz, matched flag, float 3x3}.
 // k_g_bfgs          estimateRigidTransformationBFGS + the cost functor (:188-368) + the convergence test (:483-506) in ONE
-//                   block: every thread runs the scalar BFGS / line-search logic of gicp_math.cuh on identical reduced
-//                   sums, a functor evaluation is a block-wide reduction over the correspondence records (L2 resident), so
-//                   an outer iteration needs no host round trip and the host only polls a 200-byte control block.
+//                   thread-block cluster of 8 CTAs: every thread runs the scalar BFGS / line-search logic of gicp_math.cuh on
+//                   identical reduced sums; a functor evaluation is a reduction over the correspondence records (L2
+//                   resident) split over the cluster, combined through distributed shared memory behind one hardware
+//                   cluster barrier, so an outer iteration needs no host round trip and the host only polls a 200-byte
+//                   control block.
 #include "common.cuh"
 #include "gicp_math.cuh"
 
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace b200 {
 namespace gicp {
@@ -363,19 +368,31 @@ __global__ void __launch_bounds__(256) k_g_correspond(IndexView ix, const float4
     if (lane == 0) corr[i] = c;
 }
 
-// ------------------------------------------------------------------ the optimiser block
-struct BlockEval {  // the cost functor as a block-wide collective; every thread gets the same sums
+// ------------------------------------------------------------------ the optimiser cluster
+// One thread-block cluster of kCluster CTAs (one per SM) runs the whole BFGS of a pass.  Every thread of every CTA executes
+// the same scalar control flow on the same reduced sums; a functor evaluation is: each CTA adds the terms of its share of the
+// correspondence records (strided over the cluster), reduces them to kAcc partial sums in its own shared memory, the cluster
+// barrier publishes them, and every CTA adds the kCluster partials in rank order through distributed shared memory - so all
+// CTAs hold bit-identical totals and take the same branches.  The partials are double-buffered: one hardware cluster barrier
+// per evaluation is enough (a CTA can run at most one evaluation ahead of the slowest reader).
+constexpr int kCluster = 8;  // portable cluster size
+struct ClusterEval {
     const float4* out;
     const Corr* corr;
     int n, m;
-    double (*sh)[kAcc];  // [warps + 1][kAcc] shared scratch
+    double (*sh)[kAcc];    // [warps][kAcc] block scratch
+    double (*part)[kAcc];  // [2][kAcc] this CTA's partial sums, read by the whole cluster
+    double* tot_sh;        // [kAcc]
+    int phase;
     __device__ void sums(const double* x, double* tot) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned rank = cluster.block_rank(), nblk = cluster.num_blocks();
         float T[12];
         apply_state(x, T);
         double acc[kAcc];
 #pragma unroll
         for (int a = 0; a < kAcc; ++a) acc[a] = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        for (int i = rank * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
             const float4* rec = reinterpret_cast<const float4*>(corr + i);
             const float4 r0 = rec[0];
             if (__float_as_int(r0.w) < 0) continue;
@@ -395,12 +412,19 @@ struct BlockEval {  // the cost functor as a block-wide collective; every thread
         if (threadIdx.x < kAcc) {
             double v = 0.0;
             for (int w = 0; w < nw; ++w) v += sh[w][threadIdx.x];
-            sh[nw][threadIdx.x] = v;
+            part[phase][threadIdx.x] = v;
+        }
+        cluster.sync();  // every CTA's partials of this evaluation are visible cluster-wide
+        if (threadIdx.x < kAcc) {
+            double v = 0.0;
+            for (unsigned r = 0; r < nblk; ++r) v += cluster.map_shared_rank(&part[phase][0], r)[threadIdx.x];
+            tot_sh[threadIdx.x] = v;
         }
         __syncthreads();
 #pragma unroll
-        for (int a = 0; a < kAcc; ++a) tot[a] = sh[nw][a];
-        __syncthreads();  // the scratch may be rewritten by the next evaluation
+        for (int a = 0; a < kAcc; ++a) tot[a] = tot_sh[a];
+        __syncthreads();  // tot_sh / sh may be rewritten by the next evaluation
+        phase ^= 1;
     }
     __device__ double f(const double* x) {
         double tot[kAcc];
@@ -420,46 +444,60 @@ struct BlockEval {  // the cost functor as a block-wide collective; every thread
     }
 };
 
-__device__ int block_count_matches(const Corr* corr, int n, int* sh_i) {
+// matched correspondences, counted by the whole cluster; two barriers: publish, and nobody leaves while its count is being read
+__device__ int cluster_count_matches(const Corr* corr, int n, int* sh_i, int* cnt_part) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), nblk = cluster.num_blocks();
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += corr[i].tgt >= 0 ? 1 : 0;
+    for (int i = rank * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) c += corr[i].tgt >= 0 ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (lane == 0) sh_i[warp] = c;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < nw; ++w) t += sh_i[w];
+        *cnt_part = t;
+    }
+    cluster.sync();
     int tot = 0;
-    for (int w = 0; w < nw; ++w) tot += sh_i[w];
-    __syncthreads();
+    for (unsigned r = 0; r < nblk; ++r) tot += *cluster.map_shared_rank(cnt_part, r);
+    cluster.sync();
     return tot;
 }
 
-__global__ void __launch_bounds__(kBfgsThreads) k_g_bfgs(const float4* __restrict__ out, const Corr* __restrict__ corr, int n, GCtl* ctl) {
-    __shared__ double sh[kBfgsThreads / 32 + 1][kAcc];
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kBfgsThreads) k_g_bfgs(const float4* __restrict__ out, const Corr* __restrict__ corr, int n, GCtl* ctl) {
+    __shared__ double sh[kBfgsThreads / 32][kAcc];
+    __shared__ double part[2][kAcc];
+    __shared__ double tot_sh[kAcc];
     __shared__ int sh_i[kBfgsThreads / 32];
-    if (ctl->converged | ctl->failed) return;
-    const int m = block_count_matches(corr, n, sh_i);
+    __shared__ int cnt_part;
+    if (ctl->converged | ctl->failed) return;  // the same for every CTA of the cluster: nobody is left waiting at a barrier
+    cg::cluster_group cluster = cg::this_cluster();
+    const bool writer = cluster.block_rank() == 0 && threadIdx.x == 0;
+    const int m = cluster_count_matches(corr, n, sh_i, &cnt_part);
     float T[12];
 #pragma unroll
     for (int a = 0; a < 12; ++a) T[a] = ctl->T[a];
-    __syncthreads();  // every thread has read transformation_ before thread 0 rewrites it
-    if (m < 4) {      // NotEnoughPointsException -> the loop breaks, converged_ stays false (:206-211, 496-500)
-        if (threadIdx.x == 0) {
+    const int max_inner = ctl->max_inner_iterations;
+    cluster.sync();  // every thread of the cluster has read transformation_ before the writer replaces it
+    if (m < 4) {     // NotEnoughPointsException -> the loop breaks, converged_ stays false (:206-211, 496-500)
+        if (writer) {
             for (int a = 0; a < 12; ++a) ctl->prev[a] = T[a];
             ctl->last_m = m;
             ctl->failed = 1;
         }
         return;
     }
-    BlockEval ev{out, corr, n, m, sh};
+    ClusterEval ev{out, corr, n, m, sh, part, tot_sh, 0};
     double x[6];
     state_from_transform(T, x);
     int inner = 0, calls[3];
-    const int max_inner = ctl->max_inner_iterations;
     const int result = minimize_rigid(ev, x, max_inner, &inner, calls);
     const bool ok = result == kNoProgress || result == kSuccess || inner == max_inner;
     float Tn[12];
     apply_state(x, Tn);  // transformation_matrix.setIdentity(); applyState(transformation_matrix, x)
-    if (threadIdx.x == 0) {
+    if (writer) {
         for (int a = 0; a < 12; ++a) ctl->prev[a] = T[a];  // previous_transformation_ = transformation_ (:475)
         ctl->last_m = m;
         ctl->last_inner = inner;
@@ -482,25 +520,31 @@ __global__ void __launch_bounds__(kBfgsThreads) k_g_bfgs(const float4* __restric
             }
         }
     }
+    cluster.sync();  // no CTA exits while a peer may still read its partial sums
 }
 
 // parity probe: the functor at x on the current correspondences -> {operator(), fdf's f, gradient[6], m}
-__global__ void __launch_bounds__(kBfgsThreads) k_g_cost(const float4* __restrict__ out, const Corr* __restrict__ corr, int n, const double* __restrict__ x6,
-                                                         double* __restrict__ res) {
-    __shared__ double sh[kBfgsThreads / 32 + 1][kAcc];
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kBfgsThreads) k_g_cost(const float4* __restrict__ out, const Corr* __restrict__ corr, int n,
+                                                                                          const double* __restrict__ x6, double* __restrict__ res) {
+    __shared__ double sh[kBfgsThreads / 32][kAcc];
+    __shared__ double part[2][kAcc];
+    __shared__ double tot_sh[kAcc];
     __shared__ int sh_i[kBfgsThreads / 32];
-    const int m = block_count_matches(corr, n, sh_i);
-    BlockEval ev{out, corr, n, m, sh};
+    __shared__ int cnt_part;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int m = cluster_count_matches(corr, n, sh_i, &cnt_part);
+    ClusterEval ev{out, corr, n, m, sh, part, tot_sh, 0};
     double x[6], g[6], f1;
     for (int a = 0; a < 6; ++a) x[a] = x6[a];
     const double f0 = ev.f(x);
     ev.fdf(x, f1, g);
-    if (threadIdx.x == 0) {
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
         res[0] = f0;
         res[1] = f1;
         for (int a = 0; a < 6; ++a) res[2 + a] = g[a];
         res[8] = (double)m;
     }
+    cluster.sync();
 }
 
 // getFitnessScore: squared distance of every moved source point to its exact nearest target point
@@ -824,7 +868,7 @@ struct Gicp {
         for (;;) {
             for (int a = 0; a < ahead; ++a) {
                 launch_correspond();
-                k_g_bfgs<<<1, kBfgsThreads, 0, stream>>>(d_out.p, d_corr.p, (int)n_src, d_ctl.p);
+                k_g_bfgs<<<kCluster, kBfgsThreads, 0, stream>>>(d_out.p, d_corr.p, (int)n_src, d_ctl.p);
                 LAUNCH_COUNT(1);
                 ++enq;
             }
@@ -906,7 +950,7 @@ struct Gicp {
         CUDA_TRY(cudaStreamSynchronize(stream));
         memcpy(h_d.p, x6, 6 * sizeof(double));
         CUDA_TRY(cudaMemcpyAsync(d_scratch.p, h_d.p, 6 * sizeof(double), cudaMemcpyHostToDevice, stream));
-        k_g_cost<<<1, kBfgsThreads, 0, stream>>>(d_out.p, d_corr.p, (int)n_src, d_scratch.p, d_scratch.p + 8);
+        k_g_cost<<<kCluster, kBfgsThreads, 0, stream>>>(d_out.p, d_corr.p, (int)n_src, d_scratch.p, d_scratch.p + 8);
         LAUNCH_COUNT(1);
         CUDA_TRY(cudaMemcpyAsync(h_d.p + 8, d_scratch.p + 8, 9 * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));

@@ -431,6 +431,23 @@ __global__ void __launch_bounds__(256) k_knn5_w(MapView m, const float4* __restr
     if (lane == 0) cnt[qi] = c;
 }
 
+// the same search, also returning the neighbours themselves (x, y, z, ordinal): b200_map_knn5_points
+__global__ void __launch_bounds__(256) k_knn5_wx(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                                 float* __restrict__ d2, int32_t* __restrict__ cnt, float4* __restrict__ nb) {
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi >= n) return;
+    const float4 p = __ldg(q + qi);
+    float4 mine;
+    uint32_t key;
+    const int c = knn5_warp(m, p.x, p.y, p.z, lane, mine, key);
+    if (lane < 5) {
+        idx[qi * 5 + lane] = __float_as_int(mine.w);
+        d2[qi * 5 + lane] = (key == 0xffffffffu) ? 0.0f : __uint_as_float(key);
+        nb[(size_t)qi * 5 + lane] = mine;
+    }
+    if (lane == 0) cnt[qi] = c;
+}
+
 // warp-per-query with TMA staging (knn5_warp_t<true>): every warp owns kStageCap float4 of shared memory and one mbarrier
 __global__ void __launch_bounds__(256) k_knn5_t(MapView m, const float4* __restrict__ q, int n, int32_t* __restrict__ idx,
                                                 float* __restrict__ d2, int32_t* __restrict__ cnt) {
@@ -540,7 +557,7 @@ void Map::destroy() {
     v_in.release(); v_out.release(); run_cnt.release(); run_off.release(); run_dst.release(); run_reloc.release();
     d_nruns.release(); cub_tmp.release(); h_stage.release(); h_ctr_pin.release();
     lru_in.release(); lru_out.release(); victims_dev.release(); h_runs.release(); h_lru.release(); h_small.release();
-    q_idx.release(); q_cnt.release(); q_d2.release();
+    q_idx.release(); q_cnt.release(); q_d2.release(); q_nb.release();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -552,6 +569,10 @@ int32_t Map::grow_pool(uint64_t min_cap) {
     uint64_t live = h_ctr.live_points;
     uint64_t ncap = 4 * live + 4 * min_cap + (1u << 20);
     if (ncap < pool_cap) ncap = pool_cap;
+    if (ncap > (uint64_t)INT32_MAX) {  // voxel runs address the pool with 32-bit offsets (MapEntry::start)
+        ncap = (uint64_t)INT32_MAX;
+        if (live + 2 * (live + min_cap) > ncap) B200_FAIL(B200_ERR_NOMEM, "point pool would exceed 2^31 entries");
+    }
     float4* np = nullptr;
     CUDA_TRY(cudaMalloc(&np, ncap * sizeof(float4)));
     CUDA_TRY(cudaMemsetAsync(&d_ctr->pool_top, 0, sizeof(unsigned long long), stream));
@@ -668,6 +689,9 @@ int32_t Map::evict_for_batch(int64_t n) {
 int32_t Map::insert_device(const float4* d_pts, int64_t n, const int32_t* d_count, const int32_t* h_count) {
     if (n == 0) return B200_OK;
     if (n > (int64_t)0x3fffffff) B200_FAIL(B200_ERR_ARG, "batch too large");
+    // insertion ordinals and LRU stamps are 32-bit on the device (pool.w, aux.y): refuse before they wrap (hours of continuous
+    // LIO at 200k points/s) instead of handing out negative ordinals; b200_map_clear / a fresh map restarts the count
+    if (next_ord + n > (int64_t)INT32_MAX) B200_FAIL(B200_ERR_RANGE, "insertion ordinals exhausted (2^31 points inserted): rebuild the map");
     CUDA_SET_DEVICE(device);
     // worst case for this batch: every touched voxel relocates and doubles -> <= 2*(live + n) new slots
     if (h_ctr.pool_top + 2 * (h_ctr.live_points + (uint64_t)n) > pool_cap) {
@@ -768,11 +792,11 @@ int32_t Map::insert_host(const float* xyz, int64_t n, int64_t stride) {
     return insert_device(in_pts.p, n);
 }
 
-int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt) {
+int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt, float* nb_xyz) {
     if (n == 0) return B200_OK;
     if (n < 0 || !xyz || !idx || !d2 || !cnt || stride < 12) B200_FAIL(B200_ERR_ARG, "bad query buffer");
     CUDA_SET_DEVICE(device);
-    CUDA_TRY(h_stage.reserve(n));
+    CUDA_TRY(h_stage.reserve(nb_xyz ? n * 5 : n));  // queries in, and (when asked for) 5 neighbour records per query out
     CUDA_TRY(in_pts.reserve(n));
     CUDA_TRY(q_idx.reserve(n * 5)); CUDA_TRY(q_d2.reserve(n * 5)); CUDA_TRY(q_cnt.reserve(n));
     pack_xyz_float4(xyz, n, stride, h_stage.p);
@@ -782,7 +806,10 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     CUDA_TRY(cudaEventRecord(ev0, stream));
     {
         int mode = knn_mode();
-        if (mode == 8) {  // 8 lanes per query, candidates balanced through shared memory
+        if (nb_xyz) {  // neighbours' coordinates wanted as well: the warp-per-query body with one more store
+            CUDA_TRY(q_nb.reserve(n * 5));
+            k_knn5_wx<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p, q_nb.p);
+        } else if (mode == 8) {  // 8 lanes per query, candidates balanced through shared memory
             k_knn5_p<<<(unsigned)((n * 8 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
         } else if (mode == 9) {  // one warp per query, runs staged in shared memory by 1-D TMA bulk copies
             k_knn5_t<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(view(), in_pts.p, (int)n, q_idx.p, q_d2.p, q_cnt.p);
@@ -803,7 +830,17 @@ int32_t Map::knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx
     CUDA_TRY(cudaMemcpyAsync(idx, q_idx.p, n * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(d2, q_d2.p, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(cnt, q_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (nb_xyz) {
+        // the H2D copy of the queries that used the stage completes in stream order before this copy starts
+        CUDA_TRY(cudaMemcpyAsync(h_stage.p, q_nb.p, n * 5 * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
+    if (nb_xyz)
+        for (int64_t i = 0; i < n * 5; ++i) {
+            nb_xyz[i * 3] = h_stage.p[i].x;
+            nb_xyz[i * 3 + 1] = h_stage.p[i].y;
+            nb_xyz[i * 3 + 2] = h_stage.p[i].z;
+        }
     cudaEventElapsedTime(&last_knn_ms, ev0, ev1);
     return B200_OK;
 }
@@ -845,7 +882,12 @@ int32_t b200_map_insert(b200_map* map, const float* xyz, int64_t n, int64_t stri
 }
 int32_t b200_map_knn5(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist, int32_t* count) {
     if (!map) B200_FAIL(B200_ERR_ARG, "null map");
-    return map->m.knn5_host(xyz_world, n, stride_bytes, idx, sqdist, count);
+    return map->m.knn5_host(xyz_world, n, stride_bytes, idx, sqdist, count, nullptr);
+}
+int32_t b200_map_knn5_points(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int32_t* idx, float* sqdist, int32_t* count,
+                             float* neighbours_xyz) {
+    if (!map || !neighbours_xyz) B200_FAIL(B200_ERR_ARG, "null argument");
+    return map->m.knn5_host(xyz_world, n, stride_bytes, idx, sqdist, count, neighbours_xyz);
 }
 /* bench/roofline helper: total map points and occupied cells in the stencils of n queries */
 int32_t b200_map_stencil_points(b200_map* map, const float* xyz_world, int64_t n, int64_t stride_bytes, int64_t* points, int64_t* cells) {

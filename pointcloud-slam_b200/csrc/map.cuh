@@ -696,6 +696,7 @@ struct Map {
     // knn scratch
     DevBuf<int32_t> q_idx, q_cnt;
     DevBuf<float> q_d2;
+    DevBuf<float4> q_nb;
 
     // Candidate-walk variant of the search kernels, picked per launch from the map's density: lane-owned cells (0) win while
     // every voxel holds a few points (0.2 m voxels: 27 vs 47 us per 20k queries at 3 points/voxel), the cooperative walk (1)
@@ -726,7 +727,7 @@ struct Map {
     // a count that is still being produced on the stream; h_count is its pinned host copy, valid after the call
     int32_t insert_device(const float4* d_pts, int64_t n, const int32_t* d_count = nullptr, const int32_t* h_count = nullptr);
     int32_t insert_host(const float* xyz, int64_t n, int64_t stride);
-    int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt);
+    int32_t knn5_host(const float* xyz, int64_t n, int64_t stride, int32_t* idx, float* d2, int32_t* cnt, float* nb_xyz = nullptr);
     int32_t grow_pool(uint64_t min_cap);
     int32_t evict_for_batch(int64_t n);
     int32_t rehash();

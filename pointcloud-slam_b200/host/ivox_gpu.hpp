@@ -56,7 +56,6 @@ class IVox {
         if (points_to_add.empty()) return;
         check(b200_map_insert(map_, reinterpret_cast<const float*>(points_to_add.data()), (int64_t)points_to_add.size(), sizeof(PointType)),
               "b200_map_insert");
-        cache_.insert(cache_.end(), points_to_add.begin(), points_to_add.end());  // ordinals -> full records for GetClosestPoint
     }
 
     /// IVox::GetClosestPoint(pt, closest_pt, max_num, max_range) (ivox3d.h:79).  max_num must be 5 (NUM_MATCH_POINTS) and
@@ -64,11 +63,15 @@ class IVox {
     bool GetClosestPoint(const PointType& pt, PointVector& closest_pt, int max_num = 5, double max_range = 5.0) {
         (void)max_num; (void)max_range;
         int32_t idx[5], cnt = 0;
-        float d2[5];
-        check(b200_map_knn5(map_, reinterpret_cast<const float*>(&pt), 1, sizeof(PointType), idx, d2, &cnt), "b200_map_knn5");
+        float d2[5], nb[15];
+        check(b200_map_knn5_points(map_, reinterpret_cast<const float*>(&pt), 1, sizeof(PointType), idx, d2, &cnt, nb), "b200_map_knn5_points");
         if (cnt == 0) return false;  // the reference returns before touching closest_pt (ivox3d.h:151-153)
         closest_pt.clear();
-        for (int k = 0; k < cnt; ++k) closest_pt.push_back(cache_[(std::size_t)idx[k]]);
+        for (int k = 0; k < cnt; ++k) {  // coordinates come from the device map itself (it also grows through MapIncremental);
+            PointType p{};               // the other fields of the record are not kept on the device and stay zero
+            p.x = nb[3 * k]; p.y = nb[3 * k + 1]; p.z = nb[3 * k + 2];
+            closest_pt.push_back(p);
+        }
         return true;
     }
 
@@ -83,12 +86,10 @@ class IVox {
     std::size_t NumValidGrids() const { return (std::size_t)b200_map_num_voxels(map_); }  // ivox3d.h:88
     std::size_t NumPoints() const { return (std::size_t)b200_map_num_points(map_); }
     b200_map* handle() const { return map_; }
-    const PointVector& points() const { return cache_; }
 
    private:
     Options options_;
     b200_map* map_ = nullptr;
-    PointVector cache_;
 };
 
 }  // namespace b200host

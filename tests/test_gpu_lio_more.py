@@ -95,3 +95,33 @@ def test_config1_full_size_against_the_oracle(oracle, api, synth):
     assert st.n_eff[0] > 0.9 * len(c["scan"])
     err = kf.get_x()[:3] - c["x_true"][:3]
     assert np.linalg.norm(err) < 0.02
+
+
+def test_neighbour_coordinates_come_from_the_device_map(oracle, api, synth, small_cfg):
+    """b200_map_knn5_points returns the neighbours' coordinates from the device map itself, so a caller needs no host copy of the
+    map - which would go stale once MapIncremental has inserted on the device (the host adaptor's old ordinal -> record cache)."""
+    mp = small_cfg["map"]
+    g = api.IVox(resolution=0.5, nearby=18)
+    g.AddPoints(mp)
+    q = world_scan(synth, small_cfg)
+    i0, d0, c0 = g.GetClosestPoint(q)
+    i1, d1, c1, nb = g.GetClosestPointsXYZ(q)
+    np.testing.assert_array_equal(i1, i0)
+    np.testing.assert_array_equal(d1, d0)
+    np.testing.assert_array_equal(c1, c0)
+    valid = i0 >= 0
+    assert valid.sum() > 4 * len(q)
+    np.testing.assert_array_equal(nb[valid], mp[i0[valid]][:, :3])
+    assert not nb[~valid].any()
+    # points added on the device by MapIncremental get ordinals past the host's view of the map; their coordinates still come back
+    kf = api.Esekf(g)
+    kf.change_x(small_cfg["x_prop"])
+    kf.change_P(small_cfg["P"])
+    assert kf.update_iterated_dyn_share_modified(small_cfg["scan"]) == 0
+    n_add, _ = kf.MapIncremental()
+    i2, d2, c2, nb2 = g.GetClosestPointsXYZ(q)
+    fresh = i2 >= len(mp)
+    assert n_add > 0 and fresh.any()
+    dd = ((nb2 - q[:, None, :3]) ** 2).sum(-1)
+    v2 = i2 >= 0
+    np.testing.assert_allclose(dd[v2], d2[v2], rtol=1e-5, atol=1e-9)
