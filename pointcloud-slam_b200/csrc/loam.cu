@@ -463,6 +463,9 @@ int32_t b200_loam_set_map(b200_loam* h, const float* corner_xyz, int64_t n_corne
                           int64_t stride_surf) {
     if (!h || n_corner < 0 || n_surf < 0 || (n_corner && (!corner_xyz || stride_corner < 12)) || (n_surf && (!surf_xyz || stride_surf < 12)))
         B200_FAIL(B200_ERR_ARG, "bad argument");
+    // a feature map larger than the handle was created for would make the voxel table evict (LRU) map points silently
+    if ((uint64_t)n_corner > h->corner.prm.max_points || (uint64_t)n_surf > h->surf.prm.max_points)
+        B200_FAIL(B200_ERR_CAPACITY, "feature map larger than max_map_points of b200_loam_create");
     CUDA_SET_DEVICE(h->device);
     int32_t rc = h->corner.clear();
     if (rc == B200_OK) rc = h->surf.clear();
