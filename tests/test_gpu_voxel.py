@@ -92,7 +92,7 @@ def test_full_map_builder_matches_oracle(oracle, api, synth):
     c2, n2 = b2.extract()
     np.testing.assert_array_equal(n2, n1)
     # sums are fp32 atomics: offsets from the voxel corner (< one leaf) for x, y, z, the plain value for the intensity (0..100 here)
-    np.testing.assert_allclose(c2[:, :3], c1[:, :3], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c2[:, :3], c1[:, :3], rtol=0, atol=4e-6)   # one float32 ulp of a 20 m coordinate is 1.9e-6
     np.testing.assert_allclose(c2[:, 3], c1[:, 3], rtol=0, atol=1e-3)
 
 
@@ -117,7 +117,7 @@ def test_full_map_batched_device_keyframes_match_one_by_one(oracle, api, synth):
     assert b2.num_voxels() == len(c0)
     c1, n1 = b2.extract()
     np.testing.assert_array_equal(n1, n0)
-    np.testing.assert_allclose(c1[:, :3], c0[:, :3], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(c1[:, :3], c0[:, :3], rtol=0, atol=4e-6)   # the centroid's float32 rounding may flip by one ulp (1.9e-6 at 20 m)
     np.testing.assert_allclose(c1[:, 3], c0[:, 3], rtol=0, atol=1e-3)   # intensity: fp32 sum, order of the atomics
 
 
