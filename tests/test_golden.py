@@ -84,3 +84,31 @@ def test_cuda_path_reproduces_golden(api, oracle, gold):
     c, n = vg.filter()
     np.testing.assert_array_equal(c, gold["vg_centroids"])
     np.testing.assert_array_equal(n, gold["vg_counts"])
+
+
+# ------------------------------------------------------------------ GICP (tests/golden/r02_gicp_small.npz, `python tools/make_golden.py gicp`)
+@pytest.fixture(scope="module")
+def gold_gicp():
+    return np.load(os.path.join(ROOT, "tests", "golden", "r02_gicp_small.npz"))
+
+
+def test_oracle_reproduces_gicp_golden(oracle, gold_gicp):
+    gd = gold_gicp
+    g = oracle.OracleGicp()
+    g.set_target(gd["map"])
+    g.set_source(gd["scan"])
+    np.testing.assert_array_equal(g.covariances("source"), gd["cov_src"])
+    np.testing.assert_array_equal(g.covariances("target")[::16], gd["cov_tgt_every_16"])
+    knn, _ = oracle.exact_knn(gd["scan"], gd["scan"], 20)
+    np.testing.assert_array_equal(knn, gd["knn_src"])
+    m, idx, maha, d2 = g.correspondences(np.eye(4), gd["guess"])
+    assert m == int(gd["corr_m"])
+    np.testing.assert_array_equal(idx, gd["corr_idx"])
+    np.testing.assert_array_equal(maha, gd["corr_maha"])
+    f_op, f_fdf, g_df, g_fdf = g.cost(gd["cost_x"])
+    assert f_op == float(gd["cost_f_op"]) and f_fdf == float(gd["cost_f_fdf"])
+    np.testing.assert_array_equal(g_fdf, gd["cost_g"])
+    rc, fin, r = g.align(gd["guess"])
+    assert rc == int(gd["align_rc"]) and r.iterations == int(gd["align_iterations"]) > 1 and r.inner_total == int(gd["align_inner_total"])
+    np.testing.assert_array_equal([r.n_f, r.n_df, r.n_fdf], gd["align_calls"])
+    np.testing.assert_allclose(fin, gd["align_final"], rtol=0, atol=1e-7)

@@ -188,3 +188,30 @@ def test_full_size_pose_recovery(api, synth):
     assert np.abs(fin[:3, 3] - T[:3, 3]).max() < 0.01 and np.abs(fin[:3, :3] - T[:3, :3]).max() < 1e-3
     assert g.result.last_m == len(scan)
     g.close()
+
+
+def test_cuda_gicp_reproduces_golden(api):
+    """tests/golden/r02_gicp_small.npz (oracle outputs frozen by tools/make_golden.py gicp): every stage of the device path."""
+    import os
+    from conftest import ROOT
+    gd = np.load(os.path.join(ROOT, "tests", "golden", "r02_gicp_small.npz"))
+    g = api.GeneralizedIterativeClosestPoint()
+    g.setInputTarget(gd["map"])
+    g.setInputSource(gd["scan"])
+    cov, knn = g.covariances("source", with_neighbours=True)
+    np.testing.assert_array_equal(knn, gd["knn_src"])
+    np.testing.assert_allclose(cov, gd["cov_src"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(g.covariances("target")[::16], gd["cov_tgt_every_16"], rtol=0, atol=1e-12)
+    m, idx, maha, d2 = g.correspondences(np.eye(4), gd["guess"])
+    assert m == int(gd["corr_m"])
+    np.testing.assert_array_equal(idx, gd["corr_idx"])
+    hit = idx >= 0
+    np.testing.assert_array_equal(maha[hit], gd["corr_maha"][hit])
+    np.testing.assert_array_equal(d2[hit], gd["corr_d2"][hit])
+    f_op, f_fdf, gr, mm = g.cost(gd["cost_x"])
+    assert mm == m and abs(f_op - float(gd["cost_f_op"])) <= 1e-9 * abs(float(gd["cost_f_op"])) and abs(f_fdf - float(gd["cost_f_fdf"])) <= 1e-9 * abs(float(gd["cost_f_fdf"]))
+    np.testing.assert_allclose(gr, gd["cost_g"], rtol=0, atol=1e-9 * np.abs(gd["cost_g"]).max())
+    rc = g.align(gd["guess"])
+    assert rc == int(gd["align_rc"]) and g.result.iterations == int(gd["align_iterations"]) and g.result.last_m == int(gd["align_last_m"])
+    assert np.abs(g.getFinalTransformation() - gd["align_final"]).max() <= 1e-4
+    g.close()

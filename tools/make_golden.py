@@ -2,7 +2,8 @@
 
 The reference ships no vectors for this path and cannot be built here, so these are not pins
 of the reference: they freeze the oracle (and, through the GPU tests, the CUDA path) against accidental drift.
-Regenerate with `python tools/make_golden.py` only when a deliberate change of the restated arithmetic is made."""
+Regenerate with `python tools/make_golden.py` only when a deliberate change of the restated arithmetic is made.
+`python tools/make_golden.py gicp` writes tests/golden/r02_gicp_small.npz (the GICP stages) the same way."""
 import os
 import sys
 
@@ -51,5 +52,33 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_gicp():
+    """tests/golden/r02_gicp_small.npz: the oracle's GICP outputs on a small seeded scene (drift pin, like r01_small.npz)."""
+    world = synth.make_world(synth.SEED, beams=True)
+    mp = synth.sample_map(40_000, synth.SEED + 1, world=world)
+    p_true = np.array([3.0, -2.0, 1.2, 0.0, 0.0, 0.6])
+    T = synth.pose_vec_to_matrix(p_true)
+    scan = np.ascontiguousarray(synth.raycast(T[:3, 3], T[:3, :3], synth.livox_dirs(3000, synth.SEED + 1), world, seed=synth.SEED + 1)[:2400])
+    guess = synth.pose_vec_to_matrix(p_true + np.array([0.15, -0.1, 0.05, 0.01, -0.01, 0.03])).astype(np.float32)
+    g = ob.OracleGicp()
+    g.set_target(mp)
+    g.set_source(scan)
+    cov_src, cov_tgt = g.covariances("source"), g.covariances("target")
+    knn_src, _ = ob.exact_knn(scan, scan, 20)
+    m, idx, maha, d2 = g.correspondences(np.eye(4), guess)
+    x = np.array([0.01, -0.02, 0.005, 0.002, -0.001, 0.003])
+    f_op, f_fdf, g_df, g_fdf = g.cost(x)
+    rc, fin, r = g.align(guess)
+    out = dict(map=mp, scan=scan, guess=guess, cov_src=cov_src, cov_tgt_every_16=cov_tgt[::16], knn_src=knn_src, corr_m=m, corr_idx=idx, corr_maha=maha,
+               corr_d2=d2, cost_x=x, cost_f_op=f_op, cost_f_fdf=f_fdf, cost_g=g_fdf, align_rc=rc, align_final=fin, align_iterations=r.iterations,
+               align_last_m=r.last_m, align_inner_total=r.inner_total, align_calls=np.array([r.n_f, r.n_df, r.n_fdf]))
+    path = os.path.join(ROOT, "tests", "golden", "r02_gicp_small.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes", "passes", r.iterations, "matches", r.last_m)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gicp":
+        main_gicp()
+    else:
+        main()
