@@ -6,7 +6,7 @@
  * (pointcloud-slam_b200/csrc) never does.
  *
  * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests
- * or fixtures for the iVox / IEKF / pclomp-NDT path and
+ * or fixtures for the iVox / IEKF / pclomp NDT / GICP path and
  * cannot be compiled here (no PCL / Boost / TBB; the vendored Eigen lacks
  * Eigen/Core).  The Eigen decompositions the path calls are
  * restated line by line from the vendored Eigen sources (smallmat.h).  The oracle

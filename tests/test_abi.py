@@ -38,8 +38,24 @@ def test_no_gpu_fails_loudly(api):
         api.IVox(resolution=0.5, nearby=18)
 
 
+@pytest.mark.skipif(have_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_fails_loudly_for_every_handle_type(api):
+    """NDT, GICP, the map builder and the LOAM estimator refuse to exist without a device as well."""
+    import numpy as np
+    pts = np.zeros((64, 3), np.float32)
+    for make in (lambda: api.NormalDistributionsTransform().setInputTarget(pts) or api.NormalDistributionsTransform()._handle(),
+                 lambda: api.GeneralizedIterativeClosestPoint()._handle(),
+                 lambda: api.FullMapBuilder(leaf=0.1, capacity_voxels=1000),
+                 lambda: api.ScanToMap(max_map_points=1000)):
+        with pytest.raises(api.B200Error):
+            make()
+
+
 def test_bad_arguments_are_rejected(api):
     lib = api.lib()
     assert lib.b200_map_create(None, 0, None) == -1  # B200_ERR_ARG
     assert lib.b200_map_insert(None, None, 0, 12) == -1
     assert b"null" in lib.b200_last_error()
+    assert lib.b200_gicp_create(None, 0, None) == -1
+    assert lib.b200_gicp_set_target(None, None, 0, 12) == -1
+    assert lib.b200_gicp_align(None, None, None, None) == -1
