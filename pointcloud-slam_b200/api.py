@@ -689,6 +689,42 @@ def shard_range(h_total: int, nranks: int, rank: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+# ---- host-side statement of the map builder's merge protocol (b200_mapbuild_merge, csrc/voxel.cu): used by the CPU tests that run
+# the N > 1 path over gloo; the product path is the CUDA + NCCL implementation, this is only its contract in numpy
+def voxel_key(cells) -> "np.ndarray":
+    """pack_key(cz, cy, cx) of csrc/common.cuh for an [n, 3] array of (cx, cy, cz) voxel cells (21-bit biased fields)."""
+    c = np.asarray(cells, dtype=np.int64) + (1 << 20)
+    return (c[:, 2].astype(np.uint64) << np.uint64(42)) | (c[:, 1].astype(np.uint64) << np.uint64(21)) | c[:, 0].astype(np.uint64)
+
+
+def voxel_owner(keys, nranks: int) -> "np.ndarray":
+    """owner_of(key, nranks) of csrc/voxel.cu: the rank that holds a voxel after the merge."""
+    k = np.asarray(keys, dtype=np.uint64) ^ np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xff51afd7ed558ccd)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xc4ceb9fe1a85ec53)
+        k ^= k >> np.uint64(33)
+    return (((k & np.uint64(0xFFFFFFFF)) >> np.uint64(8)) % np.uint64(nranks)).astype(np.int64)
+
+
+def mapbuild_merge_protocol_host(keys, counts, sums, nranks: int, rank: int, exchange):
+    """One rank's side of the merge: records (key, count, sums[4]) are routed to their owner and records of the same voxel are
+    added.  `exchange(list_of_per_destination_arrays)` returns the list of arrays received from every rank (an all-to-all).
+    Returns the (keys, counts, sums) this rank owns afterwards, sorted by key."""
+    owner = voxel_owner(keys, nranks)
+    rec = np.concatenate([np.asarray(keys, np.uint64).view(np.float64)[:, None], np.asarray(counts, np.float64)[:, None], np.asarray(sums, np.float64)], 1)
+    got = np.concatenate(exchange([rec[owner == r] for r in range(nranks)]), 0)
+    k = got[:, 0].copy().view(np.uint64)
+    uniq, inv = np.unique(k, return_inverse=True)
+    cnt = np.zeros(len(uniq))
+    sm = np.zeros((len(uniq), got.shape[1] - 2))
+    np.add.at(cnt, inv, got[:, 1])
+    np.add.at(sm, inv, got[:, 2:])
+    return uniq, cnt.astype(np.int64), sm
+
+
 def score_key(s: float) -> int:
     """Order-preserving map fp64 -> uint64 used by the allreduce-argmin (NaN -> 0, below every real score)."""
     import struct

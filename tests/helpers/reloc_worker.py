@@ -43,6 +43,56 @@ def main():
         full = o.score_batch(poses)
         res = dict(best=int(best), score=float(score), expect=int(np.argmax(full)), expect_score=float(full.max()), world=world,
                    slice=[b, e])
+        # construct_full_map over the ranks, protocol only (numpy + gloo): contiguous keyframe blocks, per-rank voxel sums, records
+        # routed to their owner (hash of the voxel key), owners add them up.  The union must be the oracle's single-process map.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_gpu_voxel import make_frames
+        frames, fposes = make_frames(synth, k=6, n=1500)
+        leaf = np.float32(0.1)
+        fb, fe = api.shard_range(len(frames), world, rank)
+        cells, pts = [], []
+        for f, p in zip(frames[fb:fe], fposes[fb:fe]):
+            # pose7 -> matrix with the builder's arithmetic: fp64 quaternion products, narrowed to an fp32 3x4
+            w, x, y, z = p[3], p[4], p[5], p[6]
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]).astype(np.float32)
+            t = p[:3].astype(np.float32)
+            q = np.stack([((R[r, 0] * f[:, 0] + R[r, 1] * f[:, 1]) + R[r, 2] * f[:, 2]) + t[r] for r in range(3)], 1).astype(np.float32)
+            cells.append(np.floor(q * (np.float32(1.0) / leaf)).astype(np.int64))
+            pts.append(np.concatenate([q, f[:, 3:4]], 1).astype(np.float64))
+        cells, pts = np.concatenate(cells), np.concatenate(pts)
+        keys = api.voxel_key(cells)
+        uk, inv = np.unique(keys, return_inverse=True)
+        cnt = np.bincount(inv, minlength=len(uk))
+        sums = np.zeros((len(uk), 4))
+        np.add.at(sums, inv, pts)
+
+        def exchange(per_dest):
+            sizes = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([len(a) for a in per_dest], dtype=torch.int64))
+            out = []
+            for src in range(world):           # every rank broadcasts what it has for each destination; keep what is addressed to us
+                for dst in range(world):
+                    n = int(sizes[src][dst])
+                    buf = torch.from_numpy(np.ascontiguousarray(per_dest[dst])) if src == rank else torch.zeros((n, 6), dtype=torch.float64)
+                    dist.broadcast(buf, src=src)
+                    if dst == rank:
+                        out.append(buf.numpy().copy())
+            return out
+        ok_, cn_, sm_ = api.mapbuild_merge_protocol_host(uk, cnt, sums, world, rank, exchange)
+        owned = [None] * world
+        dist.all_gather_object(owned, (ok_, cn_, sm_))
+        if rank == 0:
+            c0, n0 = ob.full_map(frames, fposes, 0.1)
+            allk = np.concatenate([o[0] for o in owned])
+            alln = np.concatenate([o[1] for o in owned])
+            alls = np.concatenate([o[2] for o in owned])
+            order = np.argsort(allk)       # pack_key(cz, cy, cx): ascending key = the builder's (z, y, x) extraction order
+            cent = (alls[order] / alln[order][:, None]).astype(np.float32)
+            res.update(fullmap_disjoint=bool(len(np.unique(allk)) == len(allk)), fullmap_voxels=int(len(allk)), oracle_voxels=int(len(c0)),
+                       fullmap_counts_equal=bool(len(allk) == len(c0) and np.array_equal(alln[order], n0)),
+                       fullmap_max_centroid_diff=float(np.abs(cent - c0).max()) if len(allk) == len(c0) else None,
+                       fullmap_owner_rule=bool(all((api.voxel_owner(o[0], world) == r).all() for r, o in enumerate(owned))))
     else:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

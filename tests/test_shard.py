@@ -54,3 +54,6 @@ def test_two_rank_gloo_argmin(tmp_path):
     assert r["world"] == 2 and r["slice"] == [0, 38]
     assert r["best"] == r["expect"]
     assert r["score"] == r["expect_score"]
+    # the map builder's merge protocol over the same two ranks: disjoint ownership by the key hash, union == the oracle's map
+    assert r["fullmap_disjoint"] and r["fullmap_owner_rule"] and r["fullmap_voxels"] == r["oracle_voxels"] > 1000
+    assert r["fullmap_counts_equal"] and r["fullmap_max_centroid_diff"] <= 2e-5
