@@ -253,3 +253,26 @@ def test_product_bfgs_matches_oracle(oracle, harness):
             assert st == st_o and inner.value == inner_o
             np.testing.assert_array_equal(calls, calls_o)
             np.testing.assert_allclose(x, x_o, rtol=0, atol=1e-15)
+
+
+def test_product_svd3_against_numpy(harness):
+    """jacobi_svd3_u (the JacobiSVD<Matrix3d>(cov, ComputeFullU) of computeCovariances): U orthonormal, singular values descending
+    and equal to numpy's, A == U diag(sv) U^T for symmetric positive semi-definite input - full rank, rank 2 (a plane), rank 1 (a line)
+    and the zero matrix."""
+    rng = np.random.default_rng(21)
+    U, sv = np.zeros(9), np.zeros(3)
+    for case in range(300):
+        rank = (3, 3, 2, 1)[case % 4]
+        B = rng.normal(0, 1, (3, rank)) * rng.uniform(1e-3, 10.0)
+        A = np.ascontiguousarray(B @ B.T)
+        harness.hh_svd3_u(_p(A), _p(U), _p(sv))
+        Um = U.reshape(3, 3)
+        scale = max(np.abs(A).max(), 1e-300)
+        np.testing.assert_allclose(Um.T @ Um, np.eye(3), atol=1e-12)
+        assert sv[0] >= sv[1] >= sv[2] >= 0
+        np.testing.assert_allclose(sv, np.linalg.svd(A, compute_uv=False), atol=1e-12 * scale)
+        np.testing.assert_allclose(Um @ np.diag(sv) @ Um.T, A, atol=1e-12 * scale)
+    Z = np.zeros(9)
+    harness.hh_svd3_u(_p(Z), _p(U), _p(sv))
+    np.testing.assert_array_equal(U.reshape(3, 3), np.eye(3))
+    np.testing.assert_array_equal(sv, 0.0)
