@@ -27,6 +27,17 @@ def test_library_exports_every_declared_symbol(api):
     assert not missing, f"libb200reg.so does not export: {missing}"
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/b200reg.h must compile as C99 (no C++ in the signatures), which is what a cgo / JNI / ctypes
+    binding generator would consume."""
+    import subprocess
+    src = tmp_path / "c_abi_check.c"
+    src.write_text('#include "b200reg.h"\nint main(void) { b200_gicp_params g; b200_ndt_params n; (void)g; (void)n; return b200_version() == 0; }\n')
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+
+
 def test_version_string(api):
     assert b"sm_100a" in api.lib().b200_version()
 
